@@ -1,0 +1,204 @@
+// vt_scale.cu -- K2: libswscale-exact separable polyphase downscale.
+//
+// Arithmetic (8-bit in/out, the SWS_ACCURATE_RND|SWS_BITEXACT C path of libswscale 9.1.100):
+//   horizontal:  mid[r][x] = min( (sum_j src[r][hpos[x]+j] * hcoef[x][j]) >> 7, 32767 )      (14-bit coefs)
+//   vertical:    out[y][x] = clip_u8( (2^18 + sum_j mid[vpos[y]+j][x] * vcoef[y][j]) >> 19 ) (12-bit coefs)
+//   vertical with one tap (axis not scaled): out = clip_u8( (mid + 64) >> 7 )
+// The reference reaches this arithmetic through `ffmpeg -vf scale=-2:360`
+// (/root/reference/src/analyzer/content_analyzer.py:193-211).
+//
+// Two implementations:
+//   * generic  : hscale kernel -> int16 scratch -> vscale kernel.  Any ratio, any tap count.  Parity sweeps.
+//   * streaming: one pass, one warp per (frame, plane, 128-column strip, row chunk).  The warp's source tile
+//                is staged in shared memory by TMA (cp.async.bulk.tensor, completion on an mbarrier); each
+//                lane owns 4 output columns, runs the horizontal taps with dp2a (two 14-bit coefs x two
+//                pixels per instruction) and keeps the vertical window of 15-bit intermediates in a
+//                register ring, so intermediates never touch memory.  NV12 chroma is de-interleaved with
+//                PRMT on the way.  HBM traffic = source once + destination once.
+#include <cuda.h>
+
+#include <mutex>
+#include <vector>
+
+#include "vt_common.cuh"
+
+struct vt_scale_plan {
+    int sw, sh, dw, dh, flags;
+    int csw, csh, cdw, cdh;  // chroma plane sizes
+    // filter banks in device memory; index 0 = luma, 1 = chroma
+    int htaps[2], vtaps[2];
+    int16_t *hcoef[2];  // dw x htaps
+    int32_t *hpos[2];
+    int16_t *vcoef[2];  // dh x vtaps
+    int32_t *vpos[2];
+    int16_t *scratch;  // generic path: dw x sh int16
+    // host copies (streaming path work-list construction)
+    std::vector<int16_t> h_hcoef[2], h_vcoef[2];
+    std::vector<int32_t> h_hpos[2], h_vpos[2];
+    // streaming path tables (device): see build_stream_tables()
+    struct Stream {
+        bool ok = false;
+        int cpt = 0;          // output columns per lane (4, 2 or 1)
+        int hp = 0;           // dp2a pairs per output (ceil(htaps/2))
+        int nw = 0;           // 32-bit words each lane loads per row and column group
+        int tv = 0;           // vertical taps
+        int strip_cols = 0;   // output columns per warp item
+        int n_strips = 0;
+        int rows_out = 0;     // output rows per item
+        int n_chunks = 0;
+        int tile_w = 0;       // bytes per staged source row (multiple of 16, <= 256)
+        int tile_h = 0;       // staged source rows
+        int32_t *strip_x0 = nullptr;   // n_strips: first source byte of the tile (16 B aligned)
+        uint32_t *lane_tab = nullptr;  // per output column: packed coefs / offsets
+    } stream[2];
+};
+
+namespace vt {
+
+// ---- generic two-kernel path -----------------------------------------------------------------------------
+// channel_step = 1 for planar sources, 2 for the interleaved UV plane of NV12 (channel_off picks U or V).
+__global__ void __launch_bounds__(256)
+hscale_generic_kernel(const uint8_t *__restrict__ src, int src_pitch, int sh, int channel_step, int channel_off,
+                      int16_t *__restrict__ mid, int dw, const int16_t *__restrict__ coef,
+                      const int32_t *__restrict__ pos, int taps) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (x >= dw || r >= sh) return;
+    const uint8_t *s = src + (size_t)r * src_pitch + (size_t)pos[x] * channel_step + channel_off;
+    const int16_t *c = coef + (size_t)x * taps;
+    int v = 0;
+    for (int j = 0; j < taps; j++) v += (int)s[(size_t)j * channel_step] * (int)c[j];
+    v >>= 7;
+    mid[(size_t)r * dw + x] = (int16_t)min(v, 32767);
+}
+
+__global__ void __launch_bounds__(256)
+vscale_generic_kernel(const int16_t *__restrict__ mid, int dw, uint8_t *__restrict__ dst, int dst_pitch, int dh,
+                      const int16_t *__restrict__ coef, const int32_t *__restrict__ pos, int taps) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= dw || y >= dh) return;
+    int v;
+    if (taps == 1) {
+        v = (mid[(size_t)pos[y] * dw + x] + 64) >> 7;
+    } else {
+        v = 1 << 18;
+        const int16_t *c = coef + (size_t)y * taps;
+        const int16_t *m = mid + (size_t)pos[y] * dw + x;
+        for (int j = 0; j < taps; j++) v += (int)m[(size_t)j * dw] * (int)c[j];
+        v >>= 19;
+    }
+    dst[(size_t)y * dst_pitch + x] = (uint8_t)max(0, min(255, v));
+}
+
+int scale_plane_generic(const vt_scale_plan *p, int chroma, const uint8_t *src, int src_pitch, int channel_step,
+                        int channel_off, uint8_t *dst, int dst_pitch, cudaStream_t st) {
+    const int c = chroma ? 1 : 0;
+    const int sh = c ? p->csh : p->sh, dw = c ? p->cdw : p->dw, dh = c ? p->cdh : p->dh;
+    dim3 b(256), gh((dw + 255) / 256, sh), gv((dw + 255) / 256, dh);
+    hscale_generic_kernel<<<gh, b, 0, st>>>(src, src_pitch, sh, channel_step, channel_off, p->scratch, dw,
+                                            p->hcoef[c], p->hpos[c], p->htaps[c]);
+    VT_LAUNCHED("hscale_generic_kernel");
+    vscale_generic_kernel<<<gv, b, 0, st>>>(p->scratch, dw, dst, dst_pitch, dh, p->vcoef[c], p->vpos[c],
+                                            p->vtaps[c]);
+    VT_LAUNCHED("vscale_generic_kernel");
+    return VT_OK;
+}
+
+}  // namespace vt
+
+// ---- plan ----------------------------------------------------------------------------------------------------
+namespace {
+
+int upload(const void *h, size_t n, void **d) {
+    if (cudaMalloc(d, n ? n : 1) != cudaSuccess) return VT_ERR_NOMEM;
+    if (n && cudaMemcpy(*d, h, n, cudaMemcpyHostToDevice) != cudaSuccess) return VT_ERR_CUDA;
+    return VT_OK;
+}
+
+int make_bank(int src, int dst, int flags, int one, std::vector<int16_t> &coef, std::vector<int32_t> &pos, int *taps) {
+    int cap = vt_sws_max_taps(src, dst, flags);
+    if (cap < 0) return cap;
+    cap = cap < 4 ? 4 : cap;
+    coef.assign((size_t)dst * cap, 0);
+    pos.assign((size_t)dst, 0);
+    int rc = vt_sws_make_filter(src, dst, flags, one, coef.data(), pos.data(), taps);
+    if (rc) return rc;
+    coef.resize((size_t)dst * *taps);
+    return VT_OK;
+}
+
+}  // namespace
+
+extern "C" int vt_scale_plan_create(int sw, int sh, int dw, int dh, int flags, vt_scale_plan **out) {
+    if (!out || sw < 2 || sh < 2 || dw < 2 || dh < 2) {
+        vt::set_error("vt_scale_plan_create: bad size %dx%d -> %dx%d", sw, sh, dw, dh);
+        return VT_ERR_INVALID;
+    }
+    vt_scale_plan *p = new (std::nothrow) vt_scale_plan();
+    if (!p) return VT_ERR_NOMEM;
+    p->sw = sw; p->sh = sh; p->dw = dw; p->dh = dh; p->flags = flags;
+    p->csw = (sw + 1) >> 1; p->csh = (sh + 1) >> 1; p->cdw = (dw + 1) >> 1; p->cdh = (dh + 1) >> 1;
+    for (int c = 0; c < 2; c++) { p->hcoef[c] = p->vcoef[c] = nullptr; p->hpos[c] = p->vpos[c] = nullptr; }
+    p->scratch = nullptr;
+    int rc = VT_OK;
+    for (int c = 0; c < 2 && rc == VT_OK; c++) {
+        const int s_w = c ? p->csw : sw, s_h = c ? p->csh : sh, d_w = c ? p->cdw : dw, d_h = c ? p->cdh : dh;
+        rc = make_bank(s_w, d_w, flags, 1 << 14, p->h_hcoef[c], p->h_hpos[c], &p->htaps[c]);
+        if (rc == VT_OK) rc = make_bank(s_h, d_h, flags, 1 << 12, p->h_vcoef[c], p->h_vpos[c], &p->vtaps[c]);
+        if (rc == VT_OK) rc = upload(p->h_hcoef[c].data(), p->h_hcoef[c].size() * 2, (void **)&p->hcoef[c]);
+        if (rc == VT_OK) rc = upload(p->h_hpos[c].data(), p->h_hpos[c].size() * 4, (void **)&p->hpos[c]);
+        if (rc == VT_OK) rc = upload(p->h_vcoef[c].data(), p->h_vcoef[c].size() * 2, (void **)&p->vcoef[c]);
+        if (rc == VT_OK) rc = upload(p->h_vpos[c].data(), p->h_vpos[c].size() * 4, (void **)&p->vpos[c]);
+    }
+    if (rc == VT_OK && cudaMalloc((void **)&p->scratch, (size_t)dw * sh * sizeof(int16_t)) != cudaSuccess)
+        rc = VT_ERR_NOMEM;
+    if (rc != VT_OK) {
+        vt::set_error("vt_scale_plan_create: failed (%d) for %dx%d -> %dx%d flags=0x%x", rc, sw, sh, dw, dh, flags);
+        vt_scale_plan_destroy(p);
+        return rc;
+    }
+    *out = p;
+    return VT_OK;
+}
+
+extern "C" void vt_scale_plan_destroy(vt_scale_plan *p) {
+    if (!p) return;
+    for (int c = 0; c < 2; c++) {
+        cudaFree(p->hcoef[c]); cudaFree(p->hpos[c]); cudaFree(p->vcoef[c]); cudaFree(p->vpos[c]);
+        cudaFree(p->stream[c].strip_x0); cudaFree(p->stream[c].lane_tab);
+    }
+    cudaFree(p->scratch);
+    delete p;
+}
+
+extern "C" int vt_scale_plane_u8(const vt_scale_plan *plan, int chroma, const uint8_t *src, int src_pitch,
+                                 uint8_t *dst, int dst_pitch, void *stream) {
+    if (!plan || !src || !dst) {
+        vt::set_error("vt_scale_plane_u8: null argument");
+        return VT_ERR_INVALID;
+    }
+    return vt::scale_plane_generic(plan, chroma, src, src_pitch, 1, 0, dst, dst_pitch, (cudaStream_t)stream);
+}
+
+extern "C" int vt_scale_nv12_to_yuv420p(const vt_scale_plan *p, const uint8_t *src, int src_pitch, size_t src_fs,
+                                        uint8_t *dst, size_t dst_fs, int n_frames, void *stream) {
+    if (!p || !src || !dst || n_frames <= 0 || src_pitch < p->sw) {
+        vt::set_error("vt_scale_nv12_to_yuv420p: bad arguments");
+        return VT_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t ysz = (size_t)p->dw * p->dh, csz = (size_t)p->cdw * p->cdh;
+    for (int f = 0; f < n_frames; f++) {
+        const uint8_t *s = src + (size_t)f * src_fs;
+        uint8_t *d = dst + (size_t)f * dst_fs;
+        int rc = vt::scale_plane_generic(p, 0, s, src_pitch, 1, 0, d, p->dw, st);
+        if (rc) return rc;
+        const uint8_t *uv = s + (size_t)src_pitch * p->sh;
+        rc = vt::scale_plane_generic(p, 1, uv, src_pitch, 2, 0, d + ysz, p->cdw, st);
+        if (rc) return rc;
+        rc = vt::scale_plane_generic(p, 1, uv, src_pitch, 2, 1, d + ysz + csz, p->cdw, st);
+        if (rc) return rc;
+    }
+    return VT_OK;
+}
