@@ -87,4 +87,4 @@ def test_cuda_pcm_decode_bit_exact(cuda, w, h, pitch):
         assert np.array_equal(got[k, h:h + ch, 1:w:2], v), k
     # a batch that starts on a skip picture needs the carried-over surface
     tail = dec.decode(5, 4, pitch=pitch, prev=surf[4]).cpu().numpy()
-    assert np.array_equal(tail, got[5:9])
+    assert np.array_equal(tail[:, :, :w], got[5:9, :, :w])   # pitch padding is never written
