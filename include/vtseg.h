@@ -118,6 +118,12 @@ int vt_h264_scan(const uint8_t *bitstream, size_t n_bytes, vt_stream_info *info,
  * Any other H.264 feature is VT_ERR_UNSUPPORTED: on this pool the driver refuses NVDEC. */
 int vt_h264_pcm_layout(const uint8_t *bitstream, size_t n_bytes, const uint64_t *frame_offsets,
                        const uint32_t *frame_sizes, int n_frames, uint64_t *payload_off);
+/* Same, with the parameter sets given explicitly (MP4: they live in avcC, samples are length-prefixed NALs;
+ * frame_offsets then point at each sample's NAL header byte inside the file image `bitstream`). */
+int vt_h264_pcm_layout_ps(const uint8_t *bitstream, size_t n_bytes, const uint8_t *sps_nal, size_t sps_len,
+                          const uint8_t *pps_nal, size_t pps_len, const uint64_t *frame_offsets,
+                          const uint32_t *frame_sizes, int n_frames, uint64_t *payload_off);
+/* bitstream_dev must be readable 32 bytes past the last picture (whole 16-byte groups are fetched). */
 int vt_h264_pcm_decode(const uint8_t *bitstream_dev, const uint64_t *payload_off, int n_frames, int width,
                        int height, const uint8_t *prev_dev, uint8_t *nv12_dev, int pitch, size_t frame_stride,
                        void *stream);

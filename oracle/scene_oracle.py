@@ -1,0 +1,40 @@
+"""Oracle (O) for K4: plain-Python restatement of scene scoring / cut selection / picture ranges.
+
+TEST INFRASTRUCTURE ONLY.  Parity unpinned by the reference (it has no content-based detection:
+/root/reference/src/utils/video_segmenter.py:157-159 is a stub); the definition is SURVEY.md section 8a K4,
+restated here with scalar loops so that it shares no code with video_transformer_b200/scene.py.
+"""
+from __future__ import annotations
+
+
+def scene_scores(sads, width, height):
+    out = []
+    prev_mafd = 0.0
+    for t, s in enumerate(sads):
+        mafd = float(int(s)) / float(width * height)
+        diff = abs(mafd - prev_mafd)
+        sc = min(mafd, diff) / 100.0
+        sc = 0.0 if sc < 0.0 else (1.0 if sc > 1.0 else sc)
+        out.append(0.0 if t == 0 else sc)
+        prev_mafd = mafd
+    return out
+
+
+def select_cuts(scores, thr):
+    return [t for t, s in enumerate(scores) if t > 0 and s > thr]
+
+
+def frames_for_window(start, end, n_frames, fps_num, fps_den, keyframes=None, stream_copy=False):
+    s = float(format(start, ".3f"))
+    d = float(format(end - start, ".3f"))
+    if d <= 0:
+        return (0, 0)
+    kept = [k for k in range(n_frames) if s <= (k * float(fps_den)) / float(fps_num) < s + d]
+    if not kept:
+        return (0, 0)
+    first, last = kept[0], kept[-1] + 1
+    if stream_copy and keyframes is not None:
+        earlier = [int(k) for k in keyframes if int(k) <= first]
+        if earlier:
+            first = max(earlier)
+    return (first, last)

@@ -43,6 +43,8 @@ SIGNATURES = {
     "vt_gather_frames": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_int, c_void_p, c_void_p]),
     "vt_h264_scan": (c_int, [c_void_p, c_size_t, POINTER(StreamInfo), c_void_p, c_void_p, c_void_p, c_int]),
     "vt_h264_pcm_layout": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_void_p]),
+    "vt_h264_pcm_layout_ps": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p,
+                                      c_int, c_void_p]),
     "vt_h264_pcm_decode": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_size_t,
                                    c_void_p]),
     "vt_nvdec_probe": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),

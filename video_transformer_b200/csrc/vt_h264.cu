@@ -305,6 +305,28 @@ extern "C" int vt_h264_scan(const uint8_t *bs, size_t n, vt_stream_info *info, u
     return VT_OK;
 }
 
+namespace {
+int layout_core(const uint8_t *bs, size_t n, const Sps &sps, const Pps &pps, const uint64_t *frame_offsets,
+                const uint32_t *frame_sizes, int n_frames, uint64_t *payload_off) {
+    uint64_t last_idr = UINT64_MAX;
+    for (int f = 0; f < n_frames; f++) {
+        if (frame_offsets[f] + frame_sizes[f] > n) {
+            vt::set_error("vt_h264_pcm_layout: frame %d outside the buffer", f);
+            return VT_ERR_BITSTREAM;
+        }
+        SliceInfo si = parse_slice(bs + frame_offsets[f], frame_sizes[f], sps, pps);
+        if (!si.ok) {
+            vt::set_error("vt_h264_pcm_layout: picture %d is outside the PCM-intra subset "
+                          "(needs NVDEC, which this driver refuses)", f);
+            return VT_ERR_UNSUPPORTED;
+        }
+        if (si.pcm) last_idr = frame_offsets[f] + si.payload;
+        payload_off[f] = last_idr;  // skip pictures repeat the picture they reference
+    }
+    return VT_OK;
+}
+}  // namespace
+
 extern "C" int vt_h264_pcm_layout(const uint8_t *bs, size_t n, const uint64_t *frame_offsets,
                                   const uint32_t *frame_sizes, int n_frames, uint64_t *payload_off) {
     if (!bs || !frame_offsets || !frame_sizes || !payload_off || n_frames <= 0) {
@@ -324,37 +346,27 @@ extern "C" int vt_h264_pcm_layout(const uint8_t *bs, size_t n, const uint64_t *f
         if (type == 8 && !pps.valid) parse_pps(bs + nl.off, nl.size, &pps);
     }
     if (!sps.valid || !pps.valid) {
-        // fall back to a full scan for the first parameter sets
-        std::vector<Nal> all;
-        split_annexb(bs, n, all);
-        for (const Nal &nl : all) {
-            if (!nl.size) continue;
-            const int type = bs[nl.off] & 31;
-            if (type == 7 && !sps.valid) parse_sps(bs + nl.off, nl.size, &sps);
-            if (type == 8 && !pps.valid) parse_pps(bs + nl.off, nl.size, &pps);
-            if (sps.valid && pps.valid) break;
-        }
-    }
-    if (!sps.valid || !pps.valid) {
-        vt::set_error("vt_h264_pcm_layout: no SPS/PPS");
+        vt::set_error("vt_h264_pcm_layout: no SPS/PPS ahead of the first picture");
         return VT_ERR_BITSTREAM;
     }
-    uint64_t last_idr = UINT64_MAX;
-    for (int f = 0; f < n_frames; f++) {
-        if (frame_offsets[f] + frame_sizes[f] > n) {
-            vt::set_error("vt_h264_pcm_layout: frame %d outside the buffer", f);
-            return VT_ERR_BITSTREAM;
-        }
-        SliceInfo si = parse_slice(bs + frame_offsets[f], frame_sizes[f], sps, pps);
-        if (!si.ok) {
-            vt::set_error("vt_h264_pcm_layout: picture %d is outside the PCM-intra subset "
-                          "(needs NVDEC, which this driver refuses)", f);
-            return VT_ERR_UNSUPPORTED;
-        }
-        if (si.pcm) last_idr = frame_offsets[f] + si.payload;
-        payload_off[f] = last_idr;  // skip pictures repeat the picture they reference
+    return layout_core(bs, n, sps, pps, frame_offsets, frame_sizes, n_frames, payload_off);
+}
+
+extern "C" int vt_h264_pcm_layout_ps(const uint8_t *bs, size_t n, const uint8_t *sps_nal, size_t sps_len,
+                                     const uint8_t *pps_nal, size_t pps_len, const uint64_t *frame_offsets,
+                                     const uint32_t *frame_sizes, int n_frames, uint64_t *payload_off) {
+    if (!bs || !sps_nal || !pps_nal || sps_len < 4 || pps_len < 2 || !frame_offsets || !frame_sizes ||
+        !payload_off || n_frames <= 0) {
+        vt::set_error("vt_h264_pcm_layout_ps: bad arguments");
+        return VT_ERR_INVALID;
     }
-    return VT_OK;
+    Sps sps;
+    Pps pps;
+    if (!parse_sps(sps_nal, sps_len, &sps) || !parse_pps(pps_nal, pps_len, &pps)) {
+        vt::set_error("vt_h264_pcm_layout_ps: parameter sets outside the supported subset");
+        return VT_ERR_UNSUPPORTED;
+    }
+    return layout_core(bs, n, sps, pps, frame_offsets, frame_sizes, n_frames, payload_off);
 }
 
 // ---- device side: macroblock-ordered PCM samples -> NV12 raster --------------------------------------------

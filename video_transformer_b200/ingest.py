@@ -1,0 +1,264 @@
+"""The fused ingest pass: bitstream (host) -> decode -> score -> convert/downscale -> segment frame buffers (host).
+
+This is the GPU body behind extract_segment().  In the reference the same work happens inside two ffmpeg child
+processes (/root/reference/src/utils/video_segmenter.py:118-154 cut/decode,
+/root/reference/src/analyzer/content_analyzer.py:193-211 decode + `scale=-2:360`); here it is three kernels per
+batch of pictures, driven from three CUDA streams so that the H2D copy of batch i+1, the kernels of batch i and
+the D2H copy of batch i-1 overlap:
+
+    copy-in stream : pinned bitstream bytes            -> HBM
+    compute stream : vt_h264_pcm_decode (K0)  NV12 surfaces in HBM
+                     vt_sad_hist_u8     (K3)  SAD + histogram on the decoded luma
+                     vt_scale_nv12_to_yuv420p (K2) or vt_nv12_to_yuv420p (K1) -> output frames in HBM
+    copy-out stream: output frames + per-picture SAD/hist -> pinned host memory -> sink
+
+K4 (scores, cuts, boundaries) runs on the host in float64 from the integer SADs (scene.py).
+PyTorch only owns memory, streams and events here.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_void_p
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib, ops, scene
+from ._lib import check, lib
+from .container import StreamIndex
+
+_NO_PAYLOAD = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+@dataclass
+class IngestOptions:
+    target_height: int = 720           # downloader.max_resolution (config/config.yaml:75, README sample: 720)
+    sws_flags: int = _lib.SWS_BICUBIC  # ffmpeg's scale filter default
+    batch_frames: int = 32
+    scene_threshold: float = 0.10
+    keep_frames: bool = True           # deliver output frames to the sink (False: scores only, config 3)
+    never_upscale: bool = True         # sources at or below the target height are converted, not resized
+    device: str = "cuda"
+
+
+@dataclass
+class IngestResult:
+    first: int
+    last: int
+    out_width: int
+    out_height: int
+    frame_bytes: int
+    sad: np.ndarray                    # uint64 [n]
+    hist: np.ndarray                   # uint32 [n, 256]
+    scores: np.ndarray                 # float64 [n]; scores[0] belongs to picture `first`
+    cuts: np.ndarray                   # absolute picture indices
+    stats: dict = field(default_factory=dict)
+
+
+class PinnedRing:
+    """Sink that keeps the most recent chunks in pinned host memory and hands each to a callback."""
+
+    def __init__(self, callback=None):
+        self.callback = callback
+        self.bytes = 0
+        self.frames = 0
+
+    def __call__(self, chunk: torch.Tensor, first_picture: int) -> None:
+        self.bytes += chunk.numel()
+        self.frames += chunk.shape[0]
+        if self.callback is not None:
+            self.callback(chunk, first_picture)
+
+
+class FileSink:
+    """Appends raw planar YUV420P frames to a file (the `segment_XXXX.frames` artefact)."""
+
+    def __init__(self, path):
+        self.f = open(path, "wb")
+        self.frames = 0
+
+    def __call__(self, chunk: torch.Tensor, first_picture: int) -> None:
+        self.f.write(chunk.numpy().tobytes())
+        self.frames += chunk.shape[0]
+
+    def close(self) -> None:
+        self.f.close()
+
+
+class SegmentIngestor:
+    """Decode/score/scale engine for one indexed file on one GPU."""
+
+    def __init__(self, index: StreamIndex, opts: IngestOptions | None = None, host_bytes: np.ndarray | None = None):
+        self.idx = index
+        self.opts = opts or IngestOptions()
+        self.dev = torch.device(self.opts.device)
+        self.host = host_bytes if host_bytes is not None else np.memmap(index.path, dtype=np.uint8, mode="r")
+        n = index.n_frames
+        L = lib()
+        self.payload = np.zeros(n, np.uint64)
+        offs = np.ascontiguousarray(index.nal_offsets, dtype=np.uint64)
+        sizes = np.ascontiguousarray(index.nal_sizes, dtype=np.uint32)
+        if index.kind == "mp4":
+            sps = np.frombuffer(index.sps, np.uint8)
+            pps = np.frombuffer(index.pps, np.uint8)
+            check(L.vt_h264_pcm_layout_ps(self.host.ctypes.data, self.host.size, sps.ctypes.data, sps.size,
+                                          pps.ctypes.data, pps.size, offs.ctypes.data, sizes.ctypes.data, n,
+                                          self.payload.ctypes.data))
+        else:
+            check(L.vt_h264_pcm_layout(self.host.ctypes.data, self.host.size, offs.ctypes.data, sizes.ctypes.data, n,
+                                       self.payload.ctypes.data))
+        self.offs, self.sizes = offs, sizes
+        self.keyframes = np.nonzero(index.keyframe)[0].astype(np.int64)
+        self.w, self.h = index.width, index.height
+        self.pitch = (self.w + 255) // 256 * 256 if self.w > 256 else (self.w + 15) // 16 * 16
+        self.rows = self.h + (self.h + 1) // 2
+        self.surface_bytes = self.rows * self.pitch
+        th = self.opts.target_height
+        if th and (self.h > th or (not self.opts.never_upscale and self.h != th)):
+            self.out_h = th
+            self.out_w = ops.scale_width_for_height(self.w, self.h, th)
+            self.plan = ops.ScalePlan(self.w, self.h, self.out_w, self.out_h, self.opts.sws_flags)
+        else:
+            self.out_w, self.out_h, self.plan = self.w, self.h, None
+        self.frame_bytes = self.out_w * self.out_h + 2 * ((self.out_w + 1) // 2) * ((self.out_h + 1) // 2)
+        B = self.opts.batch_frames
+        self.B = B
+        max_nal = int(sizes.max()) if n else 0
+        # worst case bytes one batch needs on the device: B pictures + their container framing
+        self.bs_cap = (max_nal + 64) * min(B, max(1, int(index.keyframe.sum()))) + 4096 * B + 4096
+        self.slots = []
+        for _ in range(2):
+            self.slots.append({
+                "bs_host": torch.empty(self.bs_cap, dtype=torch.uint8, pin_memory=True),
+                "bs_dev": torch.empty(self.bs_cap + 64, dtype=torch.uint8, device=self.dev),
+                "surf": torch.empty((B, self.rows, self.pitch), dtype=torch.uint8, device=self.dev),
+                "out": torch.empty((B, self.frame_bytes), dtype=torch.uint8, device=self.dev),
+                "out_host": torch.empty((B, self.frame_bytes), dtype=torch.uint8, pin_memory=True),
+                "sad": torch.empty(B, dtype=torch.int64, device=self.dev),
+                "hist": torch.empty((B, 256), dtype=torch.int32, device=self.dev),
+                "sad_host": torch.empty(B, dtype=torch.int64, pin_memory=True),
+                "hist_host": torch.empty((B, 256), dtype=torch.int32, pin_memory=True),
+                "ev_in": torch.cuda.Event(), "ev_cmp": torch.cuda.Event(), "ev_out": torch.cuda.Event(),
+                "used": False, "pending": None,
+            })
+        self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    # ------------------------------------------------------------------------------------------------------
+    def _stage_bitstream(self, slot, b0: int, b1: int):
+        """Copy the file bytes pictures [b0,b1) need into the slot's pinned buffer; return payload offsets
+        relative to the device copy (or NO_PAYLOAD for pictures that repeat one from before b0)."""
+        pay = np.full(b1 - b0, _NO_PAYLOAD, np.uint64)
+        idr = [k for k in range(b0, b1) if self.idx.keyframe[k]]
+        if not idr:
+            return pay, 0
+        lo = int(self.offs[idr[0]])
+        hi = int(self.offs[idr[-1]]) + int(self.sizes[idr[-1]])
+        nbytes = hi - lo
+        if nbytes > self.bs_cap:
+            raise _lib.VtError(_lib.VT_ERR_NOMEM, "batch bitstream %d B exceeds staging %d B" % (nbytes, self.bs_cap))
+        slot["bs_host"].numpy()[:nbytes] = self.host[lo:hi]
+        first_idr = idr[0]
+        pay[first_idr - b0:] = self.payload[first_idr:b1] - np.uint64(lo)
+        return pay, nbytes
+
+    def run(self, first: int, last: int, sink=None) -> IngestResult:
+        """Process pictures [first, last).  Output frames go to sink(chunk_host_tensor, first_picture)."""
+        n_total = self.idx.n_frames
+        if not (0 <= first < last <= n_total):
+            raise ValueError("picture range [%d,%d) outside the stream (%d pictures)" % (first, last, n_total))
+        L = lib()
+        # lead-in: the score of picture `first` needs mafd of picture first-1, i.e. SAD(first-1, first-2), so
+        # decoding starts at the keyframe that picture first-2 depends on ("decode 2 extra
+        # lead-in frames per shard" instead of communicating)
+        r0 = max(first - 1, 0)               # first picture whose SAD is reported internally
+        need = max(first - 2, 0)
+        kf = self.keyframes[self.keyframes <= need]
+        if kf.size == 0:
+            raise _lib.VtError(_lib.VT_ERR_BITSTREAM, "no keyframe at or before picture %d" % need)
+        d0 = int(kf[-1])
+        n_rep = last - r0
+        sad_all = np.zeros(n_rep, np.uint64)
+        hist_all = np.zeros((n_rep, 256), np.uint32)
+        B = self.B
+        cur = torch.cuda.current_stream(self.dev)
+        for s in (self.s_in, self.s_cmp, self.s_out):
+            s.wait_stream(cur)
+        prev_surface = None
+        batches = [(b, min(b + B, last)) for b in range(d0, last, B)]
+
+        def drain(slot):
+            p = slot["pending"]
+            if p is None:
+                return
+            slot["ev_out"].synchronize()
+            b0, b1 = p
+            lo, hi = max(b0, r0), b1
+            if hi > lo:
+                k0 = lo - b0
+                sad_all[lo - r0:hi - r0] = slot["sad_host"].numpy()[k0:k0 + hi - lo].view(np.uint64)
+                hist_all[lo - r0:hi - r0] = slot["hist_host"].numpy()[k0:k0 + hi - lo].view(np.uint32)
+            lo = max(b0, first)
+            if hi > lo and sink is not None and self.opts.keep_frames:
+                sink(slot["out_host"][lo - b0:hi - b0], lo)
+            slot["pending"] = None
+
+        for i, (b0, b1) in enumerate(batches):
+            slot = self.slots[i & 1]
+            drain(slot)                      # host may only refill pinned buffers whose copies completed
+            nb = b1 - b0
+            pay, nbytes = self._stage_bitstream(slot, b0, b1)
+            with torch.cuda.stream(self.s_in):
+                if nbytes:
+                    slot["bs_dev"][:nbytes].copy_(slot["bs_host"][:nbytes], non_blocking=True)
+                    self.h2d_bytes += nbytes
+                slot["ev_in"].record(self.s_in)
+            with torch.cuda.stream(self.s_cmp):
+                self.s_cmp.wait_event(slot["ev_in"])
+                st = c_void_p(self.s_cmp.cuda_stream)
+                surf = slot["surf"]
+                check(L.vt_h264_pcm_decode(c_void_p(slot["bs_dev"].data_ptr()), pay.ctypes.data, nb, self.w, self.h,
+                                           c_void_p(prev_surface.data_ptr()) if prev_surface is not None else None,
+                                           c_void_p(surf.data_ptr()), self.pitch, self.surface_bytes, st))
+                check(L.vt_sad_hist_u8(c_void_p(surf.data_ptr()), self.pitch, self.surface_bytes, self.w, self.h,
+                                       c_void_p(prev_surface.data_ptr()) if prev_surface is not None else None, nb,
+                                       c_void_p(slot["sad"].data_ptr()), c_void_p(slot["hist"].data_ptr()), st))
+                if self.opts.keep_frames:
+                    if self.plan is not None:
+                        check(L.vt_scale_nv12_to_yuv420p(self.plan._h, c_void_p(surf.data_ptr()), self.pitch,
+                                                         self.surface_bytes, c_void_p(slot["out"].data_ptr()),
+                                                         self.frame_bytes, nb, st))
+                    else:
+                        check(L.vt_nv12_to_yuv420p(c_void_p(surf.data_ptr()), self.pitch, self.surface_bytes, self.w,
+                                                   self.h, c_void_p(slot["out"].data_ptr()), self.frame_bytes, nb, st))
+                slot["ev_cmp"].record(self.s_cmp)
+                prev_surface = surf[nb - 1]
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(slot["ev_cmp"])
+                lo = max(b0, first)
+                if self.opts.keep_frames and b1 > lo:
+                    k0 = lo - b0
+                    slot["out_host"][k0:nb].copy_(slot["out"][k0:nb], non_blocking=True)
+                    self.d2h_bytes += (nb - k0) * self.frame_bytes
+                slot["sad_host"][:nb].copy_(slot["sad"][:nb], non_blocking=True)
+                slot["hist_host"][:nb].copy_(slot["hist"][:nb], non_blocking=True)
+                self.d2h_bytes += nb * (8 + 1024)
+                slot["ev_out"].record(self.s_out)
+            # drain() synchronises this slot's ev_out before the host issues batch i+2 into the same buffers,
+            # which orders every device-side reuse (bitstream, surfaces, output) after the copies that read them
+            slot["pending"] = (b0, b1)
+        for slot in self.slots:
+            drain(slot)
+        cur.wait_stream(self.s_cmp)
+        cur.wait_stream(self.s_out)
+        if r0 == 0:
+            sad_all[0] = 0                   # picture 0 has no predecessor
+        scores = scene.scene_scores(sad_all, self.w, self.h)
+        if first > 0:                        # element 0 was picture first-1: only its mafd was needed
+            sad_all, hist_all, scores = sad_all[1:], hist_all[1:], scores[1:]
+        cuts = scene.select_cuts(scores, self.opts.scene_threshold) + first
+        return IngestResult(first, last, self.out_w, self.out_h, self.frame_bytes, sad_all, hist_all, scores, cuts,
+                            {"decoded_from": d0, "batches": len(batches), "h2d_bytes": self.h2d_bytes,
+                             "d2h_bytes": self.d2h_bytes})
