@@ -57,6 +57,10 @@ typedef struct vt_scale_plan vt_scale_plan;
 int vt_scale_plan_create(int src_w, int src_h, int dst_w, int dst_h, int flags, vt_scale_plan **out);
 void vt_scale_plan_destroy(vt_scale_plan *plan);
 
+/* Which kernel vt_scale_nv12_to_yuv420p will use for a plane kind: info8 = {streaming ok, dp2a pairs, vertical taps,
+ * columns per lane, output rows per item, tile width, tile height, shared bytes per warp}. */
+int vt_scale_plan_stream_info(const vt_scale_plan *plan, int chroma, int *info8);
+
 /* One 8-bit plane, any ratio (generic kernel; used for parity sweeps and odd shapes). */
 int vt_scale_plane_u8(const vt_scale_plan *plan, int chroma, const uint8_t *src_dev, int src_pitch,
                       uint8_t *dst_dev, int dst_pitch, void *stream);

@@ -35,6 +35,8 @@ def lib():
         L.vto_sad_hist.restype = None
         L.vto_nv12_to_yuv420p.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, u8p, u8p, u8p]
         L.vto_nv12_to_yuv420p.restype = None
+        L.vto_pcm_picture_to_yuv420p.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, u8p, u8p, u8p]
+        L.vto_pcm_picture_to_yuv420p.restype = None
         _lib = L
     return _lib
 
@@ -88,4 +90,15 @@ def nv12_to_yuv420p(nv12: np.ndarray, w: int, h: int, pitch: int):
     v = np.zeros((ch, cw), np.uint8)
     base = nv12.ctypes.data
     lib().vto_nv12_to_yuv420p(base, base + h * pitch, pitch, w, h, y.ctypes.data, u.ctypes.data, v.ctypes.data)
+    return y, u, v
+
+
+def pcm_picture_to_yuv420p(buf: np.ndarray, payload_off: int, w: int, h: int):
+    """One I_PCM picture whose macroblock 0 starts at buf[payload_off] -> (Y, U, V)."""
+    mb_w, mb_h = (w + 15) // 16, (h + 15) // 16
+    y = np.empty((h, w), np.uint8)
+    u = np.empty(((h + 1) // 2, (w + 1) // 2), np.uint8)
+    v = np.empty_like(u)
+    lib().vto_pcm_picture_to_yuv420p(buf.ctypes.data + int(payload_off), mb_w, mb_h, w, h, y.ctypes.data,
+                                     u.ctypes.data, v.ctypes.data)
     return y, u, v

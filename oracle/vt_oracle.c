@@ -323,3 +323,37 @@ void vto_nv12_to_yuv420p(const uint8_t *y, const uint8_t *uv, int pitch, int w, 
         }
     }
 }
+
+/*
+ * K0 restatement for the CPU baseline: one I_PCM picture of the synthetic streams (macroblock-ordered raw
+ * samples, 384 per macroblock, two header bytes between macroblocks; see video_transformer_b200/synth.py
+ * and ITU-T H.264 7.3.5 "pcm_sample_luma / pcm_sample_chroma") -> planar YUV420P at the display size.
+ * `payload` points at macroblock 0's first luma sample.  Decode parity itself is pinned against libavcodec
+ * in tests/test_decode.py; this function exists so the host-core baseline pays for the same re-layout.
+ */
+void vto_pcm_picture_to_yuv420p(const uint8_t *payload, int mb_w, int mb_h, int w, int h, uint8_t *y, uint8_t *u,
+                                uint8_t *v) {
+    const int cw = (w + 1) / 2, ch = (h + 1) / 2;
+    for (int my = 0; my < mb_h; my++) {
+        for (int mx = 0; mx < mb_w; mx++) {
+            const uint8_t *mb = payload + ((size_t)my * mb_w + mx) * 386;
+            for (int r = 0; r < 16; r++) {
+                int yy = my * 16 + r;
+                if (yy >= h) break;
+                int n = w - mx * 16;
+                if (n > 16) n = 16;
+                if (n > 0) memcpy(y + (size_t)yy * w + mx * 16, mb + r * 16, (size_t)n);
+            }
+            for (int r = 0; r < 8; r++) {
+                int yy = my * 8 + r;
+                if (yy >= ch) break;
+                int n = cw - mx * 8;
+                if (n > 8) n = 8;
+                if (n > 0) {
+                    memcpy(u + (size_t)yy * cw + mx * 8, mb + 256 + r * 8, (size_t)n);
+                    memcpy(v + (size_t)yy * cw + mx * 8, mb + 320 + r * 8, (size_t)n);
+                }
+            }
+        }
+    }
+}

@@ -98,6 +98,39 @@ def test_scale_nv12_to_yuv420p_bit_exact(cuda, oracle_c, sw, sh, pitch, dw, dh, 
         assert np.array_equal(gv, ev), ("V", np.abs(gv.astype(int) - ev.astype(int)).max())
 
 
+@pytest.mark.parametrize("sw,sh,dw,dh", [(1920, 1080, 1280, 720), (1280, 720, 640, 360), (3840, 2160, 1280, 720)])
+def test_headline_shapes_take_the_streaming_kernel(cuda, sw, sh, dw, dh):
+    plan = ops.ScalePlan(sw, sh, dw, dh, ops.SWS_BICUBIC)
+    for chroma in (False, True):
+        info = plan.stream_info(chroma)
+        assert info["streaming"] == 1, info
+        assert info["tile_w"] <= 256 and info["tile_w"] % 16 == 0
+
+
+def test_streaming_and_generic_kernels_agree_on_a_batch(cuda, oracle_c):
+    # 7 frames, structured content (flat areas, ramps, noise) so that clipping paths are exercised
+    from video_transformer_b200 import synth
+    sw, sh, pitch, dw, dh = 1920, 1080, 2048, 1280, 720
+    n = 7
+    rng = np.random.default_rng(11)
+    buf = np.zeros((n, sh + sh // 2, pitch), np.uint8)
+    for f in range(n):
+        y, u, v = synth.testsrc_frame(sw, sh, 31 * f, f)
+        if f % 3 == 2:
+            y = rng.integers(0, 256, y.shape, dtype=np.uint8)     # full-range noise: over/undershoot clipping
+        buf[f] = synth.planar_to_nv12(y, u, v, pitch).reshape(sh + sh // 2, pitch)
+    plan = ops.ScalePlan(sw, sh, dw, dh, ops.SWS_BICUBIC)
+    d = torch.from_numpy(buf).to(cuda)
+    out = plan.scale_nv12(d.view(-1), pitch, n).cpu().numpy()
+    for f in range(n):
+        gy = plan.scale_plane(d[f, :sh, :sw].contiguous()).cpu().numpy()
+        assert np.array_equal(out[f, : dw * dh].reshape(dh, dw), gy), f
+        y, u, v = oracle_c.nv12_to_yuv420p(buf[f].reshape(-1), sw, sh, pitch)
+        ey, eu, ev = oracle_c.scale_yuv420p(y, u, v, dw, dh, oracle_c.BICUBIC)
+        exp = np.concatenate([ey.reshape(-1), eu.reshape(-1), ev.reshape(-1)])
+        assert np.array_equal(out[f], exp), f
+
+
 def test_gather_frames(cuda):
     rng = np.random.default_rng(3)
     src = rng.integers(0, 256, (10, 4096 + 64), dtype=np.uint8)

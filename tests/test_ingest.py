@@ -1,0 +1,126 @@
+"""End-to-end: extract_segment() on the GPU against the oracles (picture range, MP4 artefact, frame buffers,
+SAD chain, scene cuts), plus SegmentIngestor range/lead-in behaviour."""
+import json
+
+import numpy as np
+import pytest
+
+from video_transformer_b200 import container, synth, video_segmenter
+from video_transformer_b200.video_utils import probe_duration
+
+pytestmark = pytest.mark.gpu
+
+
+def _clip(tmp_path, w, h, n, gop, cuts, mp4=True):
+    bs, meta = synth.make_testsrc_h264(w, h, n, fps=30, gop=gop, cuts=cuts)
+    raw = tmp_path / "clip.h264"
+    raw.write_bytes(bs)
+    if not mp4:
+        return raw, meta
+    out = tmp_path / "clip.mp4"
+    container.annexb_to_mp4(raw, out)
+    return out, meta
+
+
+def _expected(w, h, meta):
+    scene, ref, out = 0, None, []
+    cuts = set(meta["cuts"])
+    for k in range(meta["n_frames"]):
+        if k in cuts:
+            scene += 1
+        if k in meta["idr_frames"]:
+            ref = tuple(np.maximum(p, 1) for p in synth.testsrc_frame(w, h, k, scene))
+        out.append(ref)
+    return out
+
+
+@pytest.mark.parametrize("kind", ["mp4", "h264"])
+@pytest.mark.parametrize("stream_copy", [True, False])
+def test_extract_segment_gpu_matches_oracles(cuda, oracle_c, tmp_path, kind, stream_copy):
+    from oracle import scene_oracle
+    w, h, n, gop = 640, 480, 150, 15
+    src, meta = _clip(tmp_path, w, h, n, gop, cuts=[37, 95], mp4=(kind == "mp4"))
+    assert abs(probe_duration(src) - 5.0) < 1e-9
+    video_segmenter.configure(target_height=240, batch_frames=16, scene_threshold=0.05)
+    start, end = 1.2345, 4.0
+    out = tmp_path / "segments" / "vid" / "segment_0001.mp4"
+    assert video_segmenter.extract_segment(input_path=src, start=start, end=end, output_path=out,
+                                           stream_copy=stream_copy) is True
+    assert out.exists() and out.stat().st_size > 0
+    first, last = scene_oracle.frames_for_window(start, end, n, 30, 1, meta["idr_frames"], stream_copy)
+    side = json.loads(out.with_suffix(".json").read_text())
+    assert (side["first_picture"], side["last_picture"]) == (first, last)
+    assert side["frame_size"] == [320, 240] and side["frames"] == last - first
+    # the MP4 artefact: same pictures, decodable from its first sample
+    cut = container.probe(out)
+    assert cut.n_frames == last - first and bool(cut.keyframe[0])
+    cv2 = pytest.importorskip("cv2")
+    cap = cv2.VideoCapture(str(out), cv2.CAP_FFMPEG)
+    cap.set(cv2.CAP_PROP_CONVERT_RGB, 0)
+    exp = _expected(w, h, meta)
+    k = first
+    while True:
+        ok, fr = cap.read()
+        if not ok:
+            break
+        assert np.array_equal(np.asarray(fr).reshape(-1)[: w * h].reshape(h, w), exp[k][0]), k
+        k += 1
+    assert k == last
+    # frame buffers: bit-exact against the C oracle applied to the expected decoded pictures
+    fb = 320 * 240 * 3 // 2
+    frames = np.fromfile(out.with_suffix(".frames"), np.uint8).reshape(-1, fb)
+    assert frames.shape[0] == last - first
+    cache = {}
+    for i, k in enumerate(range(first, last)):
+        key = id(exp[k])
+        if key not in cache:
+            ey, eu, ev = oracle_c.scale_yuv420p(*exp[k], 320, 240, oracle_c.BICUBIC)
+            cache[key] = np.concatenate([ey.reshape(-1), eu.reshape(-1), ev.reshape(-1)])
+        assert np.array_equal(frames[i], cache[key]), k
+    # SAD chain and cuts: integers exact, float64 scores bit-identical to the scalar oracle
+    sads = [0 if k == 0 else oracle_c.sad_hist(exp[k][0], exp[k - 1][0])[0] for k in range(max(first - 1, 0), last)]
+    if first == 0:
+        sads[0] = 0
+    sc = scene_oracle.scene_scores(sads, w, h)
+    if first > 0:
+        sads, sc = sads[1:], sc[1:]
+    assert side["sad"] == sads
+    assert [float(x).hex() for x in side["score"]] == [float(x).hex() for x in sc]
+    exp_cuts = [first + t for t, v in enumerate(sc) if v > 0.05 and first + t > 0]
+    assert side["cuts"] == exp_cuts
+    assert set(c for c in meta["cuts"] if first < c < last) <= set(side["cuts"])
+    video_segmenter.configure(target_height=720, batch_frames=32, scene_threshold=0.10)
+
+
+def test_ingest_is_shard_invariant(cuda, tmp_path):
+    """Boundaries must not depend on how pictures are sharded: per-shard SADs concatenate to the single-pass SADs."""
+    from video_transformer_b200 import ingest
+    src, meta = _clip(tmp_path, 320, 240, 120, 10, cuts=[33, 71])
+    idx = container.probe(src)
+    opts = ingest.IngestOptions(target_height=120, batch_frames=8, scene_threshold=0.05)
+    whole = ingest.SegmentIngestor(idx, opts).run(0, 120, None)
+    parts = [ingest.SegmentIngestor(idx, opts).run(a, b, None) for a, b in [(0, 33), (33, 34), (34, 95), (95, 120)]]
+    assert np.array_equal(np.concatenate([p.sad for p in parts]), whole.sad)
+    assert np.array_equal(np.concatenate([p.hist for p in parts]), whole.hist)
+    assert np.array_equal(np.concatenate([p.scores for p in parts]), whole.scores)
+    assert sorted(np.concatenate([p.cuts for p in parts]).tolist()) == whole.cuts.tolist()
+    assert set(meta["cuts"]) <= set(whole.cuts.tolist())
+
+
+def test_same_height_source_is_converted_not_resized(cuda, oracle_c, tmp_path):
+    from video_transformer_b200 import ingest
+    src, meta = _clip(tmp_path, 320, 240, 12, 4, cuts=[])
+    idx = container.probe(src)
+    got = []
+    res = ingest.SegmentIngestor(idx, ingest.IngestOptions(target_height=240, batch_frames=5)).run(
+        2, 11, lambda chunk, k0: got.append((k0, chunk.numpy().copy())))
+    assert (res.out_width, res.out_height) == (320, 240)
+    exp = _expected(320, 240, meta)
+    k = 2
+    for k0, chunk in got:
+        assert k0 == k
+        for row in chunk:
+            y, u, v = exp[k]
+            assert np.array_equal(row, np.concatenate([y.reshape(-1), u.reshape(-1), v.reshape(-1)])), k
+            k += 1
+    assert k == 11

@@ -1,53 +1,81 @@
 // vt_score.cu -- K3: per-frame 256-bin luma histogram + SAD(cur, prev).
 //
 // HBM-bound byte work: 2 bytes read per pixel (cur + prev luma), ~1 KB written per frame.
-// The histogram is the hard part: shared-memory atomics serialise on flat picture areas (test patterns,
-// letterboxing), so this kernel uses no atomics in its hot loop.  Every lane of a warp owns a private
-// column of 256 one-byte counters (8 KB per warp, laid out counter[bin][lane] so a warp's 32 accesses
-// fall in 8 words x 4 bytes); an update is LDS.U8 / IADD / STS.U8 on an address formed by one shift
-// and one LOP3.  A lane sees at most 240 pixels between flushes, so a byte never wraps.  Flushes sum the
-// 32 lane bytes of each bin with dp4a and add them to a per-block u32 histogram.
-// SAD is __vabsdiffu4 + dp4a on the same 128-bit loads.
+// The histogram is the hard part: shared-memory atomics on a per-warp histogram serialise on flat picture
+// areas (test patterns, letterboxing) and cost data-dependent bank conflicts everywhere else.  This kernel's
+// hot loop is data independent.  Every lane of a warp owns a private column of 256 one-byte counters packed
+// four to a 32-bit word; word (row r, lane l) sits at  warp_base + r*128 + l*4, so the bank is the lane and a
+// warp's 32 updates never conflict.  Bin b lives in row (b & 63), byte (b >> 6).  An update is one
+// shared-memory RED of (1 << 8*(b>>6)) on that word (measured on B200: 9.3 px/clk/SM against 7.6 for
+// LDS.U8/IADD/STS.U8 on the same layout and 4.9-7.7 for byte counters that share words between lanes;
+// tools/ubench_smem.cu).  A lane sees at most 240 pixels between flushes, so no byte can carry into its
+// neighbour.  A flush sums each row over the 32 lanes with rotated (conflict-free) word reads and adds the
+// four bins of the row to the block histogram.  SAD is VABSDIFF4 + IDP.4A on the same 128-bit loads.
 #include "vt_common.cuh"
 
 namespace vt {
 
 constexpr int SC_WARPS = 8;
 constexpr int SC_THREADS = SC_WARPS * 32;
-constexpr int SC_CNT_BYTES = 8192;                                   // per warp: 256 bins x 32 lanes x u8
+constexpr int SC_CNT_BYTES = 8192;                                   // per warp: 64 rows x 32 lanes x 4 packed u8
 constexpr int SC_SMEM = SC_WARPS * SC_CNT_BYTES + SC_CNT_BYTES + 1024;  // + alignment slack + block hist
 
-__device__ __forceinline__ void cnt_inc(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    v += 1;
-    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+__device__ __forceinline__ void red_shared(uint32_t addr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-// 4 pixels of one 32-bit word. base = (8 KB-aligned warp region) | lane, so OR-ing in bin*32 is exact.
+// 4 pixels of one 32-bit word.  base = (8 KB aligned warp region) | lane*4.
+// Per pixel: one shift + one LOP3 for the address, one PRMT + one shift for the increment, one RED.
 __device__ __forceinline__ void hist_word(uint32_t w, uint32_t base) {
-    cnt_inc(((w << 5) & 0x1FE0u) | base);
-    cnt_inc(((w >> 3) & 0x1FE0u) | base);
-    cnt_inc(((w >> 11) & 0x1FE0u) | base);
-    cnt_inc(((w >> 19) & 0x1FE0u) | base);
+    const uint32_t r = w & 0x3F3F3F3Fu;          // row index of each pixel
+    const uint32_t j8 = (w >> 3) & 0x18181818u;  // 8 * (pixel >> 6): bit offset of its counter in the word
+    red_shared(((r << 7) & 0x1F80u) | base, 1u << __byte_perm(j8, 0, 0x4440));
+    red_shared(((r >> 1) & 0x1F80u) | base, 1u << __byte_perm(j8, 0, 0x4441));
+    red_shared(((r >> 9) & 0x1F80u) | base, 1u << __byte_perm(j8, 0, 0x4442));
+    red_shared(((r >> 17) & 0x1F80u) | base, 1u << (j8 >> 24));
 }
 
-// Warp-collective: add the lane-private byte counters into the block histogram and clear them.
-__device__ __forceinline__ void flush_counters(uint32_t warp_cnt /* shared addr, 8 KB aligned */, uint32_t *bhist,
-                                               int lane) {
+// Warp-collective: add the lane-private packed counters into the block histogram and clear them.
+// Lane l owns rows 2l and 2l+1 and reads each as eight 128-bit chunks, starting at chunk (l & 7) and
+// rotating: a 128-bit shared load is served eight lanes at a time, and eight consecutive lanes always ask
+// for eight different chunks (different banks), so the loads are conflict free although every lane reads
+// a different row.  All 16 loads are issued before the first use.
+__device__ __forceinline__ void flush_counters(uint32_t warp_cnt, uint32_t *bhist, int lane) {
     __syncwarp();
-#pragma unroll 4
-    for (int p = 0; p < 16; p++) {
-        uint32_t a = warp_cnt + (uint32_t)(p * 32 + lane) * 16u;
-        uint4 v;
-        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
-        uint32_t s = __dp4a(v.x, 0x01010101u, 0u);
-        s = __dp4a(v.y, 0x01010101u, s);
-        s = __dp4a(v.z, 0x01010101u, s);
-        s = __dp4a(v.w, 0x01010101u, s);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        if (!(lane & 1) && s) atomicAdd(&bhist[p * 16 + (lane >> 1)], s);
-        asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(a), "r"(0u) : "memory");
+    uint32_t even[2], odd[2];  // per row: two 16-bit sums each (bytes 0/2 and bytes 1/3; max 32*255 = 8160)
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        uint4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t a = warp_cnt + (uint32_t)(2 * lane + h) * 128u + (uint32_t)((lane + i) & 7) * 16u;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w)
+                         : "r"(a)
+                         : "memory");
+        }
+        uint32_t e = 0, o = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            e += (v[i].x & 0x00FF00FFu) + (v[i].y & 0x00FF00FFu) + (v[i].z & 0x00FF00FFu) + (v[i].w & 0x00FF00FFu);
+            o += ((v[i].x >> 8) & 0x00FF00FFu) + ((v[i].y >> 8) & 0x00FF00FFu) + ((v[i].z >> 8) & 0x00FF00FFu) +
+                 ((v[i].w >> 8) & 0x00FF00FFu);
+        }
+        even[h] = e;
+        odd[h] = o;
+    }
+    __syncwarp();   // every lane has summed its rows: the counters can be cleared
+#pragma unroll
+    for (int p = 0; p < 16; p++)
+        asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(warp_cnt + (uint32_t)(p * 32 + lane) * 16u), "r"(0u)
+                     : "memory");
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int r = 2 * lane + h;
+        if (even[h] & 0xFFFFu) atomicAdd(&bhist[r], even[h] & 0xFFFFu);
+        if (odd[h] & 0xFFFFu) atomicAdd(&bhist[r + 64], odd[h] & 0xFFFFu);
+        if (even[h] >> 16) atomicAdd(&bhist[r + 128], even[h] >> 16);
+        if (odd[h] >> 16) atomicAdd(&bhist[r + 192], odd[h] >> 16);
     }
     __syncwarp();
 }
@@ -78,30 +106,26 @@ score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, i
                      : "memory");
     __syncthreads();
 
-    const int ngroups = (w + 15) >> 4;           // 16-byte groups per row
-    const int nit = (ngroups + 31) >> 5;         // warp passes per row
-    const int tail = w & 15;                     // valid bytes in the last group (0 = full)
-    const int nrows = (r1 - r0 - warp + SC_WARPS - 1) / SC_WARPS;  // rows this warp owns (may be <= 0)
-    const int total = nrows > 0 ? nrows * nit : 0;
-    const uint32_t base = warp_cnt | (uint32_t)lane;
+    const int ngroups = (w + 15) >> 4;  // 16-byte groups per row
+    const int tail = w & 15;            // valid bytes in the last group (0 = full)
+    const uint32_t base = warp_cnt | ((uint32_t)lane << 2);
 
     uint32_t sad = 0;
     int budget = 0;
-    // software pipeline: loads for pass i+1 are in flight while pass i updates the counters
-    uint4 c = make_uint4(0, 0, 0, 0), p = c;
-    bool have = false;
-    auto fetch = [&](int i, uint4 &cc, uint4 &pp) -> bool {
-        int rr = i / nit;
-        int g = (i - rr * nit) * 32 + lane;
-        if (g >= ngroups) return false;
-        size_t off = (size_t)(r0 + warp + rr * SC_WARPS) * pitch + (size_t)g * 16;
+    // (row, g0) walk this warp's rows pass by pass; loads for the next pass are issued before the current
+    // pass updates its counters.
+    int row = r0 + warp, g0 = 0;
+    auto fetch = [&](int rw, int gs, uint4 &cc, uint4 &pp) -> bool {
+        const int g = gs + lane;
+        if (rw >= r1 || g >= ngroups) return false;
+        const size_t off = (size_t)rw * pitch + (size_t)g * 16;
         cc = ld_stream_u4(cur + off);
         pp = ld_stream_u4(prv + off);
         if (tail && g == ngroups - 1) {  // zero the bytes past the display width in both operands
             uint32_t m[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                int nb = tail - 4 * k;
+                const int nb = tail - 4 * k;
                 m[k] = nb >= 4 ? 0xffffffffu : (nb <= 0 ? 0u : ((1u << (8 * nb)) - 1u));
             }
             cc.x &= m[0]; cc.y &= m[1]; cc.z &= m[2]; cc.w &= m[3];
@@ -109,11 +133,13 @@ score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, i
         }
         return true;
     };
-    if (total > 0) have = fetch(0, c, p);
-    for (int i = 0; i < total; i++) {
+    uint4 c = make_uint4(0, 0, 0, 0), p = c;
+    bool have = fetch(row, g0, c, p);
+    while (row < r1) {
+        int nrow = row, ng0 = g0 + 32;
+        if (ng0 >= ngroups) { ng0 = 0; nrow = row + SC_WARPS; }
         uint4 cn = make_uint4(0, 0, 0, 0), pn = cn;
-        bool have_n = false;
-        if (i + 1 < total) have_n = fetch(i + 1, cn, pn);
+        const bool have_n = fetch(nrow, ng0, cn, pn);
         if (budget > 255 - 16) {
             flush_counters(warp_cnt, bhist, lane);
             budget = 0;
@@ -130,10 +156,11 @@ score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, i
         }
         budget += 16;
         c = cn; p = pn; have = have_n;
+        row = nrow; g0 = ng0;
     }
     flush_counters(warp_cnt, bhist, lane);
 
-    // SAD: lane partials (<= 2^32) -> warp sum in 64 bit -> one global atomic per warp
+    // SAD: lane partials -> warp sum in 64 bit -> one global atomic per warp
     unsigned long long s64 = sad;
 #pragma unroll
     for (int o = 16; o; o >>= 1) s64 += __shfl_xor_sync(0xffffffffu, s64, o);

@@ -249,8 +249,8 @@ class SegmentIngestor:
             # drain() synchronises this slot's ev_out before the host issues batch i+2 into the same buffers,
             # which orders every device-side reuse (bitstream, surfaces, output) after the copies that read them
             slot["pending"] = (b0, b1)
-        for slot in self.slots:
-            drain(slot)
+        for slot in sorted(self.slots, key=lambda sl: sl["pending"][0] if sl["pending"] else -1):
+            drain(slot)                      # oldest batch first: the sink sees pictures in order
         cur.wait_stream(self.s_cmp)
         cur.wait_stream(self.s_out)
         if r0 == 0:
@@ -258,7 +258,7 @@ class SegmentIngestor:
         scores = scene.scene_scores(sad_all, self.w, self.h)
         if first > 0:                        # element 0 was picture first-1: only its mafd was needed
             sad_all, hist_all, scores = sad_all[1:], hist_all[1:], scores[1:]
-        cuts = scene.select_cuts(scores, self.opts.scene_threshold) + first
+        cuts = scene.select_cuts(scores, self.opts.scene_threshold, first)
         return IngestResult(first, last, self.out_w, self.out_h, self.frame_bytes, sad_all, hist_all, scores, cuts,
                             {"decoded_from": d0, "batches": len(batches), "h2d_bytes": self.h2d_bytes,
                              "d2h_bytes": self.d2h_bytes})

@@ -107,6 +107,13 @@ class ScalePlan:
         except Exception:  # noqa: BLE001
             pass
 
+    def stream_info(self, chroma: bool = False) -> dict:
+        """Which kernel scale_nv12 uses for a plane kind (streaming TMA kernel or the generic two-pass one)."""
+        arr = (c_int * 8)()
+        check(lib().vt_scale_plan_stream_info(self._h, 1 if chroma else 0, arr))
+        keys = ("streaming", "dp2a_pairs", "v_taps", "cols_per_lane", "rows_out", "tile_w", "tile_h", "warp_smem")
+        return dict(zip(keys, [int(v) for v in arr]))
+
     @property
     def out_frame_bytes(self) -> int:
         return self.dw * self.dh + 2 * self.cdw * self.cdh

@@ -29,10 +29,10 @@ def scene_scores(sad: np.ndarray, width: int, height: int) -> np.ndarray:
     return score
 
 
-def select_cuts(score: np.ndarray, threshold: float) -> np.ndarray:
-    """Indices t > 0 with score_t > threshold."""
-    idx = np.nonzero(np.asarray(score) > threshold)[0]
-    return idx[idx > 0].astype(np.int64)
+def select_cuts(score: np.ndarray, threshold: float, first_picture: int = 0) -> np.ndarray:
+    """Absolute picture indices t > 0 with score_t > threshold; score[0] belongs to picture `first_picture`."""
+    idx = np.nonzero(np.asarray(score) > threshold)[0].astype(np.int64) + int(first_picture)
+    return idx[idx > 0]
 
 
 def pts(k, fps_num: int, fps_den: int):
