@@ -227,7 +227,9 @@ scale_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs a
         int ynext = y0;
         int vlast = vt[1] - rs;                                          // row (relative) completing output ynext
         const int nrows = re - rs;
-        uint8_t *dplane = a.dst + (size_t)f * a.dst_fs;
+        // running pointers: this lane's first output byte of row ynext, and that row's vertical coefficients
+        uint8_t *dptr = a.dst + (size_t)f * a.dst_fs + (size_t)y0 * a.dw + xl;
+        const int32_t *vc = vt + 2;
         for (int base = 0; base < nrows; base += RING) {
 #pragma unroll
             for (int k = 0; k < RING; k++) {
@@ -270,8 +272,7 @@ scale_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs a
                         }
                     }
                     // ---- vertical pass for every output row whose window ends at this source row
-                    while (ynext < y1 && vlast == r) {
-                        const int32_t *vc = vt + (ynext - y0) * (TV + 2) + 2;
+                    while (vlast == r) {
                         int acc[CPT * NCH];
 #pragma unroll
                         for (int c = 0; c < CPT * NCH; c++) acc[c] = 1 << 18;
@@ -283,22 +284,22 @@ scale_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs a
                                 acc[c] += m[(k + RING - (TV - 1) + j) & (RING - 1)][c] * cj;
                         }
                         if (!UV) {
-                            uint8_t *d = dplane + (size_t)ynext * a.dw + xl;
 #pragma unroll
                             for (int c = 0; c < CPT; c++)
-                                if (FULL || xl + 32 * c < a.dw) d[32 * c] = (uint8_t)__vimin_s32_relu(acc[c] >> 19, 255);
+                                if (FULL || xl + 32 * c < a.dw) dptr[32 * c] = (uint8_t)__vimin_s32_relu(acc[c] >> 19, 255);
                         } else {
-                            uint8_t *du = dplane + (size_t)ynext * a.dw + xl;
-                            uint8_t *dv = du + a.dst_plane2;
+                            uint8_t *dv = dptr + a.dst_plane2;
 #pragma unroll
                             for (int c = 0; c < CPT; c++)
                                 if (FULL || xl + 32 * c < a.dw) {
-                                    du[32 * c] = (uint8_t)__vimin_s32_relu(acc[2 * c] >> 19, 255);
+                                    dptr[32 * c] = (uint8_t)__vimin_s32_relu(acc[2 * c] >> 19, 255);
                                     dv[32 * c] = (uint8_t)__vimin_s32_relu(acc[2 * c + 1] >> 19, 255);
                                 }
                         }
                         ynext++;
-                        if (ynext < y1) vlast = vt[(ynext - y0) * (TV + 2) + 1] - rs;
+                        dptr += a.dw;
+                        vc += TV + 2;
+                        vlast = ynext < y1 ? vc[-1] - rs : -1;           // -1: no further output in this chunk
                     }
                 }
             }

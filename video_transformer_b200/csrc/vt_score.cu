@@ -109,54 +109,63 @@ score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, i
     const int ngroups = (w + 15) >> 4;  // 16-byte groups per row
     const int tail = w & 15;            // valid bytes in the last group (0 = full)
     const uint32_t base = warp_cnt | ((uint32_t)lane << 2);
+    const int rpw = rows_per_block / SC_WARPS;   // consecutive rows owned by each warp
 
     uint32_t sad = 0;
-    int budget = 0;
-    // (row, g0) walk this warp's rows pass by pass; loads for the next pass are issued before the current
-    // pass updates its counters.
-    int row = r0 + warp, g0 = 0;
-    auto fetch = [&](int rw, int gs, uint4 &cc, uint4 &pp) -> bool {
-        const int g = gs + lane;
-        if (rw >= r1 || g >= ngroups) return false;
-        const size_t off = (size_t)rw * pitch + (size_t)g * 16;
-        cc = ld_stream_u4(cur + off);
-        pp = ld_stream_u4(prv + off);
-        if (tail && g == ngroups - 1) {  // zero the bytes past the display width in both operands
-            uint32_t m[4];
+    int budget = 0;                     // upper bound on pixels a lane has counted since the last flush
+    for (int rr = 0; rr < rpw; rr++) {
+        const int row = r0 + warp * rpw + rr;
+        if (row >= r1) break;
+        const uint8_t *crow = cur + (size_t)row * pitch;
+        const uint8_t *prow = prv + (size_t)row * pitch;
+        // four passes (64 bytes per lane) at a time: all eight 128-bit loads are issued before the first counter
+        // update, which is what keeps enough bytes in flight per SM
+        for (int g0 = 0; g0 < ngroups; g0 += 128) {
+            uint4 c[4], p[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const int nb = tail - 4 * k;
-                m[k] = nb >= 4 ? 0xffffffffu : (nb <= 0 ? 0u : ((1u << (8 * nb)) - 1u));
+                const int g = g0 + k * 32 + lane;
+                c[k] = make_uint4(0, 0, 0, 0);
+                p[k] = c[k];
+                if (g < ngroups) {
+                    c[k] = ld_stream_u4(crow + (size_t)g * 16);
+                    p[k] = ld_stream_u4(prow + (size_t)g * 16);
+                }
             }
-            cc.x &= m[0]; cc.y &= m[1]; cc.z &= m[2]; cc.w &= m[3];
-            pp.x &= m[0]; pp.y &= m[1]; pp.z &= m[2]; pp.w &= m[3];
+            if (tail && g0 + 128 >= ngroups) {  // the row's last group is in this block: mask bytes past the width
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (g0 + k * 32 + lane == ngroups - 1) {
+                        uint32_t m[4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int nb = tail - 4 * q;
+                            m[q] = nb >= 4 ? 0xffffffffu : (nb <= 0 ? 0u : ((1u << (8 * nb)) - 1u));
+                        }
+                        c[k].x &= m[0]; c[k].y &= m[1]; c[k].z &= m[2]; c[k].w &= m[3];
+                        p[k].x &= m[0]; p[k].y &= m[1]; p[k].z &= m[2]; p[k].w &= m[3];
+                    }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (g0 + k * 32 >= ngroups) break;          // warp-uniform
+                if (budget > 255 - 16) {                    // only reachable for rows wider than 8160 pixels
+                    flush_counters(warp_cnt, bhist, lane);
+                    budget = 0;
+                }
+                if (g0 + k * 32 + lane < ngroups) {
+                    sad = sad4(c[k].x, p[k].x, sad);
+                    sad = sad4(c[k].y, p[k].y, sad);
+                    sad = sad4(c[k].z, p[k].z, sad);
+                    sad = sad4(c[k].w, p[k].w, sad);
+                    hist_word(c[k].x, base);
+                    hist_word(c[k].y, base);
+                    hist_word(c[k].z, base);
+                    hist_word(c[k].w, base);
+                }
+                budget += 16;
+            }
         }
-        return true;
-    };
-    uint4 c = make_uint4(0, 0, 0, 0), p = c;
-    bool have = fetch(row, g0, c, p);
-    while (row < r1) {
-        int nrow = row, ng0 = g0 + 32;
-        if (ng0 >= ngroups) { ng0 = 0; nrow = row + SC_WARPS; }
-        uint4 cn = make_uint4(0, 0, 0, 0), pn = cn;
-        const bool have_n = fetch(nrow, ng0, cn, pn);
-        if (budget > 255 - 16) {
-            flush_counters(warp_cnt, bhist, lane);
-            budget = 0;
-        }
-        if (have) {
-            sad = sad4(c.x, p.x, sad);
-            sad = sad4(c.y, p.y, sad);
-            sad = sad4(c.z, p.z, sad);
-            sad = sad4(c.w, p.w, sad);
-            hist_word(c.x, base);
-            hist_word(c.y, base);
-            hist_word(c.z, base);
-            hist_word(c.w, base);
-        }
-        budget += 16;
-        c = cn; p = pn; have = have_n;
-        row = nrow; g0 = ng0;
     }
     flush_counters(warp_cnt, bhist, lane);
 
@@ -215,8 +224,13 @@ int launch_score(const uint8_t *luma, int pitch, size_t frame_stride, int w, int
     VT_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * 256 * (size_t)n_frames, st));
     const bool aligned = ((uintptr_t)luma % 16 == 0) && (pitch % 16 == 0) && (frame_stride % 16 == 0) &&
                          (!prev0 || (uintptr_t)prev0 % 16 == 0) && (((w + 15) & ~15) <= pitch);
-    // 32 rows per block: each warp owns 4 rows; enough blocks per frame to fill 148 SMs x 3 with small batches
-    const int rows_per_block = 32;
+    // Rows per block: as many consecutive rows per warp as fit the byte counters (a lane counts
+    // 16*ceil(groups/32) pixels per row and may hold 255), so a block flushes its counters exactly once.
+    const int px_per_lane_row = 16 * ((((w + 15) >> 4) + 31) / 32);
+    int rpw = 255 / px_per_lane_row;
+    if (rpw < 1) rpw = 1;
+    if (rpw > 8) rpw = 8;
+    const int rows_per_block = aligned ? rpw * SC_WARPS : 32;
     const int chunks = (h + rows_per_block - 1) / rows_per_block;
     const long long blocks = (long long)chunks * n_frames;
     if (blocks > 0x7fffffffLL) {
