@@ -37,6 +37,8 @@ def lib():
         L.vto_nv12_to_yuv420p.restype = None
         L.vto_pcm_picture_to_yuv420p.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, u8p, u8p, u8p]
         L.vto_pcm_picture_to_yuv420p.restype = None
+        L.vto_yuv_to_rgb24.argtypes = [u8p, ctypes.c_int, u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       u8p, ctypes.c_int, ctypes.c_int]
         _lib = L
     return _lib
 
@@ -102,3 +104,15 @@ def pcm_picture_to_yuv420p(buf: np.ndarray, payload_off: int, w: int, h: int):
     lib().vto_pcm_picture_to_yuv420p(buf.ctypes.data + int(payload_off), mb_w, mb_h, w, h, y.ctypes.data,
                                      u.ctypes.data, v.ctypes.data)
     return y, u, v
+
+
+def nv12_to_rgb24(nv12: np.ndarray, w: int, h: int, pitch: int, dw: int | None = None, dh: int | None = None) -> np.ndarray:
+    """NV12 surface (flat u8, Y rows then UV rows of `pitch` bytes) -> RGB24 (dh, dw, 3), swscale bicubic semantics."""
+    nv12 = np.ascontiguousarray(nv12)
+    dw, dh = dw or w, dh or h
+    out = np.zeros((dh, dw, 3), np.uint8)
+    base = nv12.ctypes.data
+    rc = lib().vto_yuv_to_rgb24(base, pitch, base + h * pitch, base + h * pitch + 1, pitch, 2, w, h, out.ctypes.data, dw, dh)
+    if rc:
+        raise RuntimeError("vto_yuv_to_rgb24 failed")
+    return out

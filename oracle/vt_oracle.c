@@ -357,3 +357,79 @@ void vto_pcm_picture_to_yuv420p(const uint8_t *payload, int mb_w, int mb_h, int 
         }
     }
 }
+
+/*
+ * K1b / config 5 restatement: NV12 (or planar 4:2:0) -> packed RGB24 with optional scaling, as libswscale's
+ * general path does it for `nv12 -> rgb24` with SWS_BICUBIC (swscale.c + output.c yuv2rgb_X_c_template +
+ * yuv2rgb.c ff_yuv2rgb_c_init_tables, ITU-R BT.601 limited range = swscale's default colourspace):
+ *   - luma:   horizontal bank sw->dw, vertical bank sh->dh
+ *   - chroma: horizontal bank ceil(sw/2)->ceil(dw/2) (pairs of output pixels share chroma),
+ *             vertical bank ceil(sh/2)->dh (chroma is interpolated vertically to full height)
+ *   - Y,U,V = (2^18 + sum mid15 * coef12) >> 19, then the table form of the matrix:
+ *       T(i)  = clip_u8(((i * cy) - (400 << 16) + 0x8000) >> 16),  cy = 65536*255/219
+ *       R = T(Y + 326 + off(V, crv)),  G = T(Y + 326 + off(U, cgu) + off(V, cgv)),  B = T(Y + 326 + off(U, cbu))
+ *       off(c, k) = ((clip_u8(c) * k) >> 16) - (k >> 9),   k = (K*65536 + 0x8000) / cy  for the BT.601 constants.
+ * The constants 326/400 are the table offsets of yuv2rgb.c for limited range; tests/test_oracle.py pins the whole
+ * function bit-for-bit against libswscale 9.1.100 (default flags and SWS_ACCURATE_RND|SWS_BITEXACT agree there).
+ */
+static int64_t vto_cdiv(int64_t a, int64_t b) { return a / b; } /* C division truncates toward zero */
+
+static int vto_rgb_T(int64_t idx) {
+    const int64_t cy = (65536LL * 255) / 219;
+    int64_t v = (idx * cy - (400LL << 16) + 0x8000) >> 16;
+    return (int)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+int vto_yuv_to_rgb24(const uint8_t *y, int y_pitch, const uint8_t *u, const uint8_t *v, int c_pitch, int c_step,
+                     int sw, int sh, uint8_t *dst, int dw, int dh) {
+    const int flags = VTO_SWS_BICUBIC;
+    const int csw = (sw + 1) / 2, csh = (sh + 1) / 2, cdw = (dw + 1) / 2;
+    const int64_t cy = (65536LL * 255) / 219;
+    const int64_t crv = vto_cdiv(104597LL * 65536 + 0x8000, cy), cbu = vto_cdiv(132201LL * 65536 + 0x8000, cy);
+    const int64_t cgu = vto_cdiv(-25675LL * 65536 + 0x8000, cy), cgv = vto_cdiv(-53279LL * 65536 + 0x8000, cy);
+    int cap_lh = vto_sws_max_taps(sw, dw, flags), cap_lv = vto_sws_max_taps(sh, dh, flags);
+    int cap_ch = vto_sws_max_taps(csw, cdw, flags), cap_cv = vto_sws_max_taps(csh, dh, flags);
+    if (cap_lh < 4) cap_lh = 4; if (cap_lv < 4) cap_lv = 4; if (cap_ch < 4) cap_ch = 4; if (cap_cv < 4) cap_cv = 4;
+    int16_t *lhc = malloc(sizeof(int16_t) * (size_t)dw * cap_lh), *lvc = malloc(sizeof(int16_t) * (size_t)dh * cap_lv);
+    int16_t *chc = malloc(sizeof(int16_t) * (size_t)cdw * cap_ch), *cvc = malloc(sizeof(int16_t) * (size_t)dh * cap_cv);
+    int32_t *lhp = malloc(4 * (size_t)dw), *lvp = malloc(4 * (size_t)dh), *chp = malloc(4 * (size_t)cdw),
+            *cvp = malloc(4 * (size_t)dh);
+    int16_t *my = malloc(sizeof(int16_t) * (size_t)dw * sh), *mu = malloc(sizeof(int16_t) * (size_t)cdw * csh),
+            *mv = malloc(sizeof(int16_t) * (size_t)cdw * csh);
+    int lht, lvt, cht, cvt, rc = -1;
+    if (!lhc || !lvc || !chc || !cvc || !lhp || !lvp || !chp || !cvp || !my || !mu || !mv) goto done;
+    if (vto_sws_make_filter(sw, dw, flags, 1 << 14, lhc, lhp, &lht) || vto_sws_make_filter(sh, dh, flags, 1 << 12, lvc, lvp, &lvt) ||
+        vto_sws_make_filter(csw, cdw, flags, 1 << 14, chc, chp, &cht) || vto_sws_make_filter(csh, dh, flags, 1 << 12, cvc, cvp, &cvt))
+        goto done;
+    for (int r = 0; r < sh; r++) vto_hscale_row(y + (size_t)r * y_pitch, my + (size_t)r * dw, dw, lhc, lhp, lht);
+    for (int r = 0; r < csh; r++)
+        for (int x = 0; x < cdw; x++) {
+            int au = 0, av = 0;
+            for (int j = 0; j < cht; j++) {
+                au += (int)u[(size_t)r * c_pitch + (size_t)(chp[x] + j) * c_step] * chc[(size_t)x * cht + j];
+                av += (int)v[(size_t)r * c_pitch + (size_t)(chp[x] + j) * c_step] * chc[(size_t)x * cht + j];
+            }
+            au >>= 7; av >>= 7;
+            mu[(size_t)r * cdw + x] = (int16_t)(au > 32767 ? 32767 : au);
+            mv[(size_t)r * cdw + x] = (int16_t)(av > 32767 ? 32767 : av);
+        }
+    for (int yy = 0; yy < dh; yy++)
+        for (int x = 0; x < dw; x++) {
+            int Y = 1 << 18, U = 1 << 18, V = 1 << 18;
+            for (int j = 0; j < lvt; j++) Y += my[(size_t)(lvp[yy] + j) * dw + x] * lvc[(size_t)yy * lvt + j];
+            for (int j = 0; j < cvt; j++) {
+                U += mu[(size_t)(cvp[yy] + j) * cdw + x / 2] * cvc[(size_t)yy * cvt + j];
+                V += mv[(size_t)(cvp[yy] + j) * cdw + x / 2] * cvc[(size_t)yy * cvt + j];
+            }
+            Y >>= 19; U >>= 19; V >>= 19;
+            int64_t Uc = U < 0 ? 0 : (U > 255 ? 255 : U), Vc = V < 0 ? 0 : (V > 255 ? 255 : V);
+            uint8_t *d = dst + ((size_t)yy * dw + x) * 3;
+            d[0] = (uint8_t)vto_rgb_T(Y + 326 + ((Vc * crv) >> 16) - (crv >> 9));
+            d[1] = (uint8_t)vto_rgb_T(Y + 326 + ((Uc * cgu) >> 16) - (cgu >> 9) + ((Vc * cgv) >> 16) - (cgv >> 9));
+            d[2] = (uint8_t)vto_rgb_T(Y + 326 + ((Uc * cbu) >> 16) - (cbu >> 9));
+        }
+    rc = 0;
+done:
+    free(lhc); free(lvc); free(chc); free(cvc); free(lhp); free(lvp); free(chp); free(cvp); free(my); free(mu); free(mv);
+    return rc;
+}

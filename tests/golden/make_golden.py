@@ -8,6 +8,9 @@ Outputs (tests/golden/):
                       Python (/root/reference/src/utils/video_segmenter.py, budget_planner.py), floats as hex
   sws_vectors.npz     libswscale 9.1.100 outputs (SWS_ACCURATE_RND|SWS_BITEXACT and default flags) for seeded
                       planes, the pin for oracle/vt_oracle.c and the CUDA scaler
+  sws_rgb_vectors.npz libswscale 9.1.100 nv12 -> rgb24 outputs (same size and scaled, default flags = what
+                      `ffmpeg -vf scale=W:H -pix_fmt rgb24` produces), the pin for vto_yuv_to_rgb24 / K1b
+                      (`python tests/golden/make_golden.py rgb` regenerates only this file)
 """
 import json
 import os
@@ -116,7 +119,32 @@ def sws_vectors():
     return out
 
 
+def sws_rgb_vectors():
+    rng = np.random.default_rng(2026)
+    out = {}
+    for name, (sw, sh, dw, dh) in {"a": (64, 48, 64, 48), "b": (128, 72, 64, 36), "c": (160, 90, 96, 96),
+                                   "d": (101, 61, 78, 52), "e": (192, 108, 48, 48)}.items():
+        pitch = (sw + 15) // 16 * 16
+        buf = rng.integers(0, 256, (sh + (sh + 1) // 2, pitch), dtype=np.uint8)
+        if name == "c":                      # limited-range content with flat areas, like real video
+            buf[:sh] = np.clip(buf[:sh], 16, 235)
+            buf[: sh // 3, : sw // 2] = 235
+            buf[sh:] = np.clip(buf[sh:], 16, 240)
+        out[name + "_nv12"] = buf
+        out[name + "_dims"] = np.array([sw, sh, pitch, dw, dh])
+        y, uv = buf[:sh, :sw], buf[sh:, : 2 * ((sw + 1) // 2)]
+        out[name + "_rgb"] = ffsws.nv12_to_rgb24(y, uv, dw, dh, ffsws.SWS_BICUBIC)
+        out[name + "_rgb_bitexact"] = ffsws.nv12_to_rgb24(y, uv, dw, dh, ffsws.SWS_BICUBIC | ffsws.SWS_ACCURATE_RND |
+                                                          ffsws.SWS_BITEXACT)
+    return out
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["rgb"]:
+        np.savez_compressed(os.path.join(HERE, "sws_rgb_vectors.npz"), swscale_version=np.array(ffsws.version()),
+                            **sws_rgb_vectors())
+        print("wrote sws_rgb_vectors.npz")
+        sys.exit(0)
     import pathlib
     import tempfile
     bv, est = budget_vectors()
@@ -128,4 +156,6 @@ if __name__ == "__main__":
         json.dump(doc, f, indent=0, sort_keys=True)
     np.savez_compressed(os.path.join(HERE, "sws_vectors.npz"), swscale_version=np.array(ffsws.version()),
                         **sws_vectors())
+    np.savez_compressed(os.path.join(HERE, "sws_rgb_vectors.npz"), swscale_version=np.array(ffsws.version()),
+                        **sws_rgb_vectors())
     print("wrote", os.listdir(HERE))

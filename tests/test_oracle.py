@@ -96,3 +96,28 @@ def test_scene_oracle_and_product_agree():
                 scene_oracle.frames_for_window(s, e, 18000, 30, 1, kf, sc)
             assert scene.frames_for_window(s, e, 17982, 30000, 1001, kf, sc) == \
                 scene_oracle.frames_for_window(s, e, 17982, 30000, 1001, kf, sc)
+
+
+RGB_GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "sws_rgb_vectors.npz"))
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c", "d", "e"])
+def test_rgb_oracle_equals_committed_libswscale_output(oracle_c, name):
+    """vto_yuv_to_rgb24 (K1b / config 5) is bit-exact against libswscale's nv12 -> rgb24, default and bit-exact flags."""
+    sw, sh, pitch, dw, dh = (int(v) for v in RGB_GOLD[name + "_dims"])
+    got = oracle_c.nv12_to_rgb24(RGB_GOLD[name + "_nv12"].reshape(-1), sw, sh, pitch, dw, dh)
+    assert np.array_equal(got, RGB_GOLD[name + "_rgb"])
+    assert np.array_equal(got, RGB_GOLD[name + "_rgb_bitexact"])
+
+
+@pytest.mark.parametrize("sw,sh,dw,dh", [(1280, 720, 768, 768), (1920, 1080, 768, 768), (320, 240, 320, 240),
+                                         (641, 363, 322, 182)])
+def test_rgb_oracle_equals_live_libswscale(oracle_c, sw, sh, dw, dh):
+    from oracle import ffsws
+    if not ffsws.available():
+        pytest.skip("libswscale not present in this image")
+    rng = np.random.default_rng(sw + dh)
+    pitch = (sw + 15) // 16 * 16
+    buf = rng.integers(0, 256, (sh + (sh + 1) // 2, pitch), dtype=np.uint8)
+    exp = ffsws.nv12_to_rgb24(buf[:sh, :sw], buf[sh:, : 2 * ((sw + 1) // 2)], dw, dh, ffsws.SWS_BICUBIC)
+    assert np.array_equal(oracle_c.nv12_to_rgb24(buf.reshape(-1), sw, sh, pitch, dw, dh), exp)
