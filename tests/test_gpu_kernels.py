@@ -104,7 +104,7 @@ def test_headline_shapes_take_the_streaming_kernel(cuda, sw, sh, dw, dh):
     for chroma in (False, True):
         info = plan.stream_info(chroma)
         assert info["streaming"] == 1, info
-        assert info["tile_w"] <= 256 and info["tile_w"] % 16 == 0
+        assert info["tile_w"] <= 1024 and info["tile_w"] % 16 == 0
 
 
 def test_streaming_and_generic_kernels_agree_on_a_batch(cuda, oracle_c):

@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Kernel micro-bench: each hot kernel launched back to back on synthetic device-resident 1080p NV12 surfaces.
+usage: python tools/kbench.py [--frames 256] [--reps 10] [--src 1920x1080] [--dst-h 720] [--kernels scale,score]"""
+import argparse, json, os, sys
+from ctypes import c_void_p
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from video_transformer_b200 import _lib, ops
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--frames", type=int, default=256)
+ap.add_argument("--reps", type=int, default=10)
+ap.add_argument("--src", default="1920x1080")
+ap.add_argument("--dst-h", type=int, default=720)
+ap.add_argument("--kernels", default="scale,score,convert")
+a = ap.parse_args()
+sw, sh = (int(v) for v in a.src.split("x"))
+dh = a.dst_h
+dw = ops.scale_width_for_height(sw, sh, dh)
+L = _lib.lib()
+dev = torch.device("cuda:0")
+F = a.frames
+pitch = (sw + 255) // 256 * 256
+rows = sh + sh // 2
+surf = torch.randint(0, 256, (F, rows, pitch), dtype=torch.uint8, device=dev)
+fb = dw * dh * 3 // 2
+out = torch.empty((F, fb), dtype=torch.uint8, device=dev)
+sad = torch.empty(F, dtype=torch.int64, device=dev)
+hist = torch.empty((F, 256), dtype=torch.int32, device=dev)
+plan = ops.ScalePlan(sw, sh, dw, dh, ops.SWS_BICUBIC)
+st = torch.cuda.current_stream(dev)
+sp = c_void_p(st.cuda_stream)
+peak = 6531.9
+try:
+    peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+
+def run(name, fn, alg_bytes):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(a.reps):
+        fn()
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.reps
+    gbs = alg_bytes * F / (ms * 1e-3) / 1e9
+    print(json.dumps({"kernel": name, "ms": round(ms, 4), "us_per_picture": round(1000 * ms / F, 4), "alg_gbs": round(gbs, 1),
+                      "frac_of_measured_peak": round(gbs / peak, 4), "frames": F, "shape": "%dx%d->%dx%d" % (sw, sh, dw, dh)}))
+
+ks = a.kernels.split(",")
+if "scale" in ks:
+    run("scale", lambda: _lib.check(L.vt_scale_nv12_to_yuv420p(plan._h, c_void_p(surf.data_ptr()), pitch, rows * pitch,
+        c_void_p(out.data_ptr()), fb, F, sp)), sw * sh * 3 // 2 + fb)
+    print(plan.stream_info(False), plan.stream_info(True))
+if "score" in ks:
+    run("score", lambda: _lib.check(L.vt_sad_hist_u8(c_void_p(surf.data_ptr()), pitch, rows * pitch, sw, sh, None, F,
+        c_void_p(sad.data_ptr()), c_void_p(hist.data_ptr()), sp)), 2 * sw * sh)
+if "convert" in ks:
+    out2 = torch.empty((F, sw * sh * 3 // 2), dtype=torch.uint8, device=dev)
+    run("nv12_to_yuv420p", lambda: _lib.check(L.vt_nv12_to_yuv420p(c_void_p(surf.data_ptr()), pitch, rows * pitch, sw, sh,
+        c_void_p(out2.data_ptr()), sw * sh * 3 // 2, F, sp)), sw * sh * 3)

@@ -6,7 +6,7 @@ import os
 from ctypes import POINTER, c_char_p, c_int, c_int32, c_size_t, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvtseg.so")
+LIB_PATH = os.environ.get("VT_LIB") or os.path.join(_HERE, "libvtseg.so")   # VT_LIB: measurement builds only
 
 VT_OK = 0
 VT_ERR_INVALID, VT_ERR_CUDA, VT_ERR_UNSUPPORTED, VT_ERR_BITSTREAM, VT_ERR_NOMEM, VT_ERR_NVDEC = -1, -2, -3, -4, -5, -6

@@ -16,39 +16,13 @@
 //                register ring, so intermediates never touch memory.  NV12 chroma is de-interleaved with
 //                PRMT on the way.  HBM traffic = source once + destination once.
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 #include <vector>
 
-#include "vt_common.cuh"
-
-struct vt_scale_plan {
-    int sw, sh, dw, dh, flags;
-    int csw, csh, cdw, cdh;  // chroma plane sizes
-    // filter banks in device memory; index 0 = luma, 1 = chroma
-    int htaps[2], vtaps[2];
-    int16_t *hcoef[2];  // dw x htaps
-    int32_t *hpos[2];
-    int16_t *vcoef[2];  // dh x vtaps
-    int32_t *vpos[2];
-    int16_t *scratch;  // generic path: dw x sh int16
-    // host copies (streaming path work-list construction)
-    std::vector<int16_t> h_hcoef[2], h_vcoef[2];
-    std::vector<int32_t> h_hpos[2], h_vpos[2];
-    // streaming path (one per plane kind): tables built by build_stream() at plan creation
-    struct Stream {
-        bool ok = false;
-        int hp = 0, tv = 0;     // dp2a pairs per output, (padded) vertical taps -> kernel instantiation
-        int cpt = 0;            // output columns per lane (per channel)
-        int strip_cols = 0, n_strips = 0;
-        int rows_out = 0, n_chunks = 0;
-        int tile_w = 0, tile_h = 0;
-        int warp_smem = 0;
-        int32_t *strip_x0 = nullptr;   // n_strips: first source byte of each strip's tile (multiple of 16)
-        uint32_t *lane_tab = nullptr;  // (n_strips*strip_cols) x (1+hp): source byte of tap 0, packed coef pairs
-        int32_t *vtab = nullptr;       // dh x (2+tv): first source row, last source row, front-padded coefs
-    } stream[2];
-};
+#include "vt_scale_plan.cuh"
 
 namespace vt {
 
@@ -329,9 +303,12 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
+}  // namespace
+
 // 3-D byte tensor (x bytes, rows, frames) with a (tile_w, tile_h, 1) box, no swizzle, zero fill outside.
-int make_tmap(CUtensorMap *m, const uint8_t *base, int row_bytes, int rows, int n_frames, int pitch, size_t frame_stride,
+int vt::make_tmap_u8_3d(void *tmap_out, const uint8_t *base, int row_bytes, int rows, int n_frames, int pitch, size_t frame_stride,
               int tile_w, int tile_h) {
+    CUtensorMap *m = (CUtensorMap *)tmap_out;
     EncodeTiledFn enc = encode_tiled();
     if (!enc) {
         vt::set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -350,6 +327,38 @@ int make_tmap(CUtensorMap *m, const uint8_t *base, int row_bytes, int rows, int 
         return VT_ERR_CUDA;
     }
     return VT_OK;
+}
+
+// The same tensor seen as 32-bit elements (rows padded up to a multiple of 4 bytes, which the pitch covers), so that a
+// box row can be up to 1024 bytes; x coordinates are then in units of 4 bytes.
+int vt::make_tmap_u32_3d(void *tmap_out, const uint8_t *base, int row_bytes, int rows, int n_frames, int pitch,
+                         size_t frame_stride, int tile_w, int tile_h) {
+    CUtensorMap *m = (CUtensorMap *)tmap_out;
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) {
+        vt::set_error("cuTensorMapEncodeTiled not available from the driver");
+        return VT_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)((row_bytes + 3) / 4), (cuuint64_t)rows, (cuuint64_t)n_frames};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frame_stride};
+    cuuint32_t box[3] = {(cuuint32_t)(tile_w / 4), (cuuint32_t)tile_h, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        vt::set_error("cuTensorMapEncodeTiled(u32) failed (%d) row_bytes=%d rows=%d pitch=%d box=%dx%d", (int)r, row_bytes,
+                      rows, pitch, tile_w, tile_h);
+        return VT_ERR_CUDA;
+    }
+    return VT_OK;
+}
+
+namespace {
+
+int make_tmap(CUtensorMap *m, const uint8_t *base, int row_bytes, int rows, int n_frames, int pitch, size_t frame_stride,
+              int tile_w, int tile_h) {
+    return vt::make_tmap_u8_3d(m, base, row_bytes, rows, n_frames, pitch, frame_stride, tile_w, tile_h);
 }
 
 int pad_hp(int taps) {
@@ -505,6 +514,12 @@ int launch_stream(const vt_scale_plan *p, int c, const uint8_t *src, int pitch, 
 
 extern "C" int vt_scale_plan_stream_info(const vt_scale_plan *p, int chroma, int *info8) {
     if (!p || !info8) return VT_ERR_INVALID;
+    const vt_scale_plan::Pair &pr = p->pair[chroma ? 1 : 0];
+    if (p->pair[0].ok && p->pair[1].ok) {
+        info8[0] = 1; info8[1] = pr.hp; info8[2] = pr.tv; info8[3] = 2 * pr.np; info8[4] = pr.stage_rows;
+        info8[5] = pr.tile_w; info8[6] = pr.stage_rows * pr.n_stages; info8[7] = pr.warp_smem;
+        return VT_OK;
+    }
     const vt_scale_plan::Stream &s = p->stream[chroma ? 1 : 0];
     info8[0] = s.ok; info8[1] = s.hp; info8[2] = s.tv; info8[3] = s.cpt; info8[4] = s.rows_out; info8[5] = s.tile_w;
     info8[6] = s.tile_h; info8[7] = s.warp_smem;
@@ -535,6 +550,7 @@ extern "C" int vt_scale_plan_create(int sw, int sh, int dw, int dh, int flags, v
     if (rc == VT_OK && cudaMalloc((void **)&p->scratch, (size_t)dw * sh * sizeof(int16_t)) != cudaSuccess)
         rc = VT_ERR_NOMEM;
     for (int c = 0; c < 2 && rc == VT_OK; c++) rc = build_stream(p, c);
+    for (int c = 0; c < 2 && rc == VT_OK; c++) rc = vt::build_pair(p, c);
     if (rc != VT_OK) {
         vt::set_error("vt_scale_plan_create: failed (%d) for %dx%d -> %dx%d flags=0x%x", rc, sw, sh, dw, dh, flags);
         vt_scale_plan_destroy(p);
@@ -550,6 +566,7 @@ extern "C" void vt_scale_plan_destroy(vt_scale_plan *p) {
         cudaFree(p->hcoef[c]); cudaFree(p->hpos[c]); cudaFree(p->vcoef[c]); cudaFree(p->vpos[c]);
         cudaFree(p->stream[c].strip_x0); cudaFree(p->stream[c].lane_tab); cudaFree(p->stream[c].vtab);
     }
+    vt::free_pair(p);
     cudaFree(p->scratch);
     delete p;
 }
@@ -573,7 +590,16 @@ extern "C" int vt_scale_nv12_to_yuv420p(const vt_scale_plan *p, const uint8_t *s
     const size_t ysz = (size_t)p->dw * p->dh, csz = (size_t)p->cdw * p->cdh;
     const bool aligned = ((uintptr_t)src % 16 == 0) && (src_pitch % 16 == 0) && (src_fs % 16 == 0) &&
                          ((uintptr_t)dst % 4 == 0) && (dst_fs % 4 == 0) && (p->sw % 2 == 0) && (p->sh % 2 == 0);
-    if (aligned && p->stream[0].ok && p->stream[1].ok) {
+    // VT_SCALE_KERNEL=stream|generic selects the older kernels (A/B measurements only)
+    static const char *force = getenv("VT_SCALE_KERNEL");
+    const bool want_pair = !force || !strcmp(force, "pair");
+    const bool want_stream = !force || !strcmp(force, "stream");
+    if (aligned && want_pair && p->pair[0].ok && p->pair[1].ok) {
+        int rc = vt::launch_pair(p, 0, src, src_pitch, src_fs, dst, dst_fs, n_frames, st);
+        if (rc) return rc;
+        return vt::launch_pair(p, 1, src, src_pitch, src_fs, dst, dst_fs, n_frames, st);
+    }
+    if (aligned && want_stream && p->stream[0].ok && p->stream[1].ok) {
         int rc = launch_stream(p, 0, src, src_pitch, src_fs, dst, dst_fs, n_frames, st);
         if (rc) return rc;
         return launch_stream(p, 1, src, src_pitch, src_fs, dst, dst_fs, n_frames, st);

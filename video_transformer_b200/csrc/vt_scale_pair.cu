@@ -1,0 +1,524 @@
+// vt_scale_pair.cu -- K2 production kernel: libswscale-exact separable polyphase downscale of NV12 -> YUV420P
+// (arithmetic stated in vt_scale.cu).  The reference reaches this work
+// through `ffmpeg -vf scale=-2:360` (/root/reference/src/analyzer/content_analyzer.py:193-211).
+//
+// Shape of the kernel (everything below is about instruction count: the pass is issue-bound, not DRAM-bound):
+//   * one warp owns a strip of output columns and walks DOWN a segment of output rows; its source rows arrive
+//     through a private TMA ring (cp.async.bulk.tensor 3-D boxes, one mbarrier per stage), so every source
+//     byte is read from HBM once and there is no block-level synchronisation at all;
+//   * a lane owns PAIRS of adjacent output columns (x, x+1).  The even column's taps are aligned with funnel
+//     shifts and run through dp2a (two 14-bit coefficients x two pixels per instruction).  The odd column
+//     starts 0..3 source samples further right, so it re-uses the SAME aligned words with its coefficients
+//     rotated into place (one more dp2a, no loads, no shifts);
+//   * the 15-bit horizontal results live in a register ring of TV rows (slot = source row mod TV, static
+//     because the row loop is unrolled by TV); whenever a source row completes an output row's window the
+//     vertical taps run out of that ring.  Vertical coefficients and the "window ends at row" schedule sit in
+//     KERNEL PARAMETER space (constant bank), are fetched with uniform loads and feed IMAD directly as uniform
+//     register operands, so the vertical pass costs no shared-memory traffic and its branch is warp-uniform;
+//   * results are clamped and packed with cvt.pack.sat (I2IP) and leave as 16-bit stores;
+//   * a ragged right edge is handled by sliding the last strip left until it ends at the last column (the
+//     overlap is computed twice with identical results), so there is no per-store bounds predicate.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "vt_scale_plan.cuh"
+
+// VT_ABLATE (measurement builds only, results are wrong): 1 no vertical taps, 2 no horizontal taps, 4 no tile loads,
+// 8 no stores
+#ifndef VT_ABLATE
+#define VT_ABLATE 0
+#endif
+
+namespace vt {
+
+template <int TV>
+struct VCfg {
+    static constexpr int STRIDE = (TV + 1 + 3) & ~3;  // coefficients[TV] (front padded), last source row, padding
+    static constexpr int ROWS = 28672 / (STRIDE * 4); // output rows one launch can cover (parameter space is 32 KB)
+};
+template <int TV>
+struct __align__(16) VTab {
+    int32_t t[VCfg<TV>::ROWS * VCfg<TV>::STRIDE];
+};
+
+struct PairArgs {
+    const uint32_t *lane_tab;
+    const int32_t *box_x0;             // n_strips x n_boxes: first source byte of each TMA box (multiple of 16)
+    const int32_t *strip_col;          // n_strips: first output column of each strip
+    uint8_t *dst;                      // frame 0: first byte of the Y plane (luma) or of the U plane (chroma)
+    unsigned long long dst_fs;         // bytes between output frames
+    unsigned long long dst_plane2;     // chroma: U plane -> V plane
+    int n_frames, n_strips, n_segs, seg_rows;
+    int dw;                            // output width of this plane kind
+    int y_begin, y_end;                // output rows covered by this launch (vtab row 0 = y_begin)
+    int tile_w;                        // bytes per box row (always PAIR_TILE_W)
+    int n_boxes;                       // TMA boxes per stage
+    int groups_per_stage;              // a stage holds groups_per_stage * TV source rows
+    int box_bytes, stage_bytes, n_stages, warp_smem;
+    int round_bias;                    // 1 << 18 (the vertical pass's rounding term)
+};
+
+__device__ __forceinline__ int dp2a_lo(uint32_t coef_pair, uint32_t pix, int acc) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(coef_pair), "r"(pix), "r"(acc));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi(uint32_t coef_pair, uint32_t pix, int acc) {
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(coef_pair), "r"(pix), "r"(acc));
+    return d;
+}
+// sum over i < N of coefficient pair i times halfword i of the byte string w[]
+template <int N>
+__device__ __forceinline__ int dot_halfwords(const uint32_t (&c)[N], const uint32_t *w) {
+    int v = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) v = (i & 1) ? dp2a_hi(c[i], w[i >> 1], v) : dp2a_lo(c[i], w[i >> 1], v);
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// (sat_u8(hi) << 8) | sat_u8(lo)
+__device__ __forceinline__ uint32_t pack_sat_u8x2(int hi, int lo) {
+    uint32_t d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(lo), "r"(0u));
+    return d;
+}
+__device__ __forceinline__ void st_u16(uint8_t *p, uint32_t v) {
+    if (VT_ABLATE & 8) {
+        if (v == 0x12345u) asm volatile("st.global.L1::no_allocate.u16 [%0], %1;" ::"l"(p), "h"((unsigned short)v) : "memory");
+        return;
+    }
+    asm volatile("st.global.L1::no_allocate.u16 [%0], %1;" ::"l"(p), "h"((unsigned short)v) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(phase)
+        : "memory");
+}
+
+constexpr uint32_t PAIR_TILE_W = 448;   // bytes per row of every TMA box (tensor of 32-bit elements: up to 1024 B per box row)
+
+__host__ __device__ constexpr int pair_np(int hp, int tv) { return (hp <= 3 && tv <= 8) ? 4 : 2; }         // luma pairs per lane
+__host__ __device__ constexpr int pair_min_blocks(int hp, int tv) { return pair_np(hp, tv) == 4 ? 5 : (tv <= 8 ? 5 : 3); }
+
+// HP  dp2a pairs of the even column (taps padded to 2*HP); the odd column uses HP+1 pairs (rotated coefficients)
+// TV  vertical taps (front padded); UV: the source is NV12's interleaved chroma plane, a lane produces U and V
+template <int HP, int TV, bool UV>
+__global__ void __launch_bounds__(128, pair_min_blocks(HP, TV))
+scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ PairArgs a,
+                  const __grid_constant__ VTab<TV> vtab) {
+    constexpr int BN = HP + 1;
+    constexpr int NP = UV ? pair_np(HP, TV) / 2 : pair_np(HP, TV);   // column pairs per lane
+    constexpr int NCH = UV ? 2 : 1;
+    constexpr int NM = NP * 2 * NCH;                  // horizontal results per lane per source row
+    constexpr int NAW = UV ? BN : (BN + 1) / 2;       // aligned 32-bit words holding a pair's source samples
+    constexpr int NW = NAW + 1;                       // words fetched (one extra for the byte misalignment)
+    constexpr int NQ = (NAW + 1) / 2;                 // chroma: de-interleaved words per channel
+    constexpr int LT = (2 * HP + 2 + 3) & ~3;         // words per lane-table entry
+    constexpr int VS = VCfg<TV>::STRIDE;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform for the compiler
+    uint8_t *wbase = smem + (size_t)warp * a.warp_smem;
+    const uint32_t wsm = smem_u32(wbase);
+    const int nst = a.n_stages;
+    const int rg = a.groups_per_stage;
+    const int stage_rows = rg * TV;
+    uint64_t *bars = (uint64_t *)(wbase + (size_t)nst * a.stage_bytes);
+    if (lane == 0) {
+        for (int s = 0; s < nst; s++) mbar_init(&bars[s], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    const uint32_t bar0 = smem_u32(bars);
+    constexpr uint32_t group_bytes = (uint32_t)TV * PAIR_TILE_W;   // tile rows are PAIR_TILE_W bytes apart: row offsets
+    uint32_t phases = 0;                                           // inside a group are immediates of the loads
+    const uint32_t stage_tx = (uint32_t)(stage_rows * PAIR_TILE_W * a.n_boxes);
+    const int per_frame = a.n_strips * a.n_segs;
+    const long long total = (long long)per_frame * a.n_frames;
+    const long long nwarps = (long long)gridDim.x * 4;
+    for (long long it = (long long)blockIdx.x * 4 + warp; it < total; it += nwarps) {
+        const int f = (int)(it / per_frame);
+        const int rem = (int)(it - (long long)f * per_frame);
+        const int seg = rem / a.n_strips, strip = rem - seg * a.n_strips;
+        const int y0 = a.y_begin + seg * a.seg_rows;
+        const int y1 = min(a.y_end, y0 + a.seg_rows);
+        int vi = (y0 - a.y_begin) * VS;
+        const int rs = vtab.t[vi + TV] - (TV - 1);                          // first source row of the segment's windows
+        const int nrows = vtab.t[(y1 - 1 - a.y_begin) * VS + TV] + 1 - rs;  // source rows the segment needs
+        const int ngroups = (nrows + TV - 1) / TV;
+        const int nloads = (ngroups + rg - 1) / rg;
+        __syncwarp();                                                        // previous item's tiles are no longer read
+        if (lane == 0) {
+            const int pre = min(nst, nloads);
+#pragma unroll 1
+            for (int s = 0; s < pre; s++) {
+                mbar_expect_tx(&bars[s], stage_tx);
+#pragma unroll 1
+                for (int b = 0; b < a.n_boxes; b++)
+                    tma_load_3d(wbase + (size_t)s * a.stage_bytes + (size_t)b * a.box_bytes, &tmap, &bars[s],
+                                a.box_x0[strip * a.n_boxes + b] >> 2, rs + s * stage_rows, f);
+            }
+        }
+        // this lane's column pairs
+        uint32_t addr[NP], shb[NP], ca[NP][HP], cb[NP][BN];
+#pragma unroll
+        for (int g = 0; g < NP; g++) {
+            const uint4 *t4 = reinterpret_cast<const uint4 *>(a.lane_tab + ((size_t)(strip * NP + g) * 32 + lane) * LT);
+            uint32_t wd[LT];
+#pragma unroll
+            for (int i = 0; i < LT / 4; i++) {
+                const uint4 q = __ldg(t4 + i);
+                wd[4 * i] = q.x; wd[4 * i + 1] = q.y; wd[4 * i + 2] = q.z; wd[4 * i + 3] = q.w;
+            }
+            addr[g] = wsm + (wd[0] & ~3u);           // wd[0]: byte offset of the pair's tap 0 inside a stage (row 0)
+            shb[g] = (wd[0] & 3u) * 8u;
+#pragma unroll
+            for (int i = 0; i < HP; i++) ca[g][i] = wd[1 + i];
+#pragma unroll
+            for (int i = 0; i < BN; i++) cb[g][i] = wd[1 + HP + i];
+        }
+        int m[TV][NM];
+#pragma unroll
+        for (int k = 0; k < TV; k++)
+#pragma unroll
+            for (int c = 0; c < NM; c++) m[k][c] = 0;
+
+        const int rnd = a.round_bias;                                        // 1 << 18, from the parameters so that it lives in a
+                                                                             // register and every tap is IMAD acc, m, UR(coef), acc
+        int y = y0;
+        int vrel = TV - 1;                                                   // row (relative to the current group) completing row y
+        int vc[TV];
+#pragma unroll
+        for (int j = 0; j < TV; j++) vc[j] = vtab.t[vi + j];
+        uint8_t *dptr = a.dst + (size_t)f * a.dst_fs + (size_t)y0 * a.dw + (size_t)a.strip_col[strip] + 2 * lane;
+
+        uint32_t ga[NP];
+        auto hpass = [&](int k, int (&out)[NM]) {                            // horizontal pass of the group's row k
+#pragma unroll
+            for (int g = 0; g < NP; g++) {
+                uint32_t w[NW], al[NAW];
+#pragma unroll
+                for (int i = 0; i < NW; i++)
+                    w[i] = (VT_ABLATE & 4) ? ga[g] * (uint32_t)(k + i + 1) : lds_u32(ga[g] + (uint32_t)k * PAIR_TILE_W + 4u * i);
+#pragma unroll
+                for (int i = 0; i < NAW; i++) al[i] = __funnelshift_r(w[i], w[i + 1], shb[g]);
+                if (VT_ABLATE & 2) {
+#pragma unroll
+                    for (int c = 0; c < NM / NP; c++) out[NM / NP * g + c] = (int)(al[c % NAW] ^ ca[g][c % HP]);
+                } else if (!UV) {
+                    out[2 * g] = min(dot_halfwords<HP>(ca[g], al) >> 7, 32767);
+                    out[2 * g + 1] = min(dot_halfwords<BN>(cb[g], al) >> 7, 32767);
+                } else {
+                    uint32_t uw[NQ], vw[NQ];
+#pragma unroll
+                    for (int q = 0; q < NQ; q++) {
+                        const uint32_t hi = (2 * q + 1 < NAW) ? al[2 * q + 1] : al[2 * q];
+                        uw[q] = __byte_perm(al[2 * q], hi, 0x6420);
+                        vw[q] = __byte_perm(al[2 * q], hi, 0x7531);
+                    }
+                    out[4 * g] = min(dot_halfwords<HP>(ca[g], uw) >> 7, 32767);
+                    out[4 * g + 1] = min(dot_halfwords<BN>(cb[g], uw) >> 7, 32767);
+                    out[4 * g + 2] = min(dot_halfwords<HP>(ca[g], vw) >> 7, 32767);
+                    out[4 * g + 3] = min(dot_halfwords<BN>(cb[g], vw) >> 7, 32767);
+                }
+            }
+        };
+        auto vstore = [&](const int (&acc)[NM]) {                            // clamp, pack and store output row y
+#pragma unroll
+            for (int g = 0; g < NP; g++) {
+                if (!UV) {
+                    st_u16(dptr + 64 * g, pack_sat_u8x2(acc[2 * g + 1] >> 19, acc[2 * g] >> 19));
+                } else {
+                    st_u16(dptr + 64 * g, pack_sat_u8x2(acc[4 * g + 1] >> 19, acc[4 * g] >> 19));
+                    st_u16(dptr + a.dst_plane2 + 64 * g, pack_sat_u8x2(acc[4 * g + 3] >> 19, acc[4 * g + 2] >> 19));
+                }
+            }
+        };
+        int rbase = rs;                                                      // absolute source row of the group's row 0
+        auto advance = [&]() -> bool {                                       // next output row; false when the item is done
+            y++;
+            dptr += a.dw;
+            if (y >= y1) return false;
+            vi += VS;
+            vrel = vtab.t[vi + TV] - rbase;
+#pragma unroll
+            for (int j = 0; j < TV; j++) vc[j] = vtab.t[vi + j];
+            return true;
+        };
+        int s = 0, gis = 0, ld = 0;                                          // stage, group inside the stage, load index
+        for (int gi = 0; gi < ngroups; gi++) {
+            if (gis == 0) {
+                mbar_wait_u32(bar0 + 8u * (uint32_t)s, (phases >> s) & 1u);
+                phases ^= 1u << s;
+            }
+            const uint32_t goff = (uint32_t)s * (uint32_t)a.stage_bytes + (uint32_t)gis * group_bytes;
+#pragma unroll
+            for (int g = 0; g < NP; g++) ga[g] = addr[g] + goff;
+#pragma unroll
+            for (int k = 0; k < TV; k++) {
+                hpass(k, m[k]);
+                // ---- vertical pass for every output row whose window ends at this source row
+                while (vrel == k) {
+                    int acc[NM];
+#pragma unroll
+                    for (int c = 0; c < NM; c++) acc[c] = rnd;
+#pragma unroll
+                    for (int j = 0; j < ((VT_ABLATE & 1) ? 1 : TV); j++) {
+#pragma unroll
+                        for (int c = 0; c < NM; c++) acc[c] += m[(k + 1 + j) % TV][c] * vc[j];
+                    }
+                    vstore(acc);
+                    if (!advance()) goto item_done;                          // the rest of this group's rows feed nothing
+                }
+            }
+            vrel -= TV;
+            rbase += TV;
+            gis++;
+            if (gis == rg || gi == ngroups - 1) {
+                __syncwarp();                                                // every lane is done with this stage
+                if (lane == 0 && ld + nst < nloads) {
+                    mbar_expect_tx(&bars[s], stage_tx);
+#pragma unroll 1
+                    for (int b = 0; b < a.n_boxes; b++)
+                        tma_load_3d(wbase + (size_t)s * a.stage_bytes + (size_t)b * a.box_bytes, &tmap, &bars[s],
+                                    a.box_x0[strip * a.n_boxes + b] >> 2, rs + (ld + nst) * stage_rows, f);
+                }
+                ld++;
+                gis = 0;
+                s = s + 1 == nst ? 0 : s + 1;
+            }
+        }
+    item_done:;
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+namespace {
+
+int pad_hp(int taps) {
+    const int hp = (taps + 1) / 2;
+    return hp <= 3 ? 3 : (hp <= 4 ? 4 : (hp <= 6 ? 6 : 0));
+}
+int pad_tv(int taps) { return taps < 2 ? 0 : (taps <= 6 ? 6 : (taps <= 8 ? 8 : (taps <= 12 ? 12 : 0))); }
+int vstride_for(int tv) { return (tv + 1 + 3) & ~3; }
+
+int upload(const void *h, size_t n, void **d) {
+    if (cudaMalloc(d, n ? n : 1) != cudaSuccess) return VT_ERR_NOMEM;
+    if (n && cudaMemcpy(*d, h, n, cudaMemcpyHostToDevice) != cudaSuccess) return VT_ERR_CUDA;
+    return VT_OK;
+}
+
+template <int HP, int TV, bool UV>
+int launch_t(const vt_scale_plan::Pair &s, const CUtensorMap &tm, PairArgs a, int rows_total, cudaStream_t st) {
+    auto k = scale_pair_kernel<HP, TV, UV>;
+    static int smem_set = 0, blocks_per_sm = 0;
+    const int smem = s.warp_smem * 4;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (smem > smem_set || !blocks_per_sm) {
+        VT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        VT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k, 128, smem));
+        if (blocks_per_sm < 1) {
+            set_error("scale_pair_kernel<%d,%d,%d>: does not fit an SM (smem %d)", HP, TV, (int)UV, smem);
+            return VT_ERR_UNSUPPORTED;
+        }
+        smem_set = smem;
+    }
+    static VTab<TV> vt_host;                 // 28 KB staging for the parameter copy; filled under the launch lock
+    const int cap = VCfg<TV>::ROWS;
+    for (int yb = 0; yb < rows_total; yb += cap) {
+        const int ye = std::min(rows_total, yb + cap);
+        std::memcpy(vt_host.t, s.vtab.data() + (size_t)yb * s.vstride, (size_t)(ye - yb) * s.vstride * sizeof(int32_t));
+        a.y_begin = yb;
+        a.y_end = ye;
+        const int rows = ye - yb;
+        const long long warps = (long long)sm_count() * blocks_per_sm * 4;
+        const long long cols = (long long)a.n_frames * a.n_strips;
+        long long n_segs = (8 * warps + cols - 1) / cols;
+        n_segs = std::max<long long>(1, std::min<long long>(n_segs, std::max(1, rows / (2 * TV))));
+        a.seg_rows = (int)((rows + n_segs - 1) / n_segs);
+        a.n_segs = (rows + a.seg_rows - 1) / a.seg_rows;
+        const long long items = cols * a.n_segs;
+        const int grid = (int)std::min<long long>((items + 3) / 4, (long long)sm_count() * blocks_per_sm);
+        k<<<grid, 128, smem, st>>>(tm, a, vt_host);
+        VT_LAUNCHED("scale_pair_kernel");
+    }
+    return VT_OK;
+}
+
+template <bool UV>
+int dispatch(int hp, int tv, const vt_scale_plan::Pair &s, const CUtensorMap &tm, const PairArgs &a, int rows,
+             cudaStream_t st) {
+#define VT_CASE(H, T) if (hp == H && tv == T) return launch_t<H, T, UV>(s, tm, a, rows, st)
+    VT_CASE(3, 6); VT_CASE(3, 8); VT_CASE(3, 12);
+    VT_CASE(4, 6); VT_CASE(4, 8); VT_CASE(4, 12);
+    VT_CASE(6, 6); VT_CASE(6, 8); VT_CASE(6, 12);
+#undef VT_CASE
+    set_error("scale_pair: no instantiation for hp=%d tv=%d", hp, tv);
+    return VT_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+// Builds the tables the pair kernel reads for one plane kind (c = 0 luma, 1 chroma).  Leaves pair[c].ok false
+// (generic kernels stay in charge) when the shape is outside what the kernel handles.
+int build_pair(vt_scale_plan *p, int c) {
+    vt_scale_plan::Pair &s = p->pair[c];
+    const bool uv = c == 1;
+    const int dw = c ? p->cdw : p->dw, dh = c ? p->cdh : p->dh;
+    const int bpp = uv ? 2 : 1;
+    const int ht = p->htaps[c], vtaps = p->vtaps[c];
+    const std::vector<int32_t> &hpos = p->h_hpos[c], &vpos = p->h_vpos[c];
+    const std::vector<int16_t> &hco = p->h_hcoef[c], &vco = p->h_vcoef[c];
+    s.hp = pad_hp(ht);
+    s.tv = pad_tv(vtaps);
+    if (!s.hp || !s.tv) return VT_OK;
+    const int bn = s.hp + 1;
+    s.np = uv ? pair_np(s.hp, s.tv) / 2 : pair_np(s.hp, s.tv);
+    s.strip_cols = s.np * 64;
+    if ((dw & 1) || (p->dw & 1) || dw < s.strip_cols) return VT_OK;
+    for (int x = 0; x + 1 < dw; x++)
+        if (hpos[x + 1] < hpos[x]) return VT_OK;
+    for (int x = 0; x + 1 < dw; x += 2)
+        if (hpos[x + 1] - hpos[x] + ht > 2 * bn) return VT_OK;
+    for (int y = 0; y + 1 < dh; y++)
+        if (vpos[y + 1] < vpos[y]) return VT_OK;
+    s.n_strips = (dw + s.strip_cols - 1) / s.strip_cols;
+    const int naw = uv ? bn : (bn + 1) / 2, nw = naw + 1;
+    s.lt_words = (2 * s.hp + 2 + 3) & ~3;
+    // boxes: a strip is cut into n_boxes runs of box_cols columns whose source span fits a 256-byte TMA box row
+    int box_cols = s.strip_cols, need = 0;
+    std::vector<int32_t> scol((size_t)s.n_strips);
+    for (int strip = 0; strip < s.n_strips; strip++) scol[strip] = std::min(strip * s.strip_cols, dw - s.strip_cols);
+    for (;; box_cols >>= 1) {
+        if (box_cols < 16) return VT_OK;
+        need = 0;
+        for (int strip = 0; strip < s.n_strips; strip++)
+            for (int b = 0; b * box_cols < s.strip_cols; b++) {
+                const int xf = scol[strip] + b * box_cols, xl = xf + box_cols - 2;   // first / last even column
+                need = std::max(need, hpos[xl] * bpp + 4 * nw - ((hpos[xf] * bpp) & ~15));
+            }
+        if (need <= (int)PAIR_TILE_W) break;
+    }
+    s.n_boxes = s.strip_cols / box_cols;
+    s.tile_w = (int)PAIR_TILE_W;
+    // stage geometry: TWO stages of about 12 rows.  Measured with tools/ubench_tma.cu on B200: per-warp rings with two
+    // stages in flight pull 6.3-6.5 TB/s, three or four stages only 2.8-4.4 TB/s (HBM row conflicts between the many
+    // row blocks then in flight); box height and alignment hardly matter.
+    const int nb = pair_min_blocks(s.hp, s.tv);
+    s.n_stages = 2;
+    s.groups_per_stage = s.tv <= 6 ? 2 : 1;
+    if (getenv("VT_PAIR_RG") && getenv("VT_PAIR_NST")) {                    // geometry experiments
+        s.groups_per_stage = atoi(getenv("VT_PAIR_RG"));
+        s.n_stages = atoi(getenv("VT_PAIR_NST"));
+    }
+    for (;; s.groups_per_stage--) {
+        if (s.groups_per_stage < 1) return VT_OK;
+        s.stage_rows = s.groups_per_stage * s.tv;
+        s.box_bytes = (s.stage_rows * s.tile_w + 127) & ~127;
+        s.stage_bytes = s.box_bytes * s.n_boxes;
+        s.warp_smem = (s.n_stages * s.stage_bytes + 64 + 127) & ~127;
+        if (4 * s.warp_smem * nb + nb * 1024 <= 227 * 1024) break;
+    }
+    if (s.n_stages < 2) return VT_OK;
+    std::vector<int32_t> bx((size_t)s.n_strips * s.n_boxes);
+    std::vector<uint32_t> lt((size_t)s.n_strips * s.np * 32 * s.lt_words, 0);
+    for (int strip = 0; strip < s.n_strips; strip++) {
+        for (int b = 0; b < s.n_boxes; b++) bx[(size_t)strip * s.n_boxes + b] = (hpos[scol[strip] + b * box_cols] * bpp) & ~15;
+        for (int g = 0; g < s.np; g++)
+            for (int lane = 0; lane < 32; lane++) {
+                const int xa = scol[strip] + g * 64 + 2 * lane, xb = xa + 1;
+                const int b = (g * 64 + 2 * lane) / box_cols;
+                uint32_t *t = &lt[((size_t)(strip * s.np + g) * 32 + lane) * s.lt_words];
+                t[0] = (uint32_t)(b * s.box_bytes + hpos[xa] * bpp - bx[(size_t)strip * s.n_boxes + b]);
+                for (int j = 0; j < ht; j++) {
+                    const uint32_t v = (uint16_t)hco[(size_t)xa * ht + j];
+                    t[1 + j / 2] |= (j & 1) ? (v << 16) : v;
+                }
+                const int d = hpos[xb] - hpos[xa];                 // the odd column's taps start d samples further right
+                for (int j = 0; j < ht; j++) {
+                    const uint32_t v = (uint16_t)hco[(size_t)xb * ht + j];
+                    const int sidx = d + j;
+                    t[1 + s.hp + sidx / 2] |= (sidx & 1) ? (v << 16) : v;
+                }
+            }
+    }
+    s.vstride = vstride_for(s.tv);
+    s.vtab.assign((size_t)dh * s.vstride, 0);
+    for (int y = 0; y < dh; y++) {
+        int32_t *t = &s.vtab[(size_t)y * s.vstride];
+        for (int j = 0; j < vtaps; j++) t[(s.tv - vtaps) + j] = vco[(size_t)y * vtaps + j];
+        t[s.tv] = vpos[y] + vtaps - 1;
+    }
+    int rc = upload(bx.data(), bx.size() * 4, (void **)&s.box_x0);
+    if (rc == VT_OK) rc = upload(scol.data(), scol.size() * 4, (void **)&s.strip_col);
+    if (rc == VT_OK) rc = upload(lt.data(), lt.size() * 4, (void **)&s.lane_tab);
+    if (rc != VT_OK) return rc;
+    s.ok = true;
+    return VT_OK;
+}
+
+void free_pair(vt_scale_plan *p) {
+    for (int c = 0; c < 2; c++) {
+        cudaFree(p->pair[c].box_x0);
+        cudaFree(p->pair[c].strip_col);
+        cudaFree(p->pair[c].lane_tab);
+        p->pair[c].box_x0 = p->pair[c].strip_col = nullptr;
+        p->pair[c].lane_tab = nullptr;
+    }
+}
+
+int launch_pair(const vt_scale_plan *p, int c, const uint8_t *src, int pitch, size_t src_fs, uint8_t *dst, size_t dst_fs,
+                int n_frames, cudaStream_t st) {
+    const vt_scale_plan::Pair &s = p->pair[c];
+    const bool uv = c == 1;
+    CUtensorMap tm;
+    const uint8_t *base = uv ? src + (size_t)pitch * p->sh : src;
+    const int row_bytes = uv ? 2 * p->csw : p->sw;
+    const int rows = uv ? p->csh : p->sh;
+    int rc = make_tmap_u32_3d(&tm, base, row_bytes, rows, n_frames, pitch, src_fs, s.tile_w, s.stage_rows);
+    if (rc) return rc;
+    PairArgs a;
+    a.lane_tab = s.lane_tab;
+    a.box_x0 = s.box_x0;
+    a.strip_col = s.strip_col;
+    a.dst = uv ? dst + (size_t)p->dw * p->dh : dst;
+    a.dst_fs = dst_fs;
+    a.dst_plane2 = (size_t)p->cdw * p->cdh;
+    a.n_frames = n_frames;
+    a.n_strips = s.n_strips;
+    a.n_segs = a.seg_rows = 0;
+    a.dw = uv ? p->cdw : p->dw;
+    a.y_begin = a.y_end = 0;
+    a.tile_w = s.tile_w;
+    a.n_boxes = s.n_boxes;
+    a.groups_per_stage = s.groups_per_stage;
+    a.box_bytes = s.box_bytes;
+    a.stage_bytes = s.stage_bytes;
+    a.n_stages = s.n_stages;
+    a.warp_smem = s.warp_smem;
+    a.round_bias = 1 << 18;
+    const int dh = uv ? p->cdh : p->dh;
+    return uv ? dispatch<true>(s.hp, s.tv, s, tm, a, dh, st) : dispatch<false>(s.hp, s.tv, s, tm, a, dh, st);
+}
+
+}  // namespace vt

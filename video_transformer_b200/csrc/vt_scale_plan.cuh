@@ -1,0 +1,60 @@
+// vt_scale_plan.cuh -- the scaling plan shared by the scaler's translation units.
+#pragma once
+#include <vector>
+
+#include "vt_common.cuh"
+
+struct vt_scale_plan {
+    int sw, sh, dw, dh, flags;
+    int csw, csh, cdw, cdh;  // chroma plane sizes
+    // filter banks in device memory; index 0 = luma, 1 = chroma
+    int htaps[2], vtaps[2];
+    int16_t *hcoef[2];  // dw x htaps
+    int32_t *hpos[2];
+    int16_t *vcoef[2];  // dh x vtaps
+    int32_t *vpos[2];
+    int16_t *scratch;  // generic path: dw x sh int16
+    // host copies (streaming path work-list construction)
+    std::vector<int16_t> h_hcoef[2], h_vcoef[2];
+    std::vector<int32_t> h_hpos[2], h_vpos[2];
+    // streaming path (one per plane kind): tables built by build_stream() at plan creation
+    struct Stream {
+        bool ok = false;
+        int hp = 0, tv = 0;     // dp2a pairs per output, (padded) vertical taps -> kernel instantiation
+        int cpt = 0;            // output columns per lane (per channel)
+        int strip_cols = 0, n_strips = 0;
+        int rows_out = 0, n_chunks = 0;
+        int tile_w = 0, tile_h = 0;
+        int warp_smem = 0;
+        int32_t *strip_x0 = nullptr;   // n_strips: first source byte of each strip's tile (multiple of 16)
+        uint32_t *lane_tab = nullptr;  // (n_strips*strip_cols) x (1+hp): source byte of tap 0, packed coef pairs
+        int32_t *vtab = nullptr;       // dh x (2+tv): first source row, last source row, front-padded coefs
+    } stream[2];
+    // pair kernel (vt_scale_pair.cu), one per plane kind: tables built by vt::build_pair() at plan creation
+    struct Pair {
+        bool ok = false;
+        int hp = 0, tv = 0;            // dp2a pairs of the even column (the odd one uses hp+1), padded vertical taps
+        int np = 0;                    // column pairs per lane (2 luma, 1 chroma)
+        int strip_cols = 0, n_strips = 0;
+        int tile_w = 0, n_boxes = 0, groups_per_stage = 0, stage_rows = 0;
+        int box_bytes = 0, stage_bytes = 0, n_stages = 0, warp_smem = 0;
+        int lt_words = 0;              // words per lane-table entry
+        int32_t *box_x0 = nullptr;     // n_strips x n_boxes: first source byte of each TMA box (multiple of 16)
+        int32_t *strip_col = nullptr;  // n_strips: first output column of each strip
+        uint32_t *lane_tab = nullptr;  // (n_strips*np*32) x lt_words
+        std::vector<int32_t> vtab;     // dh x vstride: front-padded coefficients, then the window's last source row
+        int vstride = 0;
+    } pair[2];
+};
+
+namespace vt {
+int build_pair(vt_scale_plan *p, int c);
+void free_pair(vt_scale_plan *p);
+int launch_pair(const vt_scale_plan *p, int c, const uint8_t *src, int pitch, size_t src_fs, uint8_t *dst, size_t dst_fs,
+                int n_frames, cudaStream_t st);
+int make_tmap_u32_3d(void *tmap_out, const uint8_t *base, int row_bytes, int rows, int n_frames, int pitch,
+                     size_t frame_stride, int tile_w, int tile_h);
+int make_tmap_u8_3d(void *tmap_out, const uint8_t *base, int row_bytes, int rows, int n_frames, int pitch,
+                    size_t frame_stride, int tile_w, int tile_h);
+}  // namespace vt
+
