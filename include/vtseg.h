@@ -81,6 +81,18 @@ int vt_nv12_to_yuv420p(const uint8_t *src_dev, int src_pitch, size_t src_frame_s
 int vt_nv12_to_rgb24(const uint8_t *src_dev, int src_pitch, size_t src_frame_stride, int w, int h,
                      uint8_t *dst_dev, size_t dst_frame_stride, int n_frames, void *stream);
 
+/* ---- K1b + K2 for the upload product (BASELINE.json configs[4]: sampled frames -> 768x768 RGB) -------------
+ * NV12 -> packed RGB24 at a different size, with the semantics of `ffmpeg -vf scale=W:H -pix_fmt rgb24`
+ * (libswscale general path, SWS_BICUBIC, BT.601 limited range; chroma interpolated vertically to full height,
+ * shared by horizontal pixel pairs).  The reference has no RGB anywhere; the nearest call
+ * site is the upload-size reducer src/analyzer/content_analyzer.py:167-236.  dst_w must be even.
+ *   dst: frame f at dst_dev + f*dst_frame_stride, dst_h rows of 3*dst_w bytes (R,G,B). */
+typedef struct vt_rgb_plan vt_rgb_plan;
+int vt_rgb_plan_create(int src_w, int src_h, int dst_w, int dst_h, int flags, vt_rgb_plan **out);
+void vt_rgb_plan_destroy(vt_rgb_plan *plan);
+int vt_scale_nv12_to_rgb24(const vt_rgb_plan *plan, const uint8_t *src_dev, int src_pitch, size_t src_frame_stride,
+                           uint8_t *dst_dev, size_t dst_frame_stride, int n_frames, void *stream);
+
 /* ---- K3: per-frame 256-bin luma histogram and SAD against the previous frame ---------------------------
  * Frame f's luma is at luma_dev + f*frame_stride (h rows of `pitch` bytes, display width w).
  * prev for frame 0 is prev0_dev (same pitch) or NULL (then sad[0] = 0); prev for f>0 is frame f-1.

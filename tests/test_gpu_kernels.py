@@ -140,3 +140,31 @@ def test_gather_frames(cuda):
     assert np.array_equal(out, src[idx, :4096])
     out2 = ops.gather_frames(d.view(-1)[4160 * 2:], 4160, 1000, None, 3).cpu().numpy()
     assert np.array_equal(out2, src[2:5, :1000])
+
+
+@pytest.mark.parametrize("sw,sh,pitch,dw,dh", [(1280, 720, 1280, 768, 768), (1920, 1080, 2048, 768, 768),
+                                               (640, 360, 640, 640, 360), (322, 182, 336, 160, 90)])
+def test_nv12_to_rgb24_scaled_bit_exact(cuda, oracle_c, sw, sh, pitch, dw, dh):
+    """K1b / config 5: NV12 -> RGB24 with scaling equals the oracle (itself bit-exact against libswscale)."""
+    rng = np.random.default_rng(sw + dw)
+    n = 3
+    buf = _nv12_batch(rng, n, sw, sh, pitch)
+    buf[1, : sh // 2] = 235                      # flat bright area next to noise: exercises the clamps
+    plan = ops.RgbPlan(sw, sh, dw, dh)
+    out = plan.scale_nv12(torch.from_numpy(buf).to(cuda).view(-1), pitch, n).cpu().numpy()
+    for f in range(n):
+        exp = oracle_c.nv12_to_rgb24(buf[f].reshape(-1), sw, sh, pitch, dw, dh)
+        assert np.array_equal(out[f], exp), (f, np.abs(out[f].astype(int) - exp.astype(int)).max())
+
+
+def test_nv12_to_rgb24_same_size_matches_committed_libswscale_output(cuda, oracle_c):
+    import os
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "sws_rgb_vectors.npz"))
+    for name in ("a", "b", "c", "e"):
+        sw, sh, pitch, dw, dh = (int(v) for v in gold[name + "_dims"])
+        src = torch.from_numpy(np.ascontiguousarray(gold[name + "_nv12"])).to(cuda)
+        if (sw, sh) == (dw, dh):
+            got = ops.nv12_to_rgb24(src.view(-1), sw, sh, pitch, 1).cpu().numpy()[0]
+        else:
+            got = ops.RgbPlan(sw, sh, dw, dh).scale_nv12(src.view(-1), pitch, 1).cpu().numpy()[0]
+        assert np.array_equal(got, gold[name + "_rgb"]), name

@@ -40,6 +40,9 @@ SIGNATURES = {
     "vt_scale_nv12_to_yuv420p": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_size_t, c_int, c_void_p]),
     "vt_nv12_to_yuv420p": (c_int, [c_void_p, c_int, c_size_t, c_int, c_int, c_void_p, c_size_t, c_int, c_void_p]),
     "vt_nv12_to_rgb24": (c_int, [c_void_p, c_int, c_size_t, c_int, c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    "vt_rgb_plan_create": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
+    "vt_rgb_plan_destroy": (None, [c_void_p]),
+    "vt_scale_nv12_to_rgb24": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_size_t, c_int, c_void_p]),
     "vt_sad_hist_u8": (c_int, [c_void_p, c_int, c_size_t, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "vt_gather_frames": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_int, c_void_p, c_void_p]),
     "vt_h264_scan": (c_int, [c_void_p, c_size_t, POINTER(StreamInfo), c_void_p, c_void_p, c_void_p, c_int]),

@@ -114,10 +114,16 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t phase) {
         : "memory");
 }
 
-constexpr uint32_t PAIR_TILE_W = 448;   // bytes per row of every TMA box (tensor of 32-bit elements: up to 1024 B per box row)
+#ifndef VT_PAIR_WIDE
+#define VT_PAIR_WIDE 1                   // 0: measurement build with two column pairs per lane everywhere
+#endif
+#ifndef VT_PAIR_BLOCKS
+#define VT_PAIR_BLOCKS 4
+#endif
+constexpr uint32_t PAIR_TILE_W = VT_PAIR_WIDE ? 448 : 256;   // bytes per row of every TMA box (32-bit elements: up to 1024 B)
 
-__host__ __device__ constexpr int pair_np(int hp, int tv) { return (hp <= 3 && tv <= 8) ? 4 : 2; }         // luma pairs per lane
-__host__ __device__ constexpr int pair_min_blocks(int hp, int tv) { return pair_np(hp, tv) == 4 ? 5 : (tv <= 8 ? 5 : 3); }
+__host__ __device__ constexpr int pair_np(int hp, int tv) { return (VT_PAIR_WIDE && hp <= 3 && tv <= 8) ? 4 : 2; }   // luma pairs per lane
+__host__ __device__ constexpr int pair_min_blocks(int hp, int tv) { return (hp <= 4 && tv <= 8) ? VT_PAIR_BLOCKS : 3; }
 
 // HP  dp2a pairs of the even column (taps padded to 2*HP); the odd column uses HP+1 pairs (rotated coefficients)
 // TV  vertical taps (front padded); UV: the source is NV12's interleaved chroma plane, a lane produces U and V

@@ -136,3 +136,33 @@ class ScalePlan:
         check(lib().vt_scale_nv12_to_yuv420p(self._h, c_void_p(src.data_ptr()), pitch, sfs,
                                              c_void_p(out.data_ptr()), self.out_frame_bytes, n_frames, _stream()))
         return out
+
+
+class RgbPlan:
+    """Device-resident filter banks for NV12 -> RGB24 at (dw, dh): `ffmpeg -vf scale=dw:dh -pix_fmt rgb24` semantics."""
+
+    def __init__(self, sw: int, sh: int, dw: int, dh: int, flags: int = SWS_BICUBIC):
+        self.sw, self.sh, self.dw, self.dh, self.flags = sw, sh, dw, dh, flags
+        self._h = c_void_p()
+        check(lib().vt_rgb_plan_create(sw, sh, dw, dh, flags, byref(self._h)))
+
+    def close(self) -> None:
+        if self._h:
+            lib().vt_rgb_plan_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def scale_nv12(self, src: torch.Tensor, pitch: int, n_frames: int, src_frame_stride: int | None = None,
+                   out: torch.Tensor | None = None) -> torch.Tensor:
+        _need_cuda(src, "src")
+        sfs = src_frame_stride or nv12_frame_bytes(pitch, self.sh)
+        if out is None:
+            out = torch.empty((n_frames, self.dh, self.dw, 3), dtype=torch.uint8, device=src.device)
+        check(lib().vt_scale_nv12_to_rgb24(self._h, c_void_p(src.data_ptr()), pitch, sfs, c_void_p(out.data_ptr()),
+                                           self.dw * self.dh * 3, n_frames, _stream()))
+        return out
