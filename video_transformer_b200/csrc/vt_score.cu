@@ -11,6 +11,8 @@
 // tools/ubench_smem.cu).  A lane sees at most 240 pixels between flushes, so no byte can carry into its
 // neighbour.  A flush sums each row over the 32 lanes with rotated (conflict-free) word reads and adds the
 // four bins of the row to the block histogram.  SAD is VABSDIFF4 + IDP.4A on the same 128-bit loads.
+#include <algorithm>
+
 #include "vt_common.cuh"
 
 namespace vt {
@@ -25,14 +27,27 @@ __device__ __forceinline__ void red_shared(uint32_t addr, uint32_t v) {
 }
 
 // 4 pixels of one 32-bit word.  base = (8 KB aligned warp region) | lane*4.
-// Per pixel: one shift + one LOP3 for the address, one PRMT + one shift for the increment, one RED.
+// The ALU pipe (half rate on sm_100a: LOP3/SHF/PRMT issue every other cycle, tools/ubench_pipes.cu) is the busiest
+// one in this kernel, so the address arithmetic is split between the pipes: one PRMT (ALU) extracts the row of a
+// pixel, one IMAD (FMA pipe, otherwise idle here) turns it into the counter address; the increment is a wrapping
+// funnel shift of 1 by 8*(pixel >> 6), whose shift count needs no masking (only the low five bits count).
+__device__ __forceinline__ uint32_t counter_addr(uint32_t rows, uint32_t sel, uint32_t base) {
+    uint32_t a;
+    asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(a) : "r"(__byte_perm(rows, 0, sel)), "r"(base));
+    return a;
+}
+__device__ __forceinline__ uint32_t one_shl_wrap(uint32_t n) {   // 1 << (n & 31)
+    uint32_t d;
+    asm("shf.l.wrap.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(0u), "r"(1u), "r"(n));
+    return d;
+}
 __device__ __forceinline__ void hist_word(uint32_t w, uint32_t base) {
     const uint32_t r = w & 0x3F3F3F3Fu;          // row index of each pixel
     const uint32_t j8 = (w >> 3) & 0x18181818u;  // 8 * (pixel >> 6): bit offset of its counter in the word
-    red_shared(((r << 7) & 0x1F80u) | base, 1u << __byte_perm(j8, 0, 0x4440));
-    red_shared(((r >> 1) & 0x1F80u) | base, 1u << __byte_perm(j8, 0, 0x4441));
-    red_shared(((r >> 9) & 0x1F80u) | base, 1u << __byte_perm(j8, 0, 0x4442));
-    red_shared(((r >> 17) & 0x1F80u) | base, 1u << (j8 >> 24));
+    red_shared(counter_addr(r, 0x4440, base), one_shl_wrap(j8));
+    red_shared(counter_addr(r, 0x4441, base), one_shl_wrap(j8 >> 8));
+    red_shared(counter_addr(r, 0x4442, base), one_shl_wrap(j8 >> 16));
+    red_shared(counter_addr(r, 0x4443, base), one_shl_wrap(j8 >> 24));
 }
 
 // Warp-collective: add the lane-private packed counters into the block histogram and clear them.
@@ -83,7 +98,7 @@ __device__ __forceinline__ void flush_counters(uint32_t warp_cnt, uint32_t *bhis
 // Aligned fast path: luma/prev base and pitch are multiples of 16 bytes.
 __global__ void __launch_bounds__(SC_THREADS, 3)
 score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, int w, int h,
-             const uint8_t *__restrict__ prev0, int rows_per_block, int chunks_per_frame,
+             const uint8_t *__restrict__ prev0, int rows_per_block, int chunks_per_frame, int chunks_per_block,
              unsigned long long *__restrict__ sad_out, uint32_t *__restrict__ hist_out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -92,10 +107,13 @@ score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, i
     uint32_t *bhist = (uint32_t *)(smem_raw + (cnt0 - s0) + SC_WARPS * SC_CNT_BYTES);
     const uint32_t warp_cnt = cnt0 + warp * SC_CNT_BYTES;
 
-    const int f = blockIdx.x / chunks_per_frame;
-    const int chunk = blockIdx.x - f * chunks_per_frame;
-    const int r0 = chunk * rows_per_block;
-    const int r1 = min(h, r0 + rows_per_block);
+    // a block owns chunks_per_block consecutive row chunks of one frame: its 256 global histogram atomics and its
+    // SAD atomics are paid once for all of them
+    const int blocks_per_frame = (chunks_per_frame + chunks_per_block - 1) / chunks_per_block;
+    const int f = blockIdx.x / blocks_per_frame;
+    const int chunk0 = (blockIdx.x - f * blocks_per_frame) * chunks_per_block;
+    const int chunk1 = min(chunks_per_frame, chunk0 + chunks_per_block);
+    const int rows_first = chunk0 * rows_per_block, rows_last = min(h, chunk1 * rows_per_block);
     const uint8_t *cur = luma + (size_t)f * frame_stride;
     const uint8_t *prv = f ? cur - frame_stride : (prev0 ? prev0 : cur);
 
@@ -112,6 +130,9 @@ score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, i
     const int rpw = rows_per_block / SC_WARPS;   // consecutive rows owned by each warp
 
     uint32_t sad = 0;
+    for (int chunk = chunk0; chunk < chunk1; chunk++) {
+    const int r0 = chunk * rows_per_block;
+    const int r1 = min(h, r0 + rows_per_block);
     int budget = 0;                     // upper bound on pixels a lane has counted since the last flush
     for (int rr = 0; rr < rpw; rr++) {
         const int row = r0 + warp * rpw + rr;
@@ -168,6 +189,7 @@ score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, i
         }
     }
     flush_counters(warp_cnt, bhist, lane);
+    }
 
     // SAD: lane partials -> warp sum in 64 bit -> one global atomic per warp
     unsigned long long s64 = sad;
@@ -177,7 +199,7 @@ score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, i
 
     __syncthreads();
     uint32_t v = bhist[tid];
-    if (tid == 0 && tail) v -= (uint32_t)(r1 - r0) * (uint32_t)(16 - tail);  // masked bytes were counted as 0
+    if (tid == 0 && tail) v -= (uint32_t)(rows_last - rows_first) * (uint32_t)(16 - tail);  // masked bytes were counted as 0
     if (v) atomicAdd(&hist_out[(size_t)f * 256 + tid], v);
 }
 
@@ -232,7 +254,13 @@ int launch_score(const uint8_t *luma, int pitch, size_t frame_stride, int w, int
     if (rpw > 8) rpw = 8;
     const int rows_per_block = aligned ? rpw * SC_WARPS : 32;
     const int chunks = (h + rows_per_block - 1) / rows_per_block;
-    const long long blocks = (long long)chunks * n_frames;
+    // chunks per block: keep about six waves of blocks, fold the rest into fewer global atomics
+    int cpb = 1;
+    if (aligned) {
+        const long long want = 6LL * sm_count() * 3;
+        cpb = (int)std::max<long long>(1, std::min<long long>(chunks, (long long)chunks * n_frames / want));
+    }
+    const long long blocks = (long long)((chunks + cpb - 1) / cpb) * n_frames;
     if (blocks > 0x7fffffffLL) {
         set_error("vt_sad_hist_u8: batch too large");
         return VT_ERR_INVALID;
@@ -244,7 +272,7 @@ int launch_score(const uint8_t *luma, int pitch, size_t frame_stride, int w, int
             attr_done = true;
         }
         score_kernel<<<(unsigned)blocks, SC_THREADS, SC_SMEM, st>>>(luma, pitch, frame_stride, w, h, prev0,
-                                                                  rows_per_block, chunks,
+                                                                  rows_per_block, chunks, cpb,
                                                                   (unsigned long long *)sad, hist);
         VT_LAUNCHED("score_kernel");
     } else {
