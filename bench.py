@@ -41,6 +41,15 @@ BYTES_SCORE = 2 * SRC_W * SRC_H          # cur + prev luma
 BYTES_DECODE = 2 * 3110400               # samples in, NV12 surface out
 
 
+def load_traffic():
+    """DRAM bytes per picture per kernel from the committed ncu capture (profiles/r01_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return json.load(open(p))["per_picture_bytes"]
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -333,6 +342,7 @@ def main():
     dominant = max(names, key=lambda n: kern_ms[n])
     alg = {"decode": BYTES_DECODE, "score": BYTES_SCORE, "scale": BYTES_SCALE}
     ach = {n: alg[n] * F / (kern_ms[n] * 1e-3) / 1e9 for n in names}
+    traffic = load_traffic()
     value = world * K * F / (dev_ms_max * 1e-3)
     e2e_value = world * K * F / (e2e_ms_max * 1e-3)
     segs_per_s = value / (720.0 * FPS)                   # shipped plan for 7200 s: 10 segments of 720 s
@@ -345,7 +355,10 @@ def main():
                 "d2h_bytes_per_step": eng.d2h_bytes // max(K, 1)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": ach[dominant], "peak": peak, "unit": "GB/s",
-                     "frac": ach[dominant] / peak, "traffic": None, "peak_source": peak_kind,
+                     "frac": ach[dominant] / peak,
+                     "traffic": (traffic[dominant] * F if traffic and dominant in traffic else None),
+                     "traffic_source": "profiles/r01_traffic.json (ncu dram__bytes_read+write per launch of %d pictures)" % F,
+                     "algorithmic_bytes": alg[dominant] * F, "peak_source": peak_kind,
                      "frac_of_nominal_8000": ach[dominant] / 8000.0},
         "kernels": {n: {"ms_per_step": kern_ms[n], "achieved_gbs": ach[n], "frac": ach[n] / peak,
                         "alg_bytes_per_picture": alg[n]} for n in names},

@@ -95,6 +95,12 @@ __device__ __forceinline__ void flush_counters(uint32_t warp_cnt, uint32_t *bhis
     __syncwarp();
 }
 
+// Out-of-line copy for the mid-row flush (rows wider than 8160 pixels only): keeps the hot loop's code small enough
+// for the instruction cache.
+__device__ __noinline__ void flush_counters_cold(uint32_t warp_cnt, uint32_t *bhist, int lane) {
+    flush_counters(warp_cnt, bhist, lane);
+}
+
 // Aligned fast path: luma/prev base and pitch are multiples of 16 bytes.
 __global__ void __launch_bounds__(SC_THREADS, 3)
 score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, int w, int h,
@@ -171,7 +177,7 @@ score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, i
             for (int k = 0; k < 4; k++) {
                 if (g0 + k * 32 >= ngroups) break;          // warp-uniform
                 if (budget > 255 - 16) {                    // only reachable for rows wider than 8160 pixels
-                    flush_counters(warp_cnt, bhist, lane);
+                    flush_counters_cold(warp_cnt, bhist, lane);
                     budget = 0;
                 }
                 if (g0 + k * 32 + lane < ngroups) {
