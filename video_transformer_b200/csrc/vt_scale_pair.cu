@@ -158,13 +158,35 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     constexpr uint32_t group_bytes = (uint32_t)TV * PAIR_TILE_W;   // tile rows are PAIR_TILE_W bytes apart: row offsets
     uint32_t phases = 0;                                           // inside a group are immediates of the loads
     const uint32_t stage_tx = (uint32_t)(stage_rows * PAIR_TILE_W * a.n_boxes);
-    const int per_frame = a.n_strips * a.n_segs;
-    const long long total = (long long)per_frame * a.n_frames;
-    const long long nwarps = (long long)gridDim.x * 4;
-    for (long long it = (long long)blockIdx.x * 4 + warp; it < total; it += nwarps) {
-        const int f = (int)(it / per_frame);
-        const int rem = (int)(it - (long long)f * per_frame);
-        const int seg = rem / a.n_strips, strip = rem - seg * a.n_strips;
+    // A warp keeps ONE strip for the whole launch (its column tables are loaded once) and walks over that strip's
+    // (frame, segment) items; warps beyond a multiple of n_strips have nothing to do.
+    const int warps_per_strip = (int)(((long long)gridDim.x * 4) / a.n_strips);
+    const int gw = blockIdx.x * 4 + warp;
+    if (gw >= warps_per_strip * a.n_strips) return;
+    const int strip = gw % a.n_strips;
+    const int total = a.n_frames * a.n_segs;
+    // this lane's column pairs
+    uint32_t addr[NP], shb[NP], ca[NP][HP], cb[NP][BN];
+#pragma unroll
+    for (int g = 0; g < NP; g++) {
+        const uint4 *t4 = reinterpret_cast<const uint4 *>(a.lane_tab + ((size_t)(strip * NP + g) * 32 + lane) * LT);
+        uint32_t wd[LT];
+#pragma unroll
+        for (int i = 0; i < LT / 4; i++) {
+            const uint4 q = __ldg(t4 + i);
+            wd[4 * i] = q.x; wd[4 * i + 1] = q.y; wd[4 * i + 2] = q.z; wd[4 * i + 3] = q.w;
+        }
+        addr[g] = wsm + (wd[0] & ~3u);               // wd[0]: byte offset of the pair's tap 0 inside a stage (row 0)
+        shb[g] = (wd[0] & 3u) * 8u;
+#pragma unroll
+        for (int i = 0; i < HP; i++) ca[g][i] = wd[1 + i];
+#pragma unroll
+        for (int i = 0; i < BN; i++) cb[g][i] = wd[1 + HP + i];
+    }
+    const size_t strip_byte = (size_t)a.strip_col[strip] + 2 * lane;
+    for (int it = gw / a.n_strips; it < total; it += warps_per_strip) {
+        const int f = it / a.n_segs;
+        const int seg = it - f * a.n_segs;
         const int y0 = a.y_begin + seg * a.seg_rows;
         const int y1 = min(a.y_end, y0 + a.seg_rows);
         int vi = (y0 - a.y_begin) * VS;
@@ -184,24 +206,6 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                                 a.box_x0[strip * a.n_boxes + b] >> 2, rs + s * stage_rows, f);
             }
         }
-        // this lane's column pairs
-        uint32_t addr[NP], shb[NP], ca[NP][HP], cb[NP][BN];
-#pragma unroll
-        for (int g = 0; g < NP; g++) {
-            const uint4 *t4 = reinterpret_cast<const uint4 *>(a.lane_tab + ((size_t)(strip * NP + g) * 32 + lane) * LT);
-            uint32_t wd[LT];
-#pragma unroll
-            for (int i = 0; i < LT / 4; i++) {
-                const uint4 q = __ldg(t4 + i);
-                wd[4 * i] = q.x; wd[4 * i + 1] = q.y; wd[4 * i + 2] = q.z; wd[4 * i + 3] = q.w;
-            }
-            addr[g] = wsm + (wd[0] & ~3u);           // wd[0]: byte offset of the pair's tap 0 inside a stage (row 0)
-            shb[g] = (wd[0] & 3u) * 8u;
-#pragma unroll
-            for (int i = 0; i < HP; i++) ca[g][i] = wd[1 + i];
-#pragma unroll
-            for (int i = 0; i < BN; i++) cb[g][i] = wd[1 + HP + i];
-        }
         int m[TV][NM];
 #pragma unroll
         for (int k = 0; k < TV; k++)
@@ -215,7 +219,7 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         int vc[TV];
 #pragma unroll
         for (int j = 0; j < TV; j++) vc[j] = vtab.t[vi + j];
-        uint8_t *dptr = a.dst + (size_t)f * a.dst_fs + (size_t)y0 * a.dw + (size_t)a.strip_col[strip] + 2 * lane;
+        uint8_t *dptr = a.dst + (size_t)f * a.dst_fs + (size_t)y0 * a.dw + strip_byte;
 
         uint32_t ga[NP];
         auto hpass = [&](int k, int (&out)[NM]) {                            // horizontal pass of the group's row k
@@ -270,47 +274,53 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             for (int j = 0; j < TV; j++) vc[j] = vtab.t[vi + j];
             return true;
         };
-        int s = 0, gis = 0, ld = 0;                                          // stage, group inside the stage, load index
-        for (int gi = 0; gi < ngroups; gi++) {
-            if (gis == 0) {
-                mbar_wait_u32(bar0 + 8u * (uint32_t)s, (phases >> s) & 1u);
-                phases ^= 1u << s;
-            }
-            const uint32_t goff = (uint32_t)s * (uint32_t)a.stage_bytes + (uint32_t)gis * group_bytes;
-#pragma unroll
-            for (int g = 0; g < NP; g++) ga[g] = addr[g] + goff;
-#pragma unroll
-            for (int k = 0; k < TV; k++) {
-                hpass(k, m[k]);
-                // ---- vertical pass for every output row whose window ends at this source row
-                while (vrel == k) {
-                    int acc[NM];
-#pragma unroll
-                    for (int c = 0; c < NM; c++) acc[c] = rnd;
-#pragma unroll
-                    for (int j = 0; j < ((VT_ABLATE & 1) ? 1 : TV); j++) {
-#pragma unroll
-                        for (int c = 0; c < NM; c++) acc[c] += m[(k + 1 + j) % TV][c] * vc[j];
-                    }
-                    vstore(acc);
-                    if (!advance()) goto item_done;                          // the rest of this group's rows feed nothing
-                }
-            }
-            vrel -= TV;
-            rbase += TV;
-            gis++;
-            if (gis == rg || gi == ngroups - 1) {
-                __syncwarp();                                                // every lane is done with this stage
-                if (lane == 0 && ld + nst < nloads) {
-                    mbar_expect_tx(&bars[s], stage_tx);
+        int s = 0;                                                           // stage of load ld
+        uint32_t soff = 0;                                                   // its byte offset in the warp's ring
+        int groups_left = ngroups;
+        for (int ld = 0; ld < nloads; ld++) {
+            mbar_wait_u32(bar0 + 8u * (uint32_t)s, (phases >> s) & 1u);
+            phases ^= 1u << s;
+            const int ng = min(rg, groups_left);
+            groups_left -= ng;
+            uint32_t goff = soff;
 #pragma unroll 1
-                    for (int b = 0; b < a.n_boxes; b++)
-                        tma_load_3d(wbase + (size_t)s * a.stage_bytes + (size_t)b * a.box_bytes, &tmap, &bars[s],
-                                    a.box_x0[strip * a.n_boxes + b] >> 2, rs + (ld + nst) * stage_rows, f);
+            for (int gis = 0; gis < ng; gis++) {
+#pragma unroll
+                for (int g = 0; g < NP; g++) ga[g] = addr[g] + goff;
+#pragma unroll
+                for (int k = 0; k < TV; k++) {
+                    hpass(k, m[k]);
+                    // ---- vertical pass for every output row whose window ends at this source row
+                    while (vrel == k) {
+                        int acc[NM];
+#pragma unroll
+                        for (int c = 0; c < NM; c++) acc[c] = rnd;
+#pragma unroll
+                        for (int j = 0; j < ((VT_ABLATE & 1) ? 1 : TV); j++) {
+#pragma unroll
+                            for (int c = 0; c < NM; c++) acc[c] += m[(k + 1 + j) % TV][c] * vc[j];
+                        }
+                        vstore(acc);
+                        if (!advance()) goto item_done;                      // the rest of this group's rows feed nothing
+                    }
                 }
-                ld++;
-                gis = 0;
-                s = s + 1 == nst ? 0 : s + 1;
+                vrel -= TV;
+                rbase += TV;
+                goff += group_bytes;
+            }
+            __syncwarp();                                                    // every lane is done with this stage
+            if (lane == 0 && ld + nst < nloads) {
+                mbar_expect_tx(&bars[s], stage_tx);
+#pragma unroll 1
+                for (int b = 0; b < a.n_boxes; b++)
+                    tma_load_3d(wbase + soff + (size_t)b * a.box_bytes, &tmap, &bars[s],
+                                a.box_x0[strip * a.n_boxes + b] >> 2, rs + (ld + nst) * stage_rows, f);
+            }
+            s++;
+            soff += (uint32_t)a.stage_bytes;
+            if (s == nst) {
+                s = 0;
+                soff = 0;
             }
         }
     item_done:;
@@ -357,14 +367,21 @@ int launch_t(const vt_scale_plan::Pair &s, const CUtensorMap &tm, PairArgs a, in
         a.y_begin = yb;
         a.y_end = ye;
         const int rows = ye - yb;
-        const long long warps = (long long)sm_count() * blocks_per_sm * 4;
-        const long long cols = (long long)a.n_frames * a.n_strips;
-        long long n_segs = (8 * warps + cols - 1) / cols;
-        n_segs = std::max<long long>(1, std::min<long long>(n_segs, std::max(1, rows / (2 * TV))));
-        a.seg_rows = (int)((rows + n_segs - 1) / n_segs);
+        // Grid: every SM full.  Segments per (frame, strip): the count that minimises rounds x rows per item, where a
+        // round is one item per warp (a warp keeps its strip) and an item costs its source rows plus the TV-1 rows of
+        // window overlap plus a few rows' worth of set-up.
+        const int grid = sm_count() * blocks_per_sm;
+        const long long wps = std::max<long long>(1, (long long)grid * 4 / a.n_strips);   // warps per strip
+        const double src_rows = (double)rows * s.src_rows_per_dst_row;
+        int best = 1;
+        double best_cost = 1e30;
+        for (int n = 1; n <= std::max(1, rows / (2 * TV)); n++) {
+            const long long rounds = ((long long)a.n_frames * n + wps - 1) / wps;
+            const double cost = (double)rounds * (src_rows / n + (TV - 1) + 3.0);
+            if (cost < best_cost * 0.999) { best_cost = cost; best = n; }
+        }
+        a.seg_rows = (rows + best - 1) / best;
         a.n_segs = (rows + a.seg_rows - 1) / a.seg_rows;
-        const long long items = cols * a.n_segs;
-        const int grid = (int)std::min<long long>((items + 3) / 4, (long long)sm_count() * blocks_per_sm);
         k<<<grid, 128, smem, st>>>(tm, a, vt_host);
         VT_LAUNCHED("scale_pair_kernel");
     }
@@ -468,6 +485,7 @@ int build_pair(vt_scale_plan *p, int c) {
                 }
             }
     }
+    s.src_rows_per_dst_row = (double)(c ? p->csh : p->sh) / dh;
     s.vstride = vstride_for(s.tv);
     s.vtab.assign((size_t)dh * s.vstride, 0);
     for (int y = 0; y < dh; y++) {

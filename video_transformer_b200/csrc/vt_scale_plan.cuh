@@ -44,6 +44,7 @@ struct vt_scale_plan {
         uint32_t *lane_tab = nullptr;  // (n_strips*np*32) x lt_words
         std::vector<int32_t> vtab;     // dh x vstride: front-padded coefficients, then the window's last source row
         int vstride = 0;
+        double src_rows_per_dst_row = 1.0;
     } pair[2];
 };
 
