@@ -124,3 +124,27 @@ def test_same_height_source_is_converted_not_resized(cuda, oracle_c, tmp_path):
             assert np.array_equal(row, np.concatenate([y.reshape(-1), u.reshape(-1), v.reshape(-1)])), k
             k += 1
     assert k == 11
+
+
+def test_config5_sampled_rgb_frames(cuda, oracle_c, tmp_path):
+    """BASELINE.json configs[4]: 1 fps sampling + fixed-size RGB for upload.  Every picture is scored, only pictures
+    whose index is a multiple of sample_every are converted; RGB is bit-exact against the libswscale-pinned oracle."""
+    from video_transformer_b200 import ingest
+    w, h, n = 320, 240, 75
+    src, meta = _clip(tmp_path, w, h, n, 10, cuts=[41])
+    idx = container.probe(src)
+    got = []
+    opts = ingest.IngestOptions(output="rgb24", rgb_size=(96, 96), sample_every=30, batch_frames=8, scene_threshold=0.05)
+    eng = ingest.SegmentIngestor(idx, opts)
+    res = eng.run(5, n, lambda chunk, k0: got.append((k0, chunk.numpy().copy())))
+    assert (res.out_width, res.out_height, res.frame_bytes) == (96, 96, 96 * 96 * 3)
+    assert [k0 for k0, _ in got] == [30, 60] and all(c.shape[0] == 1 for _, c in got)
+    exp = _expected(w, h, meta)
+    for k0, chunk in got:
+        y, u, v = exp[k0]
+        nv12 = synth.planar_to_nv12(y, u, v, eng.pitch)
+        want = oracle_c.nv12_to_rgb24(nv12.reshape(-1), w, h, eng.pitch, 96, 96)
+        assert np.array_equal(chunk[0].reshape(96, 96, 3), want), k0
+    # scoring is unaffected by the sampling
+    whole = ingest.SegmentIngestor(idx, ingest.IngestOptions(target_height=120, batch_frames=8, scene_threshold=0.05)).run(5, n, None)
+    assert np.array_equal(res.sad, whole.sad) and res.cuts.tolist() == whole.cuts.tolist() and 41 in res.cuts.tolist()

@@ -39,6 +39,12 @@ class IngestOptions:
     scene_threshold: float = 0.10
     keep_frames: bool = True           # deliver output frames to the sink (False: scores only, config 3)
     never_upscale: bool = True         # sources at or below the target height are converted, not resized
+    # BASELINE.json configs[4]: "1 fps frame sampling + 768x768 RGB resize for upload".  output = "rgb24" delivers
+    # packed RGB at rgb_size (stretch, like `scale=W:H`); sample_every = N keeps pictures whose index is a multiple
+    # of N (every picture is still decoded and scored, boundaries do not depend on the sampling).
+    output: str = "yuv420p"
+    rgb_size: tuple | None = None
+    sample_every: int = 1
     device: str = "cuda"
 
 
@@ -115,13 +121,27 @@ class SegmentIngestor:
         self.rows = self.h + (self.h + 1) // 2
         self.surface_bytes = self.rows * self.pitch
         th = self.opts.target_height
-        if th and (self.h > th or (not self.opts.never_upscale and self.h != th)):
+        self.rgb_plan = None
+        if self.opts.output not in ("yuv420p", "rgb24") or self.opts.sample_every < 1:
+            raise ValueError("output must be 'yuv420p' or 'rgb24', sample_every >= 1")
+        if self.opts.output == "rgb24":
+            if self.opts.rgb_size:
+                self.out_w, self.out_h = (int(v) for v in self.opts.rgb_size)
+            elif th and self.h > th:
+                self.out_w, self.out_h = ops.scale_width_for_height(self.w, self.h, th), th
+            else:
+                self.out_w, self.out_h = self.w, self.h
+            self.plan = None
+            self.rgb_plan = ops.RgbPlan(self.w, self.h, self.out_w, self.out_h, self.opts.sws_flags)
+        elif th and (self.h > th or (not self.opts.never_upscale and self.h != th)):
             self.out_h = th
             self.out_w = ops.scale_width_for_height(self.w, self.h, th)
             self.plan = ops.ScalePlan(self.w, self.h, self.out_w, self.out_h, self.opts.sws_flags)
         else:
             self.out_w, self.out_h, self.plan = self.w, self.h, None
         self.frame_bytes = self.out_w * self.out_h + 2 * ((self.out_w + 1) // 2) * ((self.out_h + 1) // 2)
+        if self.rgb_plan is not None:
+            self.frame_bytes = self.out_w * self.out_h * 3
         B = self.opts.batch_frames
         self.B = B
         max_nal = int(sizes.max()) if n else 0
@@ -135,12 +155,16 @@ class SegmentIngestor:
                 "surf": torch.empty((B, self.rows, self.pitch), dtype=torch.uint8, device=self.dev),
                 "out": torch.empty((B, self.frame_bytes), dtype=torch.uint8, device=self.dev),
                 "out_host": torch.empty((B, self.frame_bytes), dtype=torch.uint8, pin_memory=True),
+                "sel_surf": (torch.empty((B, self.rows, self.pitch), dtype=torch.uint8, device=self.dev)
+                             if self.opts.sample_every > 1 else None),
+                "sel_idx": torch.empty(B, dtype=torch.int32, device=self.dev),
+                "sel_idx_host": torch.empty(B, dtype=torch.int32, pin_memory=True),
                 "sad": torch.empty(B, dtype=torch.int64, device=self.dev),
                 "hist": torch.empty((B, 256), dtype=torch.int32, device=self.dev),
                 "sad_host": torch.empty(B, dtype=torch.int64, pin_memory=True),
                 "hist_host": torch.empty((B, 256), dtype=torch.int32, pin_memory=True),
                 "ev_in": torch.cuda.Event(), "ev_cmp": torch.cuda.Event(), "ev_out": torch.cuda.Event(),
-                "used": False, "pending": None,
+                "used": False, "pending": None, "kept": None,
             })
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
         self.h2d_bytes = 0
@@ -200,9 +224,14 @@ class SegmentIngestor:
                 k0 = lo - b0
                 sad_all[lo - r0:hi - r0] = slot["sad_host"].numpy()[k0:k0 + hi - lo].view(np.uint64)
                 hist_all[lo - r0:hi - r0] = slot["hist_host"].numpy()[k0:k0 + hi - lo].view(np.uint32)
-            lo = max(b0, first)
-            if hi > lo and sink is not None and self.opts.keep_frames:
-                sink(slot["out_host"][lo - b0:hi - b0], lo)
+            if sink is not None and self.opts.keep_frames:
+                keep = slot["kept"]
+                if keep is None:                              # every picture from max(b0, first) on, in place
+                    lo = max(b0, first)
+                    if hi > lo:
+                        sink(slot["out_host"][lo - b0:hi - b0], lo)
+                elif len(keep):                               # sampled pictures, packed from row 0
+                    sink(slot["out_host"][:len(keep)], keep[0])
             slot["pending"] = None
 
         for i, (b0, b1) in enumerate(batches):
@@ -225,20 +254,42 @@ class SegmentIngestor:
                 check(L.vt_sad_hist_u8(c_void_p(surf.data_ptr()), self.pitch, self.surface_bytes, self.w, self.h,
                                        c_void_p(prev_surface.data_ptr()) if prev_surface is not None else None, nb,
                                        c_void_p(slot["sad"].data_ptr()), c_void_p(slot["hist"].data_ptr()), st))
-                if self.opts.keep_frames:
-                    if self.plan is not None:
-                        check(L.vt_scale_nv12_to_yuv420p(self.plan._h, c_void_p(surf.data_ptr()), self.pitch,
+                kept = None
+                src_t, n_conv, out_row0 = surf, nb, 0
+                if self.opts.keep_frames and self.opts.sample_every > 1:
+                    # sampled output: gather the kept surfaces (K5) and convert only those, packed from row 0
+                    kept = [k for k in range(max(b0, first), b1) if k % self.opts.sample_every == 0]
+                    n_conv = len(kept)
+                    if n_conv:
+                        slot["sel_idx_host"][:n_conv] = torch.tensor([k - b0 for k in kept], dtype=torch.int32)
+                        slot["sel_idx"][:n_conv].copy_(slot["sel_idx_host"][:n_conv], non_blocking=True)
+                        check(L.vt_gather_frames(c_void_p(surf.data_ptr()), self.surface_bytes, self.surface_bytes,
+                                                 c_void_p(slot["sel_idx"].data_ptr()), n_conv,
+                                                 c_void_p(slot["sel_surf"].data_ptr()), st))
+                        src_t = slot["sel_surf"]
+                slot["kept"] = kept
+                if self.opts.keep_frames and n_conv:
+                    if self.rgb_plan is not None:
+                        check(L.vt_scale_nv12_to_rgb24(self.rgb_plan._h, c_void_p(src_t.data_ptr()), self.pitch,
+                                                       self.surface_bytes, c_void_p(slot["out"].data_ptr()),
+                                                       self.frame_bytes, n_conv, st))
+                    elif self.plan is not None:
+                        check(L.vt_scale_nv12_to_yuv420p(self.plan._h, c_void_p(src_t.data_ptr()), self.pitch,
                                                          self.surface_bytes, c_void_p(slot["out"].data_ptr()),
-                                                         self.frame_bytes, nb, st))
+                                                         self.frame_bytes, n_conv, st))
                     else:
-                        check(L.vt_nv12_to_yuv420p(c_void_p(surf.data_ptr()), self.pitch, self.surface_bytes, self.w,
-                                                   self.h, c_void_p(slot["out"].data_ptr()), self.frame_bytes, nb, st))
+                        check(L.vt_nv12_to_yuv420p(c_void_p(src_t.data_ptr()), self.pitch, self.surface_bytes, self.w,
+                                                   self.h, c_void_p(slot["out"].data_ptr()), self.frame_bytes, n_conv, st))
                 slot["ev_cmp"].record(self.s_cmp)
                 prev_surface = surf[nb - 1]
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(slot["ev_cmp"])
                 lo = max(b0, first)
-                if self.opts.keep_frames and b1 > lo:
+                if self.opts.keep_frames and kept is not None:
+                    if len(kept):
+                        slot["out_host"][:len(kept)].copy_(slot["out"][:len(kept)], non_blocking=True)
+                        self.d2h_bytes += len(kept) * self.frame_bytes
+                elif self.opts.keep_frames and b1 > lo:
                     k0 = lo - b0
                     slot["out_host"][k0:nb].copy_(slot["out"][k0:nb], non_blocking=True)
                     self.d2h_bytes += (nb - k0) * self.frame_bytes
