@@ -16,6 +16,10 @@
 
 #include <vector>
 
+#include <string.h>
+
+#include <algorithm>
+
 #include "vt_common.cuh"
 
 namespace {
@@ -380,15 +384,22 @@ __device__ __forceinline__ uint32_t lds_u32_unaligned(const uint8_t *s, uint32_t
     return __funnelshift_r(w[0], w[1], (off & 3u) * 8u);
 }
 
+// Payload offsets of the pictures of one launch travel as a kernel parameter (constant bank): no device allocation,
+// no extra copy, nothing to free -- the call stays a single asynchronous launch.
+constexpr int PCM_FRAMES_PER_LAUNCH = 1024;
+struct PcmOffsets {
+    uint64_t off[PCM_FRAMES_PER_LAUNCH];
+};
+
 __global__ void __launch_bounds__(256)
-h264_pcm_kernel(const uint8_t *__restrict__ bs, const uint64_t *__restrict__ payload_off, int mb_w, int mb_h,
+h264_pcm_kernel(const uint8_t *__restrict__ bs, const __grid_constant__ PcmOffsets payload, int mb_w, int mb_h,
                 int width, int height, const uint8_t *__restrict__ prev, uint8_t *__restrict__ out, int pitch,
                 size_t frame_stride) {
     extern __shared__ __align__(16) uint8_t srow[];
     const int f = blockIdx.x / mb_h, my = blockIdx.x - f * mb_h;
     const int tid = threadIdx.x;
     uint8_t *dst = out + (size_t)f * frame_stride;
-    const uint64_t p0 = payload_off[f];
+    const uint64_t p0 = payload.off[f];
     const int wq = (width + 15) >> 4;  // 16 B groups per output row (pitch >= 16*wq is checked on the host)
     if (p0 == UINT64_MAX) {
         // skip picture with no IDR in this batch: repeat the carried-over surface
@@ -468,23 +479,20 @@ extern "C" int vt_h264_pcm_decode(const uint8_t *bs_dev, const uint64_t *payload
             return VT_ERR_INVALID;
         }
     cudaStream_t st = (cudaStream_t)stream;
-    // payload offsets travel through a small device buffer owned by this call's stream order
-    uint64_t *d_off = nullptr;
-    VT_CUDA(cudaMallocAsync((void **)&d_off, sizeof(uint64_t) * (size_t)n_frames, st));
-    cudaError_t e = cudaMemcpyAsync(d_off, payload_off, sizeof(uint64_t) * (size_t)n_frames, cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) { cudaFreeAsync(d_off, st); return vt::cuda_fail(e, "cudaMemcpyAsync(payload_off)"); }
     const size_t smem = (size_t)mb_w * 386 + 64;
     static size_t smem_set = 0;
     if (smem > 48 * 1024 && smem > smem_set) {
-        e = cudaFuncSetAttribute(vt::h264_pcm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { cudaFreeAsync(d_off, st); return vt::cuda_fail(e, "cudaFuncSetAttribute(h264_pcm)"); }
+        VT_CUDA(cudaFuncSetAttribute(vt::h264_pcm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    vt::h264_pcm_kernel<<<(unsigned)(n_frames * mb_h), 256, smem, st>>>(bs_dev, d_off, mb_w, mb_h, width, height,
-                                                                        prev_dev, nv12_dev, pitch, frame_stride);
-    vt::g_launches.fetch_add(1, std::memory_order_relaxed);
-    e = cudaGetLastError();
-    cudaFreeAsync(d_off, st);
-    if (e != cudaSuccess) return vt::cuda_fail(e, "h264_pcm_kernel");
+    for (int f0 = 0; f0 < n_frames; f0 += vt::PCM_FRAMES_PER_LAUNCH) {
+        const int nf = std::min(vt::PCM_FRAMES_PER_LAUNCH, n_frames - f0);
+        vt::PcmOffsets po;
+        memcpy(po.off, payload_off + f0, sizeof(uint64_t) * (size_t)nf);
+        vt::h264_pcm_kernel<<<(unsigned)(nf * mb_h), 256, smem, st>>>(bs_dev, po, mb_w, mb_h, width, height, prev_dev,
+                                                                     nv12_dev + (size_t)f0 * frame_stride, pitch,
+                                                                     frame_stride);
+        VT_LAUNCHED("h264_pcm_kernel");
+    }
     return VT_OK;
 }

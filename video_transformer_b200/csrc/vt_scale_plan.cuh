@@ -14,22 +14,9 @@ struct vt_scale_plan {
     int16_t *vcoef[2];  // dh x vtaps
     int32_t *vpos[2];
     int16_t *scratch;  // generic path: dw x sh int16
-    // host copies (streaming path work-list construction)
+    // host copies (table construction for the pair kernel)
     std::vector<int16_t> h_hcoef[2], h_vcoef[2];
     std::vector<int32_t> h_hpos[2], h_vpos[2];
-    // streaming path (one per plane kind): tables built by build_stream() at plan creation
-    struct Stream {
-        bool ok = false;
-        int hp = 0, tv = 0;     // dp2a pairs per output, (padded) vertical taps -> kernel instantiation
-        int cpt = 0;            // output columns per lane (per channel)
-        int strip_cols = 0, n_strips = 0;
-        int rows_out = 0, n_chunks = 0;
-        int tile_w = 0, tile_h = 0;
-        int warp_smem = 0;
-        int32_t *strip_x0 = nullptr;   // n_strips: first source byte of each strip's tile (multiple of 16)
-        uint32_t *lane_tab = nullptr;  // (n_strips*strip_cols) x (1+hp): source byte of tap 0, packed coef pairs
-        int32_t *vtab = nullptr;       // dh x (2+tv): first source row, last source row, front-padded coefs
-    } stream[2];
     // pair kernel (vt_scale_pair.cu), one per plane kind: tables built by vt::build_pair() at plan creation
     struct Pair {
         bool ok = false;

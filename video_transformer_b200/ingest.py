@@ -148,7 +148,10 @@ class SegmentIngestor:
         # worst case bytes one batch needs on the device: B pictures + their container framing
         self.bs_cap = (max_nal + 64) * min(B, max(1, int(index.keyframe.sum()))) + 4096 * B + 4096
         self.slots = []
-        for _ in range(2):
+        import os
+        self.n_slots = int(os.environ.get("VT_INGEST_SLOTS", "3"))   # batch i+1 is staged by a helper thread while i computes, i-1 copies out
+        self.stage_thread = os.environ.get("VT_INGEST_THREAD", "1") == "1"
+        for _ in range(self.n_slots):
             self.slots.append({
                 "bs_host": torch.empty(self.bs_cap, dtype=torch.uint8, pin_memory=True),
                 "bs_dev": torch.empty(self.bs_cap + 64, dtype=torch.uint8, device=self.dev),
@@ -169,6 +172,7 @@ class SegmentIngestor:
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self._pool = None
 
     # ------------------------------------------------------------------------------------------------------
     def _stage_bitstream(self, slot, b0: int, b1: int):
@@ -234,11 +238,28 @@ class SegmentIngestor:
                     sink(slot["out_host"][:len(keep)], keep[0])
             slot["pending"] = None
 
+        # The bitstream of batch i+1 is copied into its pinned staging buffer by a helper thread (numpy releases the
+        # GIL) while this thread enqueues batch i: the host side then keeps up with the D2H copy engine.
+        def stage(j):
+            sl = self.slots[j % self.n_slots]
+            sl["ev_in"].synchronize()        # the previous H2D out of this staging buffer has completed
+            return self._stage_bitstream(sl, *batches[j])
+
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=1)
+        staged = self._pool.submit(stage, 0) if (batches and self.stage_thread) else None
         for i, (b0, b1) in enumerate(batches):
-            slot = self.slots[i & 1]
-            drain(slot)                      # host may only refill pinned buffers whose copies completed
+            slot = self.slots[i % self.n_slots]
             nb = b1 - b0
-            pay, nbytes = self._stage_bitstream(slot, b0, b1)
+            if self.stage_thread:
+                pay, nbytes = staged.result()
+                drain(slot)                  # host may only reuse pinned/device buffers whose copies completed
+                if i + 1 < len(batches):
+                    staged = self._pool.submit(stage, i + 1)  # only touches that slot's pinned bitstream buffer
+            else:
+                drain(slot)
+                pay, nbytes = self._stage_bitstream(slot, b0, b1)
             with torch.cuda.stream(self.s_in):
                 if nbytes:
                     slot["bs_dev"][:nbytes].copy_(slot["bs_host"][:nbytes], non_blocking=True)

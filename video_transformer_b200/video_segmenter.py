@@ -67,6 +67,9 @@ _OPTIONS = {
     "scene_threshold": 0.10,
     "batch_frames": 32,
     "frame_buffers": True,     # run the GPU pass and write .frames/.json beside the MP4
+    "output": "yuv420p",       # or "rgb24" (the upload product: BASELINE.json configs[4])
+    "rgb_size": None,          # (width, height) of the RGB output, e.g. (768, 768)
+    "sample_every": 1,         # keep pictures whose index is a multiple of this (30 = 1 fps at 30 fps)
     "device": "cuda",
 }
 
@@ -191,7 +194,8 @@ def _ingest_to_files(idx, data, first: int, last: int, dst: Path) -> None:
     from . import ingest
     opts = ingest.IngestOptions(target_height=_OPTIONS["target_height"], sws_flags=_OPTIONS["sws_flags"],
                                 batch_frames=_OPTIONS["batch_frames"], scene_threshold=_OPTIONS["scene_threshold"],
-                                device=_OPTIONS["device"])
+                                output=_OPTIONS["output"], rgb_size=_OPTIONS["rgb_size"],
+                                sample_every=_OPTIONS["sample_every"], device=_OPTIONS["device"])
     eng = ingest.SegmentIngestor(idx, opts, host_bytes=data)
     sink = ingest.FileSink(_frames_path(dst))
     try:
@@ -201,7 +205,8 @@ def _ingest_to_files(idx, data, first: int, last: int, dst: Path) -> None:
     side = {
         "source": str(idx.path), "first_picture": first, "last_picture": last, "fps": [idx.fps_num, idx.fps_den],
         "source_size": [idx.width, idx.height], "frame_size": [res.out_width, res.out_height],
-        "pixel_format": "yuv420p", "frame_bytes": res.frame_bytes, "frames": sink.frames,
+        "pixel_format": opts.output, "sample_every": opts.sample_every, "frame_bytes": res.frame_bytes,
+        "frames": sink.frames,
         "scene_threshold": opts.scene_threshold, "cuts": [int(c) for c in res.cuts],
         "sad": [int(s) for s in res.sad], "score": [float(s) for s in res.scores],
     }
