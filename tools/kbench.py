@@ -56,6 +56,27 @@ if "scale" in ks:
     run("scale", lambda: _lib.check(L.vt_scale_nv12_to_yuv420p(plan._h, c_void_p(surf.data_ptr()), pitch, rows * pitch,
         c_void_p(out.data_ptr()), fb, F, sp)), sw * sh * 3 // 2 + fb)
     print(plan.stream_info(False), plan.stream_info(True))
+if "overlap" in ks:
+    # score and scale of the same surfaces on two streams (they do not depend on each other)
+    s2 = torch.cuda.Stream(dev)
+    sp2 = c_void_p(s2.cuda_stream)
+    ev_a, ev_b = torch.cuda.Event(), torch.cuda.Event()
+    def both():
+        ev_a.record(st)
+        s2.wait_event(ev_a)
+        _lib.check(L.vt_scale_nv12_to_yuv420p(plan._h, c_void_p(surf.data_ptr()), pitch, rows * pitch,
+                                              c_void_p(out.data_ptr()), fb, F, sp))
+        _lib.check(L.vt_sad_hist_u8(c_void_p(surf.data_ptr()), pitch, rows * pitch, sw, sh, None, F,
+                                    c_void_p(sad.data_ptr()), c_void_p(hist.data_ptr()), sp2))
+        ev_b.record(s2)
+        st.wait_event(ev_b)
+    run("scale||score", both, sw * sh * 3 // 2 + fb + 2 * sw * sh)
+    def serial():
+        _lib.check(L.vt_scale_nv12_to_yuv420p(plan._h, c_void_p(surf.data_ptr()), pitch, rows * pitch,
+                                              c_void_p(out.data_ptr()), fb, F, sp))
+        _lib.check(L.vt_sad_hist_u8(c_void_p(surf.data_ptr()), pitch, rows * pitch, sw, sh, None, F,
+                                    c_void_p(sad.data_ptr()), c_void_p(hist.data_ptr()), sp))
+    run("scale;score", serial, sw * sh * 3 // 2 + fb + 2 * sw * sh)
 if "score" in ks:
     run("score", lambda: _lib.check(L.vt_sad_hist_u8(c_void_p(surf.data_ptr()), pitch, rows * pitch, sw, sh, None, F,
         c_void_p(sad.data_ptr()), c_void_p(hist.data_ptr()), sp)), 2 * sw * sh)

@@ -370,7 +370,8 @@ int launch_t(const vt_scale_plan::Pair &s, const CUtensorMap &tm, PairArgs a, in
         // Grid: every SM full.  Segments per (frame, strip): the count that minimises rounds x rows per item, where a
         // round is one item per warp (a warp keeps its strip) and an item costs its source rows plus the TV-1 rows of
         // window overlap plus a few rows' worth of set-up.
-        const int grid = sm_count() * blocks_per_sm;
+        static const int grid_cap = getenv("VT_PAIR_GRID_BLOCKS") ? atoi(getenv("VT_PAIR_GRID_BLOCKS")) : 0;   // experiments
+        const int grid = sm_count() * ((grid_cap > 0 && grid_cap < blocks_per_sm) ? grid_cap : blocks_per_sm);
         const long long wps = std::max<long long>(1, (long long)grid * 4 / a.n_strips);   // warps per strip
         const double src_rows = (double)rows * s.src_rows_per_dst_row;
         int best = 1;
