@@ -256,7 +256,7 @@ def main():
     # ---- device-resident arm: whole bitstream in HBM, one step = decode + score + scale of 256 pictures ----------
     host = np.memmap(path, dtype=np.uint8, mode="r")
     bs_dev = torch.zeros(host.size + 64, dtype=torch.uint8, device=dev)
-    bs_dev[:host.size].copy_(torch.from_numpy(np.ascontiguousarray(host)))
+    bs_dev[:host.size].copy_(torch.from_numpy(np.array(host)))
     F = STEP_FRAMES
     surf = torch.empty((F, eng.rows, eng.pitch), dtype=torch.uint8, device=dev)
     out = torch.empty((F, fb), dtype=torch.uint8, device=dev)

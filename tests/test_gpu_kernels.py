@@ -79,6 +79,12 @@ def test_scale_plane_generic_bit_exact(cuda, oracle_c, flags, sw, sh, dw, dh):
     (1920, 1080, 1920, 1280, 720, ops.SWS_BILINEAR),
     (854, 480, 896, 640, 360, ops.SWS_BICUBIC),
     (1280, 720, 1280, 768, 768, ops.SWS_BICUBIC),
+    (1920, 1080, 1920, 1000, 562, ops.SWS_BICUBIC),     # ragged right edge: the last strip slides left
+    (1920, 1080, 2048, 854, 480, ops.SWS_BICUBIC),      # ratio 2.25: non-periodic phases, 10 horizontal taps
+    (1280, 720, 1280, 854, 480, ops.SWS_BICUBIC),
+    (3840, 2160, 3840, 1920, 1080, ops.SWS_BICUBIC),    # 1080 output rows: the vertical table spans two launches
+    (1920, 1080, 1920, 1280, 720, ops.SWS_BICUBIC | 0),
+    (640, 480, 640, 320, 240, ops.SWS_AREA),
 ])
 def test_scale_nv12_to_yuv420p_bit_exact(cuda, oracle_c, sw, sh, pitch, dw, dh, flags):
     rng = np.random.default_rng(sw * 3 + dw)
@@ -168,3 +174,36 @@ def test_nv12_to_rgb24_same_size_matches_committed_libswscale_output(cuda, oracl
         else:
             got = ops.RgbPlan(sw, sh, dw, dh).scale_nv12(src.view(-1), pitch, 1).cpu().numpy()[0]
         assert np.array_equal(got, gold[name + "_rgb"]), name
+
+
+def test_scaler_properties_at_full_config2_size(cuda):
+    """BASELINE.json configs[1] shape, 64 pictures per launch: properties that need no oracle.
+    (1) a flat picture stays flat (every filter row sums to one and the rounding terms cancel);
+    (2) a picture's output does not depend on its position in the batch (segment / strip scheduling);
+    (3) histogram mass and SAD symmetry on the same batch."""
+    sw, sh, pitch, dw, dh = 1920, 1080, 2048, 1280, 720
+    n = 64
+    g = torch.Generator(device="cpu").manual_seed(7)
+    base = torch.randint(0, 256, (sh + sh // 2, pitch), dtype=torch.uint8, generator=g)
+    buf = torch.empty((n, sh + sh // 2, pitch), dtype=torch.uint8)
+    buf[:] = base
+    for f, v in ((3, 0), (17, 255), (40, 77)):
+        buf[f] = v
+    buf[50] = torch.randint(0, 256, (sh + sh // 2, pitch), dtype=torch.uint8, generator=g)
+    d = buf.to(cuda)
+    plan = ops.ScalePlan(sw, sh, dw, dh, ops.SWS_BICUBIC)
+    assert plan.stream_info(False)["streaming"] == 1
+    out = plan.scale_nv12(d.view(-1), pitch, n)
+    for f, v in ((3, 0), (17, 255), (40, 77)):
+        assert bool((out[f] == v).all()), (f, v)
+    same = [f for f in range(n) if f not in (3, 17, 40, 50)]
+    ref = out[same[0]]
+    for f in same[1:]:
+        assert torch.equal(out[f], ref), f
+    assert not torch.equal(out[50], ref)
+    sad, hist = ops.sad_hist(d.view(-1), sw, sh, pitch, (sh + sh // 2) * pitch, n)
+    assert bool((hist.to(torch.int64).sum(dim=1) == sw * sh).all())
+    assert int(sad[1]) == 0 and int(sad[0]) == 0                 # identical neighbours
+    pair = torch.stack([buf[50], buf[49]]).to(cuda)             # SAD(a, b) == SAD(b, a)
+    s_ab, _ = ops.sad_hist(pair.view(-1), sw, sh, pitch, (sh + sh // 2) * pitch, 2)
+    assert int(s_ab[1]) == int(sad[50]) and int(sad[51]) == int(sad[50])

@@ -60,7 +60,10 @@ class H264PcmDecoder:
     def upload(self) -> None:
         # 64 bytes of slack: the kernel reads whole 16-byte groups around each macroblock row
         self.dev = torch.zeros(self.host.size + 64, dtype=torch.uint8, device=self.device)
-        self.dev[: self.host.size].copy_(torch.from_numpy(self.host), non_blocking=True)
+        import warnings
+        with warnings.catch_warnings():          # a read-only bitstream view is fine: it is only copied from
+            warnings.simplefilter("ignore", UserWarning)
+            self.dev[: self.host.size].copy_(torch.from_numpy(self.host), non_blocking=True)
 
     @property
     def duration(self) -> float:
