@@ -389,7 +389,10 @@ int vto_yuv_to_rgb24(const uint8_t *y, int y_pitch, const uint8_t *u, const uint
     const int64_t cgu = vto_cdiv(-25675LL * 65536 + 0x8000, cy), cgv = vto_cdiv(-53279LL * 65536 + 0x8000, cy);
     int cap_lh = vto_sws_max_taps(sw, dw, flags), cap_lv = vto_sws_max_taps(sh, dh, flags);
     int cap_ch = vto_sws_max_taps(csw, cdw, flags), cap_cv = vto_sws_max_taps(csh, dh, flags);
-    if (cap_lh < 4) cap_lh = 4; if (cap_lv < 4) cap_lv = 4; if (cap_ch < 4) cap_ch = 4; if (cap_cv < 4) cap_cv = 4;
+    if (cap_lh < 4) cap_lh = 4;
+    if (cap_lv < 4) cap_lv = 4;
+    if (cap_ch < 4) cap_ch = 4;
+    if (cap_cv < 4) cap_cv = 4;
     int16_t *lhc = malloc(sizeof(int16_t) * (size_t)dw * cap_lh), *lvc = malloc(sizeof(int16_t) * (size_t)dh * cap_lv);
     int16_t *chc = malloc(sizeof(int16_t) * (size_t)cdw * cap_ch), *cvc = malloc(sizeof(int16_t) * (size_t)dh * cap_cv);
     int32_t *lhp = malloc(4 * (size_t)dw), *lvp = malloc(4 * (size_t)dh), *chp = malloc(4 * (size_t)cdw),
