@@ -18,7 +18,9 @@ def _nv12_batch(rng, n, w, h, pitch, lo=0, hi=256):
 
 
 @pytest.mark.parametrize("w,h,pitch,n", [(1280, 720, 1280, 3), (1920, 1080, 2048, 2), (3840, 2160, 3840, 2),
-                                         (1000, 562, 1024, 3), (333, 77, 397, 4), (16, 16, 16, 2)])
+                                         (1000, 562, 1024, 3), (333, 77, 397, 4), (16, 16, 16, 2),
+                                         (8640, 24, 8704, 2),      # rows wider than 8160: counters flush mid-row
+                                         (7680, 4320, 7680, 1)])   # 8K: the largest picture NVDEC would hand over
 def test_sad_hist_matches_oracle(cuda, oracle_c, w, h, pitch, n):
     rng = np.random.default_rng(w * 7 + h)
     luma = rng.integers(0, 256, (n, h, pitch), dtype=np.uint8)
@@ -207,3 +209,23 @@ def test_scaler_properties_at_full_config2_size(cuda):
     pair = torch.stack([buf[50], buf[49]]).to(cuda)             # SAD(a, b) == SAD(b, a)
     s_ab, _ = ops.sad_hist(pair.view(-1), sw, sh, pitch, (sh + sh // 2) * pitch, 2)
     assert int(s_ab[1]) == int(sad[50]) and int(sad[51]) == int(sad[50])
+
+
+def test_bad_arguments_return_error_codes_not_crashes(cuda, vtlib):
+    from ctypes import c_void_p
+    from video_transformer_b200 import _lib
+    t = torch.zeros(4096, dtype=torch.uint8, device=cuda)
+    sad = torch.zeros(1, dtype=torch.int64, device=cuda)
+    hist = torch.zeros(256, dtype=torch.int32, device=cuda)
+    p = c_void_p(t.data_ptr())
+    assert vtlib.vt_sad_hist_u8(p, 8, 64, 16, 4, None, 1, c_void_p(sad.data_ptr()), c_void_p(hist.data_ptr()), None) == _lib.VT_ERR_INVALID
+    assert vtlib.vt_sad_hist_u8(p, 16, 64, 16, 4, None, 0, c_void_p(sad.data_ptr()), c_void_p(hist.data_ptr()), None) == _lib.VT_ERR_INVALID
+    assert vtlib.vt_nv12_to_yuv420p(None, 16, 64, 16, 4, p, 96, 1, None) == _lib.VT_ERR_INVALID
+    assert vtlib.vt_gather_frames(p, 64, 0, None, 1, p, None) == _lib.VT_ERR_INVALID
+    h = c_void_p()
+    from ctypes import byref
+    assert vtlib.vt_scale_plan_create(1, 1, 1, 1, 4, byref(h)) == _lib.VT_ERR_INVALID
+    assert vtlib.vt_rgb_plan_create(64, 48, 33, 24, 4, byref(h)) == _lib.VT_ERR_UNSUPPORTED       # odd output width
+    assert b"odd output width" in vtlib.vt_last_error()
+    plan = ops.ScalePlan(64, 48, 32, 24)
+    assert vtlib.vt_scale_nv12_to_yuv420p(plan._h, p, 32, 64 * 72, p, 32 * 24 * 3 // 2, 1, None) == _lib.VT_ERR_INVALID   # pitch < width
