@@ -148,3 +148,28 @@ def test_config5_sampled_rgb_frames(cuda, oracle_c, tmp_path):
     # scoring is unaffected by the sampling
     whole = ingest.SegmentIngestor(idx, ingest.IngestOptions(target_height=120, batch_frames=8, scene_threshold=0.05)).run(5, n, None)
     assert np.array_equal(res.sad, whole.sad) and res.cuts.tolist() == whole.cuts.tolist() and 41 in res.cuts.tolist()
+
+
+def test_config3_4k_scene_cuts_scores_only(cuda, oracle_c, tmp_path):
+    """BASELINE.json configs[2] shape (3840x2160, 60 fps), score-only pass: SADs are exact integers, scores are
+    bit-identical float64 and the cut list equals the scalar oracle's on the same decoded pictures.
+    (HEVC is not available on this pool: the clip is H.264 PCM-intra)"""
+    from oracle import scene_oracle
+    from video_transformer_b200 import ingest
+    w, h, n = 3840, 2160, 36
+    bs, meta = synth.make_testsrc_h264(w, h, n, fps=60, gop=12, cuts=[7, 20, 29])
+    raw = tmp_path / "uhd.h264"
+    raw.write_bytes(bs)
+    idx = container.probe(raw)
+    assert (idx.width, idx.height, idx.fps_num // idx.fps_den) == (w, h, 60)
+    opts = ingest.IngestOptions(keep_frames=False, batch_frames=8, scene_threshold=0.10)
+    res = ingest.SegmentIngestor(idx, opts).run(0, n, None)
+    exp = _expected(w, h, meta)
+    sads = [0] + [oracle_c.sad_hist(exp[k][0], exp[k - 1][0])[0] for k in range(1, n)]
+    assert res.sad.tolist() == sads
+    sc = scene_oracle.scene_scores(sads, w, h)
+    assert [float(x).hex() for x in res.scores] == [float(x).hex() for x in sc]
+    assert res.cuts.tolist() == scene_oracle.select_cuts(sc, 0.10)
+    assert set(meta["cuts"]) <= set(res.cuts.tolist())
+    for k in (0, 7, 35):
+        assert np.array_equal(res.hist[k], oracle_c.sad_hist(exp[k][0], None)[1])
