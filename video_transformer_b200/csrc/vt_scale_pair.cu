@@ -54,7 +54,7 @@ struct PairArgs {
     unsigned long long dst_fs;         // bytes between output frames
     unsigned long long dst_plane2;     // chroma: U plane -> V plane
     int n_frames, n_strips, n_segs, seg_rows;
-    int dw;                            // output width of this plane kind
+    unsigned int dw;                   // output width of this plane kind
     int y_begin, y_end;                // output rows covered by this launch (vtab row 0 = y_begin)
     int tile_w;                        // bytes per box row (always PAIR_TILE_W)
     int n_boxes;                       // TMA boxes per stage
@@ -219,6 +219,8 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         int vc[TV];
 #pragma unroll
         for (int j = 0; j < TV; j++) vc[j] = vtab.t[vi + j];
+        int last_next = vtab.t[vi + VS + TV];                                // row y+1's window end, fetched one row ahead so that
+                                                                             // the "does a row end here" branch never waits on a load
         uint8_t *dptr = a.dst + (size_t)f * a.dst_fs + (size_t)y0 * a.dw + strip_byte;
 
         uint32_t ga[NP];
@@ -269,7 +271,8 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             dptr += a.dw;
             if (y >= y1) return false;
             vi += VS;
-            vrel = vtab.t[vi + TV] - rbase;
+            vrel = last_next - rbase;
+            last_next = vtab.t[vi + VS + TV];                                // (one entry past the launch's rows is padding)
 #pragma unroll
             for (int j = 0; j < TV; j++) vc[j] = vtab.t[vi + j];
             return true;
@@ -360,7 +363,7 @@ int launch_t(const vt_scale_plan::Pair &s, const CUtensorMap &tm, PairArgs a, in
         smem_set = smem;
     }
     static VTab<TV> vt_host;                 // 28 KB staging for the parameter copy; filled under the launch lock
-    const int cap = VCfg<TV>::ROWS;
+    const int cap = VCfg<TV>::ROWS - 1;      // the kernel reads one table entry ahead
     for (int yb = 0; yb < rows_total; yb += cap) {
         const int ye = std::min(rows_total, yb + cap);
         std::memcpy(vt_host.t, s.vtab.data() + (size_t)yb * s.vstride, (size_t)(ye - yb) * s.vstride * sizeof(int32_t));
@@ -532,7 +535,7 @@ int launch_pair(const vt_scale_plan *p, int c, const uint8_t *src, int pitch, si
     a.n_frames = n_frames;
     a.n_strips = s.n_strips;
     a.n_segs = a.seg_rows = 0;
-    a.dw = uv ? p->cdw : p->dw;
+    a.dw = (unsigned)(uv ? p->cdw : p->dw);
     a.y_begin = a.y_end = 0;
     a.tile_w = s.tile_w;
     a.n_boxes = s.n_boxes;
