@@ -56,6 +56,77 @@ __global__ void k(int iters, uint32_t seed, uint32_t *out, const __grid_constant
     if (r == 0x12345678u) out[0] = r;
 }
 
+// The scaler's essential instruction mix with none of its bookkeeping: per iteration three "source rows"
+// (12 LDS + 8 funnel shifts + 28 dp2a + 8 shifts + 8 clamps each) and two "output rows" (48 IMAD + 8 shifts + 4 packs
+// + 4 16-bit stores each), eight independent columns per thread like the real kernel.  Tells how many of these
+// instructions per clock an SM can issue at best.
+__global__ void __launch_bounds__(128) scaler_mix(int iters, uint32_t seed, unsigned short *out) {
+    __shared__ uint32_t tile[128 * 16];
+    for (int i = threadIdx.x; i < 128 * 16; i += 128) tile[i] = seed * i;
+    __syncthreads();
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(tile) + threadIdx.x * 4;
+    uint32_t ca[4][3], cb[4][4], sh = ((seed + threadIdx.x) & 3) * 8;
+    int m[6][8], coef[6];
+    for (int g = 0; g < 4; g++) { for (int i = 0; i < 3; i++) ca[g][i] = seed + g + i + threadIdx.x; for (int i = 0; i < 4; i++) cb[g][i] = seed * 3 + g + i + threadIdx.x; }
+    for (int k = 0; k < 6; k++) { coef[k] = (int)seed + k; for (int c = 0; c < 8; c++) m[k][c] = k + c; }
+    unsigned short *dst = out + (size_t)(blockIdx.x * 4 + (threadIdx.x >> 5)) * 4 * 32 + (threadIdx.x & 31);   // 64 B per warp store
+    for (int it = 0; it < iters; it++) {
+        const uint32_t rowbase = base + (uint32_t)(it & 7) * 16;      // loop-variant addresses: nothing can be hoisted
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const int slot = r * 2;
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                uint32_t w0, w1, w2;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(rowbase + (uint32_t)(r * 512 + g * 12)));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(rowbase + (uint32_t)(r * 512 + g * 12 + 4)));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w2) : "r"(rowbase + (uint32_t)(r * 512 + g * 12 + 8)));
+                const uint32_t a0 = shf(w0, w1, sh), a1 = shf(w1, w2, sh);
+                int va = dp2a_lo(ca[g][0], a0, 0); va = dp2a_lo(ca[g][1], a0, va); va = dp2a_lo(ca[g][2], a1, va);
+                int vb = dp2a_lo(cb[g][0], a0, 0); vb = dp2a_lo(cb[g][1], a0, vb); vb = dp2a_lo(cb[g][2], a1, vb); vb = dp2a_lo(cb[g][3], a1, vb);
+                m[slot][2 * g] = vmin(va >> 7, 32767);
+                m[slot][2 * g + 1] = vmin(vb >> 7, 32767);
+            }
+            if (r != 1) {   // two of three rows complete an output row
+                int acc[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) acc[c] = 1 << 18;
+#pragma unroll
+                for (int j = 0; j < 6; j++)
+#pragma unroll
+                    for (int c = 0; c < 8; c++) acc[c] = imad(m[(slot + 1 + j) % 6][c], coef[j], acc[c]);
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const uint32_t pk = i2ip(acc[2 * g + 1] >> 19, acc[2 * g] >> 19);
+                    asm volatile("st.global.u16 [%0], %1;" ::"l"(dst + g * 32), "h"((unsigned short)pk) : "memory");
+                }
+            }
+        }
+    }
+}
+
+void run_scaler_mix(int blocks_per_sm) {
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    unsigned short *out; cudaMalloc(&out, (size_t)sms * blocks_per_sm * 128 * 8 * 2 + 64);
+    const int iters = 4000;
+    scaler_mix<<<sms * blocks_per_sm, 128>>>(10, 1, out);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    scaler_mix<<<sms * blocks_per_sm, 128>>>(iters, 1, out);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) printf("scaler_mix: %s\n", cudaGetErrorString(err));
+    int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+    const double per_iter = 3 * 64 + 2 * 64;                       // instructions per warp per iteration (essentials only)
+    const double winst = (double)iters * per_iter * 4 * blocks_per_sm;   // per SM
+    const double cycles = ms * 1e-3 * clk * 1e3;
+    const double px_per_clk = (double)iters * 2 * 8 * 128 * blocks_per_sm / cycles;   // output pixels per clock per SM
+    printf("(%.3f ms) scaler essential mix        warps/SM %2d : %.3f warp-instr/clk/SM (%.3f per SMSP), %.2f output px/clk/SM\n",
+           ms, 4 * blocks_per_sm, winst / cycles, winst / cycles / 4, px_per_clk);
+    cudaFree(out);
+}
+
 template <int MODE>
 void run(const char *name, int per_iter, int threads, int blocks_per_sm) {
     int sms = 148;
@@ -78,6 +149,9 @@ void run(const char *name, int per_iter, int threads, int blocks_per_sm) {
 }
 
 int main() {
+    run_scaler_mix(4);
+    run_scaler_mix(5);
+    run_scaler_mix(8);
     for (int w = 0; w < 2; w++) {
         const int threads = w ? 128 : 1024, bps = w ? 5 : 2;
         run<0>("IDP.2A", 1, threads, bps);

@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -61,6 +62,10 @@ struct PairArgs {
     int groups_per_stage;              // a stage holds groups_per_stage * TV source rows
     int box_bytes, stage_bytes, n_stages, warp_smem;
     int round_bias;                    // 1 << 18 (the vertical pass's rounding term)
+    // static vertical schedule (kernels instantiated with MASK != 0): output rows [reg_lo, reg_hi) repeat one pattern
+    // of window ends and coefficient sets every align_p source rows; segments start on rows = align_r0 (mod align_p)
+    int reg_lo, reg_hi, align_p, align_r0;
+    int sc[24];                        // [phase][TV] front-padded coefficients of the pattern's output rows
 };
 
 __device__ __forceinline__ int dp2a_lo(uint32_t coef_pair, uint32_t pix, int acc) {
@@ -125,9 +130,26 @@ constexpr uint32_t PAIR_TILE_W = VT_PAIR_WIDE ? 448 : 256;   // bytes per row of
 __host__ __device__ constexpr int pair_np(int hp, int tv) { return (VT_PAIR_WIDE && hp <= 3 && tv <= 8) ? 4 : 2; }   // luma pairs per lane
 __host__ __device__ constexpr int pair_min_blocks(int hp, int tv) { return (hp <= 4 && tv <= 8) ? VT_PAIR_BLOCKS : 3; }
 
+// compile-time loop: f(std::integral_constant<int, K>) for K = I .. N-1 (the row index must be a constant expression
+// so that ring slots, mask bits and coefficient offsets fold into the instructions)
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F &&f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+__host__ __device__ constexpr int popc_c(unsigned v) { return v ? (int)(v & 1u) + popc_c(v >> 1) : 0; }
+__host__ __device__ constexpr int ctz_c(unsigned v) { return (v & 1u) ? 0 : 1 + ctz_c(v >> 1); }
+
 // HP  dp2a pairs of the even column (taps padded to 2*HP); the odd column uses HP+1 pairs (rotated coefficients)
 // TV  vertical taps (front padded); UV: the source is NV12's interleaved chroma plane, a lane produces U and V
-template <int HP, int TV, bool UV>
+// MASK, Q  static vertical schedule for ratios whose vertical phases repeat inside a group of TV source rows
+//     (3:2, 2:1, 3:1): bit k of MASK = "an output row's window ends at row k of every regular group", Q = number of
+//     distinct coefficient sets.  Regular groups then run without any per-row branch or table fetch (coefficients
+//     are constant-bank operands of the IMADs); picture edges and MASK == 0 plans take the table-driven path.
+template <int HP, int TV, bool UV, int MASK, int Q>
 __global__ void __launch_bounds__(128, pair_min_blocks(HP, TV))
 scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ PairArgs a,
                   const __grid_constant__ VTab<TV> vtab) {
@@ -140,6 +162,8 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     constexpr int NQ = (NAW + 1) / 2;                 // chroma: de-interleaved words per channel
     constexpr int LT = (2 * HP + 2 + 3) & ~3;         // words per lane-table entry
     constexpr int VS = VCfg<TV>::STRIDE;
+    constexpr int NOUT = popc_c((unsigned)MASK);      // output rows per regular group
+    constexpr int FIRSTK = MASK ? ctz_c((unsigned)MASK) : 0;
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform for the compiler
@@ -190,7 +214,11 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         const int y0 = a.y_begin + seg * a.seg_rows;
         const int y1 = min(a.y_end, y0 + a.seg_rows);
         int vi = (y0 - a.y_begin) * VS;
-        const int rs = vtab.t[vi + TV] - (TV - 1);                          // first source row of the segment's windows
+        int rs = vtab.t[vi + TV] - (TV - 1);                                // first source row of the segment's windows
+        if (MASK) {                                                          // start on the pattern's row phase
+            int d = (rs - a.align_r0) % a.align_p;
+            rs -= d < 0 ? d + a.align_p : d;
+        }
         const int nrows = vtab.t[(y1 - 1 - a.y_begin) * VS + TV] + 1 - rs;  // source rows the segment needs
         const int ngroups = (nrows + TV - 1) / TV;
         const int nloads = (ngroups + rg - 1) / rg;
@@ -215,7 +243,9 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         const int rnd = a.round_bias;                                        // 1 << 18, from the parameters so that it lives in a
                                                                              // register and every tap is IMAD acc, m, UR(coef), acc
         int y = y0;
-        int vrel = TV - 1;                                                   // row (relative to the current group) completing row y
+        int vrel = vtab.t[vi + TV] - rs;                                     // row (relative to the current group) completing row y
+        const int ylim = min(y1, a.reg_hi);
+        bool stale = false;                                                  // vc[] / last_next do not belong to row y
         int vc[TV];
 #pragma unroll
         for (int j = 0; j < TV; j++) vc[j] = vtab.t[vi + j];
@@ -290,21 +320,53 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             for (int gis = 0; gis < ng; gis++) {
 #pragma unroll
                 for (int g = 0; g < NP; g++) ga[g] = addr[g] + goff;
+                if (MASK && vrel == FIRSTK && y >= a.reg_lo && y + NOUT <= ylim) {
+                    // ---- regular group: the schedule is static, coefficients are parameter-space constants
+                    static_for<0, TV>([&](auto kc) {
+                        constexpr int k = decltype(kc)::value;
+                        hpass(k, m[k]);
+                        if constexpr ((MASK >> k) & 1) {
+                            constexpr int q = popc_c((unsigned)MASK & ((1u << k) - 1u)) % Q;
+                            int acc[NM];
 #pragma unroll
-                for (int k = 0; k < TV; k++) {
-                    hpass(k, m[k]);
-                    // ---- vertical pass for every output row whose window ends at this source row
-                    while (vrel == k) {
-                        int acc[NM];
+                            for (int c = 0; c < NM; c++) acc[c] = rnd;
 #pragma unroll
-                        for (int c = 0; c < NM; c++) acc[c] = rnd;
+                            for (int j = 0; j < ((VT_ABLATE & 1) ? 1 : TV); j++) {
 #pragma unroll
-                        for (int j = 0; j < ((VT_ABLATE & 1) ? 1 : TV); j++) {
-#pragma unroll
-                            for (int c = 0; c < NM; c++) acc[c] += m[(k + 1 + j) % TV][c] * vc[j];
+                                for (int c = 0; c < NM; c++) acc[c] += m[(k + 1 + j) % TV][c] * a.sc[q * TV + j];
+                            }
+                            vstore(acc);
+                            dptr += a.dw;
                         }
-                        vstore(acc);
-                        if (!advance()) goto item_done;                      // the rest of this group's rows feed nothing
+                    });
+                    y += NOUT;
+                    vi += NOUT * VS;
+                    stale = true;
+                    if (y >= y1) goto item_done;
+                    vrel = vtab.t[vi + TV] - rbase;
+                } else {
+                    if (MASK && stale) {
+                        last_next = vtab.t[vi + VS + TV];
+#pragma unroll
+                        for (int j = 0; j < TV; j++) vc[j] = vtab.t[vi + j];
+                        stale = false;
+                    }
+#pragma unroll
+                    for (int k = 0; k < TV; k++) {
+                        hpass(k, m[k]);
+                        // ---- vertical pass for every output row whose window ends at this source row
+                        while (vrel == k) {
+                            int acc[NM];
+#pragma unroll
+                            for (int c = 0; c < NM; c++) acc[c] = rnd;
+#pragma unroll
+                            for (int j = 0; j < ((VT_ABLATE & 1) ? 1 : TV); j++) {
+#pragma unroll
+                                for (int c = 0; c < NM; c++) acc[c] += m[(k + 1 + j) % TV][c] * vc[j];
+                            }
+                            vstore(acc);
+                            if (!advance()) goto item_done;                  // the rest of this group's rows feed nothing
+                        }
                     }
                 }
                 vrel -= TV;
@@ -346,9 +408,9 @@ int upload(const void *h, size_t n, void **d) {
     return VT_OK;
 }
 
-template <int HP, int TV, bool UV>
+template <int HP, int TV, bool UV, int MASK, int Q>
 int launch_t(const vt_scale_plan::Pair &s, const CUtensorMap &tm, PairArgs a, int rows_total, cudaStream_t st) {
-    auto k = scale_pair_kernel<HP, TV, UV>;
+    auto k = scale_pair_kernel<HP, TV, UV, MASK, Q>;
     static int smem_set = 0, blocks_per_sm = 0;
     const int smem = s.warp_smem * 4;
     static std::mutex mu;
@@ -357,7 +419,7 @@ int launch_t(const vt_scale_plan::Pair &s, const CUtensorMap &tm, PairArgs a, in
         VT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         VT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k, 128, smem));
         if (blocks_per_sm < 1) {
-            set_error("scale_pair_kernel<%d,%d,%d>: does not fit an SM (smem %d)", HP, TV, (int)UV, smem);
+            set_error("scale_pair_kernel<%d,%d,%d,0x%x>: does not fit an SM (smem %d)", HP, TV, (int)UV, MASK, smem);
             return VT_ERR_UNSUPPORTED;
         }
         smem_set = smem;
@@ -385,6 +447,8 @@ int launch_t(const vt_scale_plan::Pair &s, const CUtensorMap &tm, PairArgs a, in
             if (cost < best_cost * 0.999) { best_cost = cost; best = n; }
         }
         a.seg_rows = (rows + best - 1) / best;
+        constexpr int nout = MASK ? popc_c((unsigned)MASK) : 1;   // whole regular groups per segment
+        a.seg_rows = (a.seg_rows + nout - 1) / nout * nout;
         a.n_segs = (rows + a.seg_rows - 1) / a.seg_rows;
         k<<<grid, 128, smem, st>>>(tm, a, vt_host);
         VT_LAUNCHED("scale_pair_kernel");
@@ -395,13 +459,75 @@ int launch_t(const vt_scale_plan::Pair &s, const CUtensorMap &tm, PairArgs a, in
 template <bool UV>
 int dispatch(int hp, int tv, const vt_scale_plan::Pair &s, const CUtensorMap &tm, const PairArgs &a, int rows,
              cudaStream_t st) {
-#define VT_CASE(H, T) if (hp == H && tv == T) return launch_t<H, T, UV>(s, tm, a, rows, st)
+    // static vertical schedules (exact 3:2, 2:1 and 3:1 ratios)
+    if (s.mask == 0x36 && s.n_phases == 2 && hp == 3 && tv == 6) return launch_t<3, 6, UV, 0x36, 2>(s, tm, a, rows, st);
+    if (s.mask == 0xAA && s.n_phases == 1 && hp == 4 && tv == 8) return launch_t<4, 8, UV, 0xAA, 1>(s, tm, a, rows, st);
+    if (s.mask == 0x924 && s.n_phases == 1 && hp == 6 && tv == 12) return launch_t<6, 12, UV, 0x924, 1>(s, tm, a, rows, st);
+#define VT_CASE(H, T) if (hp == H && tv == T) return launch_t<H, T, UV, 0, 1>(s, tm, a, rows, st)
     VT_CASE(3, 6); VT_CASE(3, 8); VT_CASE(3, 12);
     VT_CASE(4, 6); VT_CASE(4, 8); VT_CASE(4, 12);
     VT_CASE(6, 6); VT_CASE(6, 8); VT_CASE(6, 12);
 #undef VT_CASE
     set_error("scale_pair: no instantiation for hp=%d tv=%d", hp, tv);
     return VT_ERR_UNSUPPORTED;
+}
+
+// Finds the static vertical schedule of a plane, if it has one: output rows [reg_lo, reg_hi) whose window positions
+// advance by P source rows every Q output rows with Q repeating coefficient sets, P dividing the group size tv, and
+// an alignment (row phase r0 mod P) for which the window ends inside a group are exactly the canonical mask.
+void find_static_schedule(vt_scale_plan::Pair &s, const std::vector<int32_t> &vpos, const std::vector<int16_t> &vco,
+                          int vtaps, int src_rows, int dh) {
+    s.mask = 0;
+    s.n_phases = 1;
+    s.align_p = 1;
+    s.align_r0 = 0;
+    s.reg_lo = s.reg_hi = 0;
+    int g = src_rows, b = dh;
+    while (b) { const int t = g % b; g = b; b = t; }
+    const int P = src_rows / g, Q = dh / g;
+    const unsigned canon = (s.tv == 6 && P == 3 && Q == 2) ? 0x36u : (s.tv == 8 && P == 2 && Q == 1) ? 0xAAu
+                         : (s.tv == 12 && P == 3 && Q == 1) ? 0x924u : 0u;
+    if (!canon || dh < 8 * Q) return;
+    const int yref = (dh / 2) / Q * Q;
+    auto regular = [&](int y) {
+        int q = (y - yref) % Q;
+        if (q < 0) q += Q;
+        const int n = (y - yref - q) / Q;
+        if (vpos[y] != vpos[yref] + n * P + (vpos[yref + q] - vpos[yref])) return false;
+        for (int j = 0; j < vtaps; j++)
+            if (vco[(size_t)y * vtaps + j] != vco[(size_t)(yref + q) * vtaps + j]) return false;
+        return true;
+    };
+    int lo = yref, hi = yref;
+    while (lo > 0 && regular(lo - 1)) lo--;
+    while (hi < dh && regular(hi)) hi++;
+    if (hi - lo < 4 * Q) return;
+    // alignment: a group starting at row rb (inside the regular region) must see window ends exactly at the mask
+    for (int al = 0; al < P; al++) {
+        const int rb = vpos[yref] + vtaps + al;                 // first row after yref's window end, plus al
+        unsigned m = 0;
+        int y_first = -1;
+        for (int y = lo; y < hi; y++) {
+            const int last = vpos[y] + vtaps - 1;
+            if (last >= rb && last < rb + s.tv) {
+                m |= 1u << (last - rb);
+                if (y_first < 0) y_first = y;
+            }
+        }
+        if (m != canon || y_first < 0 || y_first + Q > hi) continue;
+        s.mask = (int)canon;
+        s.n_phases = Q;
+        s.align_p = P;
+        s.align_r0 = ((rb % P) + P) % P;
+        s.reg_lo = lo;
+        s.reg_hi = hi;
+        for (int q = 0; q < Q; q++)
+            for (int j = 0; j < s.tv; j++) s.sc[q * s.tv + j] = 0;
+        for (int q = 0; q < Q; q++)
+            for (int j = 0; j < vtaps; j++)
+                s.sc[q * s.tv + (s.tv - vtaps) + j] = vco[(size_t)(y_first + q) * vtaps + j];
+        return;
+    }
 }
 
 }  // namespace
@@ -490,6 +616,7 @@ int build_pair(vt_scale_plan *p, int c) {
             }
     }
     s.src_rows_per_dst_row = (double)(c ? p->csh : p->sh) / dh;
+    find_static_schedule(s, vpos, vco, vtaps, c ? p->csh : p->sh, dh);
     s.vstride = vstride_for(s.tv);
     s.vtab.assign((size_t)dh * s.vstride, 0);
     for (int y = 0; y < dh; y++) {
@@ -545,6 +672,11 @@ int launch_pair(const vt_scale_plan *p, int c, const uint8_t *src, int pitch, si
     a.n_stages = s.n_stages;
     a.warp_smem = s.warp_smem;
     a.round_bias = 1 << 18;
+    a.reg_lo = s.reg_lo;
+    a.reg_hi = s.reg_hi;
+    a.align_p = s.align_p;
+    a.align_r0 = s.align_r0;
+    for (int i = 0; i < 24; i++) a.sc[i] = s.sc[i];
     const int dh = uv ? p->cdh : p->dh;
     return uv ? dispatch<true>(s.hp, s.tv, s, tm, a, dh, st) : dispatch<false>(s.hp, s.tv, s, tm, a, dh, st);
 }

@@ -32,6 +32,9 @@ struct vt_scale_plan {
         std::vector<int32_t> vtab;     // dh x vstride: front-padded coefficients, then the window's last source row
         int vstride = 0;
         double src_rows_per_dst_row = 1.0;
+        // static vertical schedule (0 = none): see find_static_schedule()
+        int mask = 0, n_phases = 1, align_p = 1, align_r0 = 0, reg_lo = 0, reg_hi = 0;
+        int sc[24] = {0};
     } pair[2];
 };
 
