@@ -208,11 +208,19 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         for (int i = 0; i < BN; i++) cb[g][i] = wd[1 + HP + i];
     }
     const size_t strip_byte = (size_t)a.strip_col[strip] + 2 * lane;
-    for (int it = gw / a.n_strips; it < total; it += warps_per_strip) {
-        const int f = it / a.n_segs;
-        const int seg = it - f * a.n_segs;
+    // Work units are (frame, segment) pairs in frame-major order; a warp takes a CONTIGUOUS run of them, so vertically
+    // adjacent segments of one frame merge into one item (one ring warm-up, one pipeline start) and the unit size only
+    // sets the balancing granularity.
+    const int per_warp = (total + warps_per_strip - 1) / warps_per_strip;
+    int unit = (gw / a.n_strips) * per_warp;
+    const int unit_end = min(total, unit + per_warp);
+    while (unit < unit_end) {
+        const int f = unit / a.n_segs;
+        const int seg = unit - f * a.n_segs;
+        const int nseg = min(a.n_segs - seg, unit_end - unit);              // segments of this frame in the run
+        unit += nseg;
         const int y0 = a.y_begin + seg * a.seg_rows;
-        const int y1 = min(a.y_end, y0 + a.seg_rows);
+        const int y1 = min(a.y_end, y0 + nseg * a.seg_rows);
         int vi = (y0 - a.y_begin) * VS;
         int rs = vtab.t[vi + TV] - (TV - 1);                                // first source row of the segment's windows
         if (MASK) {                                                          // start on the pattern's row phase
@@ -432,23 +440,25 @@ int launch_t(const vt_scale_plan::Pair &s, const CUtensorMap &tm, PairArgs a, in
         a.y_begin = yb;
         a.y_end = ye;
         const int rows = ye - yb;
-        // Grid: every SM full.  Segments per (frame, strip): the count that minimises rounds x rows per item, where a
-        // round is one item per warp (a warp keeps its strip) and an item costs its source rows plus the TV-1 rows of
-        // window overlap plus a few rows' worth of set-up.
+        // Grid: every SM full.  Work units are (frame, segment); a warp keeps its strip and takes a contiguous run of
+        // units (adjacent segments of a frame merge into one item), so the segment height only sets the balancing
+        // granularity: pick the height (a multiple of the regular group's output rows) that minimises
+        // units per warp x rows per unit + items per warp x (window overlap + set-up).
         static const int grid_cap = getenv("VT_PAIR_GRID_BLOCKS") ? atoi(getenv("VT_PAIR_GRID_BLOCKS")) : 0;   // experiments
         const int grid = sm_count() * ((grid_cap > 0 && grid_cap < blocks_per_sm) ? grid_cap : blocks_per_sm);
         const long long wps = std::max<long long>(1, (long long)grid * 4 / a.n_strips);   // warps per strip
-        const double src_rows = (double)rows * s.src_rows_per_dst_row;
-        int best = 1;
+        constexpr int nout = MASK ? popc_c((unsigned)MASK) : 1;
+        int best_rows = rows;
         double best_cost = 1e30;
-        for (int n = 1; n <= std::max(1, rows / (2 * TV)); n++) {
-            const long long rounds = ((long long)a.n_frames * n + wps - 1) / wps;
-            const double cost = (double)rounds * (src_rows / n + (TV - 1) + 3.0);
-            if (cost < best_cost * 0.999) { best_cost = cost; best = n; }
+        for (int sr = nout; sr <= rows + nout - 1; sr += nout) {
+            if (sr < 2 * nout && sr < rows) continue;
+            const int n = (rows + sr - 1) / sr;
+            const long long upw = ((long long)a.n_frames * n + wps - 1) / wps;             // units per warp
+            const double items = 1.0 + (double)upw / n;                                    // frames a run touches
+            const double cost = (double)upw * sr * s.src_rows_per_dst_row + items * ((TV - 1) + 12.0);
+            if (cost < best_cost * 0.9995) { best_cost = cost; best_rows = sr; }
         }
-        a.seg_rows = (rows + best - 1) / best;
-        constexpr int nout = MASK ? popc_c((unsigned)MASK) : 1;   // whole regular groups per segment
-        a.seg_rows = (a.seg_rows + nout - 1) / nout * nout;
+        a.seg_rows = best_rows;
         a.n_segs = (rows + a.seg_rows - 1) / a.seg_rows;
         k<<<grid, 128, smem, st>>>(tm, a, vt_host);
         VT_LAUNCHED("scale_pair_kernel");
