@@ -164,6 +164,7 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     constexpr int VS = VCfg<TV>::STRIDE;
     constexpr int NOUT = popc_c((unsigned)MASK);      // output rows per regular group
     constexpr int FIRSTK = MASK ? ctz_c((unsigned)MASK) : 0;
+    constexpr int SG = TV <= 6 ? 2 : 1;               // groups per static block (= groups per TMA stage)
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform for the compiler
@@ -325,16 +326,19 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             groups_left -= ng;
             uint32_t goff = soff;
 #pragma unroll 1
-            for (int gis = 0; gis < ng; gis++) {
+            for (int gis = 0; gis < ng;) {
 #pragma unroll
                 for (int g = 0; g < NP; g++) ga[g] = addr[g] + goff;
-                if (MASK && vrel == FIRSTK && y >= a.reg_lo && y + NOUT <= ylim) {
-                    // ---- regular group: the schedule is static, coefficients are parameter-space constants
-                    static_for<0, TV>([&](auto kc) {
-                        constexpr int k = decltype(kc)::value;
-                        hpass(k, m[k]);
+                int adv = 1;                                                 // groups this iteration consumes
+                if (MASK && gis + SG <= ng && vrel == FIRSTK && y >= a.reg_lo && y + SG * NOUT <= ylim) {
+                    // ---- a whole stage of regular groups: the schedule is static (no branch, no table fetch), the
+                    // coefficients are parameter-space constants, and horizontal / vertical work of neighbouring rows
+                    // interleaves freely because it is one basic block
+                    static_for<0, SG * TV>([&](auto kc) {
+                        constexpr int kk = decltype(kc)::value, k = kk % TV;
+                        hpass(kk, m[k]);
                         if constexpr ((MASK >> k) & 1) {
-                            constexpr int q = popc_c((unsigned)MASK & ((1u << k) - 1u)) % Q;
+                            constexpr int q = (popc_c((unsigned)MASK & ((1u << k) - 1u)) + (kk / TV) * NOUT) % Q;
                             int acc[NM];
 #pragma unroll
                             for (int c = 0; c < NM; c++) acc[c] = rnd;
@@ -347,8 +351,9 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                             dptr += a.dw;
                         }
                     });
-                    y += NOUT;
-                    vi += NOUT * VS;
+                    adv = SG;
+                    y += SG * NOUT;
+                    vi += SG * NOUT * VS;
                     stale = true;
                     if (y >= y1) goto item_done;
                     vrel = vtab.t[vi + TV] - rbase;
@@ -377,9 +382,10 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                         }
                     }
                 }
-                vrel -= TV;
-                rbase += TV;
-                goff += group_bytes;
+                vrel -= adv * TV;
+                rbase += adv * TV;
+                goff += adv * group_bytes;
+                gis += adv;
             }
             __syncwarp();                                                    // every lane is done with this stage
             if (lane == 0 && ld + nst < nloads) {
