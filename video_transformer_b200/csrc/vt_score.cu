@@ -27,15 +27,11 @@ __device__ __forceinline__ void red_shared(uint32_t addr, uint32_t v) {
 }
 
 // 4 pixels of one 32-bit word.  base = (8 KB aligned warp region) | lane*4.
-// The ALU pipe (half rate on sm_100a: LOP3/SHF/PRMT issue every other cycle, tools/ubench_pipes.cu) is the busiest
-// one in this kernel, so the address arithmetic is split between the pipes: one PRMT (ALU) extracts the row of a
-// pixel, one IMAD (FMA pipe, otherwise idle here) turns it into the counter address; the increment is a wrapping
-// funnel shift of 1 by 8*(pixel >> 6), whose shift count needs no masking (only the low five bits count).
-__device__ __forceinline__ uint32_t counter_addr(uint32_t rows, uint32_t sel, uint32_t base) {
-    uint32_t a;
-    asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(a) : "r"(__byte_perm(rows, 0, sel)), "r"(base));
-    return a;
-}
+// The ALU pipe (half rate on sm_100a: LOP3/SHF/PRMT issue every other cycle, tools/ubench_pipes.cu) was the busiest
+// one in this kernel, so everything that is linear goes to the FMA pipe instead: the counter address of pixel k is
+// ONE dp4a, base + 128 * byte_k(rows) (u8 x u8 dot product with the one-hot vector 128 << 8k), and the shift count of
+// its increment is another dp4a that picks byte k of j8.  The increment itself is a wrapping funnel shift of 1
+// (only the low five bits of the count matter, so pixel 0 needs no extraction at all).
 __device__ __forceinline__ uint32_t one_shl_wrap(uint32_t n) {   // 1 << (n & 31)
     uint32_t d;
     asm("shf.l.wrap.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(0u), "r"(1u), "r"(n));
@@ -44,10 +40,10 @@ __device__ __forceinline__ uint32_t one_shl_wrap(uint32_t n) {   // 1 << (n & 31
 __device__ __forceinline__ void hist_word(uint32_t w, uint32_t base) {
     const uint32_t r = w & 0x3F3F3F3Fu;          // row index of each pixel
     const uint32_t j8 = (w >> 3) & 0x18181818u;  // 8 * (pixel >> 6): bit offset of its counter in the word
-    red_shared(counter_addr(r, 0x4440, base), one_shl_wrap(j8));
-    red_shared(counter_addr(r, 0x4441, base), one_shl_wrap(j8 >> 8));
-    red_shared(counter_addr(r, 0x4442, base), one_shl_wrap(j8 >> 16));
-    red_shared(counter_addr(r, 0x4443, base), one_shl_wrap(j8 >> 24));
+    red_shared(__dp4a(r, 0x00000080u, base), one_shl_wrap(j8));
+    red_shared(__dp4a(r, 0x00008000u, base), one_shl_wrap(__dp4a(j8, 0x00000100u, 0u)));
+    red_shared(__dp4a(r, 0x00800000u, base), one_shl_wrap(__dp4a(j8, 0x00010000u, 0u)));
+    red_shared(__dp4a(r, 0x80000000u, base), one_shl_wrap(__dp4a(j8, 0x01000000u, 0u)));
 }
 
 // Warp-collective: add the lane-private packed counters into the block histogram and clear them.
