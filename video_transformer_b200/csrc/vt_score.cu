@@ -98,6 +98,11 @@ __device__ __noinline__ void flush_counters_cold(uint32_t warp_cnt, uint32_t *bh
 }
 
 // Aligned fast path: luma/prev base and pitch are multiples of 16 bytes.
+// U = passes (of 32 lanes x 16 bytes) per unpredicated block of the row loop: min(4, full passes per row).  Rows are
+// walked as  [blocks of U full passes] [single full passes] [one partial pass with the byte mask of a ragged width];
+// only the last step carries predicates.  U = 0 keeps the fully general loop (rows wider than 4080 pixels per lane
+// budget, i.e. more than 15 passes, where the counters must be flushed inside a row).
+template <int U>
 __global__ void __launch_bounds__(SC_THREADS, 3)
 score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, int w, int h,
              const uint8_t *__restrict__ prev0, int rows_per_block, int chunks_per_frame, int chunks_per_block,
@@ -141,6 +146,64 @@ score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, i
         if (row >= r1) break;
         const uint8_t *crow = cur + (size_t)row * pitch;
         const uint8_t *prow = prv + (size_t)row * pitch;
+        if constexpr (U > 0) {
+            const int nfull = tail ? ngroups - 1 : ngroups;   // groups that need no byte mask
+            int g0 = 0;
+            for (; g0 + 32 * U <= nfull; g0 += 32 * U) {     // blocks of U full passes: all loads first
+                uint4 c[U ? U : 1], p[U ? U : 1];
+#pragma unroll
+                for (int k = 0; k < U; k++) {
+                    c[k] = ld_stream_u4(crow + (size_t)(g0 + k * 32 + lane) * 16);
+                    p[k] = ld_stream_u4(prow + (size_t)(g0 + k * 32 + lane) * 16);
+                }
+#pragma unroll
+                for (int k = 0; k < U; k++) {
+                    sad = sad4(c[k].x, p[k].x, sad);
+                    sad = sad4(c[k].y, p[k].y, sad);
+                    sad = sad4(c[k].z, p[k].z, sad);
+                    sad = sad4(c[k].w, p[k].w, sad);
+                    hist_word(c[k].x, base);
+                    hist_word(c[k].y, base);
+                    hist_word(c[k].z, base);
+                    hist_word(c[k].w, base);
+                }
+            }
+            for (; g0 + 32 <= nfull; g0 += 32) {             // single full passes
+                const uint4 c = ld_stream_u4(crow + (size_t)(g0 + lane) * 16);
+                const uint4 p = ld_stream_u4(prow + (size_t)(g0 + lane) * 16);
+                sad = sad4(c.x, p.x, sad);
+                sad = sad4(c.y, p.y, sad);
+                sad = sad4(c.z, p.z, sad);
+                sad = sad4(c.w, p.w, sad);
+                hist_word(c.x, base);
+                hist_word(c.y, base);
+                hist_word(c.z, base);
+                hist_word(c.w, base);
+            }
+            if (g0 + lane < ngroups) {                       // the partial pass; its last group may be ragged
+                uint4 c = ld_stream_u4(crow + (size_t)(g0 + lane) * 16);
+                uint4 p = ld_stream_u4(prow + (size_t)(g0 + lane) * 16);
+                if (tail && g0 + lane == ngroups - 1) {
+                    uint32_t m[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int nb = tail - 4 * q;
+                        m[q] = nb >= 4 ? 0xffffffffu : (nb <= 0 ? 0u : ((1u << (8 * nb)) - 1u));
+                    }
+                    c.x &= m[0]; c.y &= m[1]; c.z &= m[2]; c.w &= m[3];
+                    p.x &= m[0]; p.y &= m[1]; p.z &= m[2]; p.w &= m[3];
+                }
+                sad = sad4(c.x, p.x, sad);
+                sad = sad4(c.y, p.y, sad);
+                sad = sad4(c.z, p.z, sad);
+                sad = sad4(c.w, p.w, sad);
+                hist_word(c.x, base);
+                hist_word(c.y, base);
+                hist_word(c.z, base);
+                hist_word(c.w, base);
+            }
+            // (a lane sees at most 16 * 15 pixels of a row: no mid-row flush)
+        } else {
         // four passes (64 bytes per lane) at a time: all eight 128-bit loads are issued before the first counter
         // update, which is what keeps enough bytes in flight per SM
         for (int g0 = 0; g0 < ngroups; g0 += 128) {
@@ -188,6 +251,7 @@ score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, i
                 }
                 budget += 16;
             }
+        }
         }
     }
     flush_counters(warp_cnt, bhist, lane);
@@ -268,14 +332,22 @@ int launch_score(const uint8_t *luma, int pitch, size_t frame_stride, int w, int
         return VT_ERR_INVALID;
     }
     if (aligned) {
+        const int ngroups = (w + 15) >> 4;
+        const int npass = (ngroups + 31) / 32;
+        const int u = npass > 15 ? 0 : std::max(1, std::min(4, (w >> 4) / 32));
         static bool attr_done = false;
         if (!attr_done) {
-            VT_CUDA(cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
+            VT_CUDA(cudaFuncSetAttribute(score_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
+            VT_CUDA(cudaFuncSetAttribute(score_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
+            VT_CUDA(cudaFuncSetAttribute(score_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
+            VT_CUDA(cudaFuncSetAttribute(score_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
+            VT_CUDA(cudaFuncSetAttribute(score_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
             attr_done = true;
         }
-        score_kernel<<<(unsigned)blocks, SC_THREADS, SC_SMEM, st>>>(luma, pitch, frame_stride, w, h, prev0,
-                                                                  rows_per_block, chunks, cpb,
-                                                                  (unsigned long long *)sad, hist);
+        auto kern = u == 0 ? score_kernel<0> : u == 1 ? score_kernel<1> : u == 2 ? score_kernel<2>
+                  : u == 3 ? score_kernel<3> : score_kernel<4>;
+        kern<<<(unsigned)blocks, SC_THREADS, SC_SMEM, st>>>(luma, pitch, frame_stride, w, h, prev0, rows_per_block, chunks,
+                                                            cpb, (unsigned long long *)sad, hist);
         VT_LAUNCHED("score_kernel");
     } else {
         score_generic_kernel<<<(unsigned)blocks, 256, 0, st>>>(luma, pitch, frame_stride, w, h, prev0, rows_per_block,
