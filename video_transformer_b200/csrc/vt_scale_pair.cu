@@ -123,7 +123,7 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t phase) {
 #define VT_PAIR_WIDE 1                   // 0: measurement build with two column pairs per lane everywhere
 #endif
 #ifndef VT_PAIR_BLOCKS
-#define VT_PAIR_BLOCKS 4
+#define VT_PAIR_BLOCKS 5
 #endif
 constexpr uint32_t PAIR_TILE_W = VT_PAIR_WIDE ? 448 : 256;   // bytes per row of every TMA box (32-bit elements: up to 1024 B)
 
