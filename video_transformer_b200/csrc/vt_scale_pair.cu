@@ -86,6 +86,16 @@ __device__ __forceinline__ int dot_halfwords(const uint32_t (&c)[N], const uint3
     for (int i = 0; i < N; i++) v = (i & 1) ? dp2a_hi(c[i], w[i >> 1], v) : dp2a_lo(c[i], w[i >> 1], v);
     return v;
 }
+// The odd column of a pair: its taps start 0..2 samples right of the even column's.  Halfwords 1..HP-1 of the aligned
+// samples carry HP-1 coefficient pairs in place; the (at most two) samples that fall outside them are fetched into
+// one halfword by a byte permute (ALU pipe) and cost one more dp2a -- HP dp2a in all, like the even column.
+template <int HP>
+__device__ __forceinline__ int dot_odd(const uint32_t (&c)[HP], const uint32_t *w, uint32_t w_last, uint32_t sel) {
+    int v = dp2a_lo(c[HP - 1], __byte_perm(w[0], w_last, sel), 0);
+#pragma unroll
+    for (int i = 1; i < HP; i++) v = (i & 1) ? dp2a_hi(c[i - 1], w[i >> 1], v) : dp2a_lo(c[i - 1], w[i >> 1], v);
+    return v;
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -160,7 +170,7 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     constexpr int NAW = UV ? BN : (BN + 1) / 2;       // aligned 32-bit words holding a pair's source samples
     constexpr int NW = NAW + 1;                       // words fetched (one extra for the byte misalignment)
     constexpr int NQ = (NAW + 1) / 2;                 // chroma: de-interleaved words per channel
-    constexpr int LT = (2 * HP + 2 + 3) & ~3;         // words per lane-table entry
+    constexpr int LT = (2 * HP + 2 + 3) & ~3;         // words per lane-table entry: offset, HP + HP pairs, selector
     constexpr int VS = VCfg<TV>::STRIDE;
     constexpr int NOUT = popc_c((unsigned)MASK);      // output rows per regular group
     constexpr int FIRSTK = MASK ? ctz_c((unsigned)MASK) : 0;
@@ -191,7 +201,9 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     const int strip = gw % a.n_strips;
     const int total = a.n_frames * a.n_segs;
     // this lane's column pairs
-    uint32_t addr[NP], shb[NP], ca[NP][HP], cb[NP][BN];
+    // per pair: tile address, byte shift, even column's HP coefficient pairs; odd column: HP-1 pairs on the aligned
+    // halfwords 1..HP-1, one pair on the two leftover samples, and the byte selector that fetches those two samples
+    uint32_t addr[NP], shb[NP], ca[NP][HP], cb[NP][HP], selx[NP];
 #pragma unroll
     for (int g = 0; g < NP; g++) {
         const uint4 *t4 = reinterpret_cast<const uint4 *>(a.lane_tab + ((size_t)(strip * NP + g) * 32 + lane) * LT);
@@ -206,7 +218,8 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 #pragma unroll
         for (int i = 0; i < HP; i++) ca[g][i] = wd[1 + i];
 #pragma unroll
-        for (int i = 0; i < BN; i++) cb[g][i] = wd[1 + HP + i];
+        for (int i = 0; i < HP; i++) cb[g][i] = wd[1 + HP + i];
+        selx[g] = wd[1 + 2 * HP];
     }
     const size_t strip_byte = (size_t)a.strip_col[strip] + 2 * lane;
     // Work units are (frame, segment) pairs in frame-major order; a warp takes a CONTIGUOUS run of them, so vertically
@@ -277,7 +290,7 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                     for (int c = 0; c < NM / NP; c++) out[NM / NP * g + c] = (int)(al[c % NAW] ^ ca[g][c % HP]);
                 } else if (!UV) {
                     out[2 * g] = min(dot_halfwords<HP>(ca[g], al) >> 7, 32767);
-                    out[2 * g + 1] = min(dot_halfwords<BN>(cb[g], al) >> 7, 32767);
+                    out[2 * g + 1] = min(dot_odd<HP>(cb[g], al, al[NAW - 1], selx[g]) >> 7, 32767);
                 } else {
                     uint32_t uw[NQ], vw[NQ];
 #pragma unroll
@@ -287,9 +300,9 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                         vw[q] = __byte_perm(al[2 * q], hi, 0x7531);
                     }
                     out[4 * g] = min(dot_halfwords<HP>(ca[g], uw) >> 7, 32767);
-                    out[4 * g + 1] = min(dot_halfwords<BN>(cb[g], uw) >> 7, 32767);
+                    out[4 * g + 1] = min(dot_odd<HP>(cb[g], uw, uw[NQ - 1], selx[g]) >> 7, 32767);
                     out[4 * g + 2] = min(dot_halfwords<HP>(ca[g], vw) >> 7, 32767);
-                    out[4 * g + 3] = min(dot_halfwords<BN>(cb[g], vw) >> 7, 32767);
+                    out[4 * g + 3] = min(dot_odd<HP>(cb[g], vw, vw[NQ - 1], selx[g]) >> 7, 32767);
                 }
             }
         };
@@ -624,11 +637,29 @@ int build_pair(vt_scale_plan *p, int c) {
                     t[1 + j / 2] |= (j & 1) ? (v << 16) : v;
                 }
                 const int d = hpos[xb] - hpos[xa];                 // the odd column's taps start d samples further right
+                // samples 2..2*hp-1 (halfwords 1..hp-1) keep their place; what falls outside goes to the spare halfword
+                const int words = uv ? (bn + 1) / 2 : (bn + 1) / 2; // aligned words (luma) / de-interleaved words (chroma)
+                int spare[2] = {-1, -1}, nspare = 0;
                 for (int j = 0; j < ht; j++) {
                     const uint32_t v = (uint16_t)hco[(size_t)xb * ht + j];
                     const int sidx = d + j;
-                    t[1 + s.hp + sidx / 2] |= (sidx & 1) ? (v << 16) : v;
+                    if (sidx >= 2 && sidx < 2 * s.hp) {
+                        t[1 + s.hp + (sidx / 2 - 1)] |= (sidx & 1) ? (v << 16) : v;
+                    } else if (v) {
+                        if (nspare == 2) return VT_OK;             // cannot happen for d + ht <= 2*hp + 2; stay generic
+                        t[1 + s.hp + (s.hp - 1)] |= nspare ? (v << 16) : v;
+                        spare[nspare++] = sidx;
+                    }
                 }
+                // byte selector for __byte_perm(first word, last word, sel): low byte = spare[0], next = spare[1]
+                uint32_t sel = 0;
+                for (int q = 0; q < 2; q++) {
+                    int sidx = spare[q] < 0 ? 0 : spare[q];
+                    int code = sidx < 4 ? sidx : 4 + (sidx - 4 * (words - 1));
+                    if (code < 0 || code > 7) return VT_OK;
+                    sel |= (uint32_t)code << (4 * q);
+                }
+                t[1 + 2 * s.hp] = sel | 0x4400u;                   // upper halfword of the permute: don't care (zero coefficients)
             }
     }
     s.src_rows_per_dst_row = (double)(c ? p->csh : p->sh) / dh;
