@@ -216,6 +216,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample-frames", type=int, default=32768,
                     help="pictures the host-core baseline processes at N=1 (about 10 s of CPU work)")
+    ap.add_argument("--batch-frames", type=int, default=int(os.environ.get("VT_BENCH_BATCH", "32")),
+                    help="pictures per pipeline batch of the end-to-end arm")
     ap.add_argument("--cpu-step-frames", type=int, default=2048, help="pictures per step of --impl reference")
     args = ap.parse_args()
     K, Wm = args.steps, max(args.warmup, 0)
@@ -271,7 +273,7 @@ def main():
     n_clip = min(n_clip, 16 * STEP_FRAMES)              # bounded clip; steps cycle through its chunks
     path, idx, cuts = make_clip(n_clip, tmpdir)
     n_chunks = n_clip // STEP_FRAMES
-    opts = ingest.IngestOptions(target_height=OUT_H, batch_frames=32, device=str(dev))
+    opts = ingest.IngestOptions(target_height=OUT_H, batch_frames=args.batch_frames, device=str(dev))
     eng = ingest.SegmentIngestor(idx, opts)
     dw, dh, fb = eng.out_w, eng.out_h, eng.frame_bytes
 

@@ -107,6 +107,19 @@ __device__ __forceinline__ uint32_t pack_sat_u8x2(int hi, int lo) {
     asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(lo), "r"(0u));
     return d;
 }
+// sat_u8 of four results, b0 in the low byte (two I2IP: the second takes the first as its upper half)
+__device__ __forceinline__ uint32_t pack_sat_u8x4(int b3, int b2, int b1, int b0) {
+    uint32_t t, d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(b3), "r"(b2), "r"(0u));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(b1), "r"(b0), "r"(t));
+    return d;
+}
+__device__ __forceinline__ void st_u32(uint8_t *p, uint32_t v) {
+    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_u32x2(uint8_t *p, uint32_t lo, uint32_t hi) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(lo), "r"(hi) : "memory");
+}
 __device__ __forceinline__ void st_u16(uint8_t *p, uint32_t v) {
     if (VT_ABLATE & 8) {
         if (v == 0x12345u) asm volatile("st.global.L1::no_allocate.u16 [%0], %1;" ::"l"(p), "h"((unsigned short)v) : "memory");
@@ -159,7 +172,13 @@ __host__ __device__ constexpr int ctz_c(unsigned v) { return (v & 1u) ? 0 : 1 + 
 //     (3:2, 2:1, 3:1): bit k of MASK = "an output row's window ends at row k of every regular group", Q = number of
 //     distinct coefficient sets.  Regular groups then run without any per-row branch or table fetch (coefficients
 //     are constant-bank operands of the IMADs); picture edges and MASK == 0 plans take the table-driven path.
-template <int HP, int TV, bool UV, int MASK, int Q>
+// HS  static horizontal pattern (exact 3:2 ratio, HP == 3): a lane owns 2*NP ADJACENT output columns, i.e. a 12-byte
+//     step of the source per lane.  Column c's first tap then sits at a fixed byte offset of the lane's window
+//     (luma 2,3,5,6,8,9,11,12; chroma samples 0,1,3,4), so the alignment of every tap pair is a compile-time choice
+//     between the loaded words and ONE byte-shifted copy of them (luma), or one byte permute per sample pair that
+//     serves U (dp2a.lo) and V (dp2a.hi) at once (chroma).  Five loads per source row per lane instead of twelve,
+//     no per-pair shifts or selectors, and the lane's output bytes leave as one 8-byte (2 x 4-byte) store.
+template <int HP, int TV, bool UV, int MASK, int Q, int HS>
 __global__ void __launch_bounds__(128, pair_min_blocks(HP, TV))
 scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ PairArgs a,
                   const __grid_constant__ VTab<TV> vtab) {
@@ -203,9 +222,29 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     // this lane's column pairs
     // per pair: tile address, byte shift, even column's HP coefficient pairs; odd column: HP-1 pairs on the aligned
     // halfwords 1..HP-1, one pair on the two leftover samples, and the byte selector that fetches those two samples
+    constexpr int NCOL = 2 * NP;                      // HS: adjacent output columns per lane
     uint32_t addr[NP], shb[NP], ca[NP][HP], cb[NP][HP], selx[NP];
+    uint32_t hc[HS ? NCOL : 1][HP];                   // HS: coefficient pairs of column c, placed on its nominal window
+    int hs_xa = 0;
+    if constexpr (HS) {
+        static_assert(!HS || (NCOL * HP) % 4 == 0, "lane entries are fetched as 16-byte words");
+        const uint4 *t4 = reinterpret_cast<const uint4 *>(a.lane_tab + ((size_t)strip * 32 + lane) * (NCOL * HP));
 #pragma unroll
-    for (int g = 0; g < NP; g++) {
+        for (int i = 0; i < NCOL * HP / 4; i++) {
+            const uint4 q = __ldg(t4 + i);
+            hc[(4 * i) / HP][(4 * i) % HP] = q.x;
+            hc[(4 * i + 1) / HP][(4 * i + 1) % HP] = q.y;
+            hc[(4 * i + 2) / HP][(4 * i + 2) % HP] = q.z;
+            hc[(4 * i + 3) / HP][(4 * i + 3) % HP] = q.w;
+        }
+        // the strip's source window starts 4 bytes left of lane 0's nominal taps.  A TMA box must start on a 16-byte
+        // boundary (measured: 4-byte starts fault) but may start left of column 0 (zero fill), so round down
+        const int x0 = a.box_x0[strip];
+        hs_xa = x0 & ~15;
+        addr[0] = wsm + 12u * (uint32_t)lane + (uint32_t)(x0 - hs_xa);
+    }
+#pragma unroll
+    for (int g = 0; g < (HS ? 0 : NP); g++) {
         const uint4 *t4 = reinterpret_cast<const uint4 *>(a.lane_tab + ((size_t)(strip * NP + g) * 32 + lane) * LT);
         uint32_t wd[LT];
 #pragma unroll
@@ -221,7 +260,7 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         for (int i = 0; i < HP; i++) cb[g][i] = wd[1 + HP + i];
         selx[g] = wd[1 + 2 * HP];
     }
-    const size_t strip_byte = (size_t)a.strip_col[strip] + 2 * lane;
+    const size_t strip_byte = (size_t)a.strip_col[strip] + (HS ? (UV ? 4 : 8) : 2) * lane;
     // Work units are (frame, segment) pairs in frame-major order; a warp takes a CONTIGUOUS run of them, so vertically
     // adjacent segments of one frame merge into one item (one ring warm-up, one pipeline start) and the unit size only
     // sets the balancing granularity.
@@ -253,7 +292,7 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 #pragma unroll 1
                 for (int b = 0; b < a.n_boxes; b++)
                     tma_load_3d(wbase + (size_t)s * a.stage_bytes + (size_t)b * a.box_bytes, &tmap, &bars[s],
-                                a.box_x0[strip * a.n_boxes + b] >> 2, rs + s * stage_rows, f);
+                                (HS ? hs_xa : a.box_x0[strip * a.n_boxes + b]) >> 2, rs + s * stage_rows, f);
             }
         }
         int m[TV][NM];
@@ -277,6 +316,47 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 
         uint32_t ga[NP];
         auto hpass = [&](int k, int (&out)[NM]) {                            // horizontal pass of the group's row k
+            if constexpr (HS != 0) {
+                const uint32_t ra = ga[0] + (uint32_t)k * PAIR_TILE_W;
+                uint32_t w[5];
+#pragma unroll
+                for (int i = 0; i < 5; i++) w[i] = lds_u32(ra + 4u * i);
+                if constexpr (!UV) {
+                    uint32_t s1[4];                                          // the same bytes, one byte further on
+#pragma unroll
+                    for (int i = 0; i < 4; i++) s1[i] = __funnelshift_r(w[i], w[i + 1], 8);
+#pragma unroll
+                    for (int c = 0; c < NCOL; c++) {
+                        const int off = 2 + 3 * (c >> 1) + (c & 1), h = off >> 1;
+                        int v = 0;
+#pragma unroll
+                        for (int t = 0; t < HP; t++) {
+                            const int hw = h + t;
+                            const uint32_t word = (off & 1) ? s1[hw >> 1] : w[hw >> 1];
+                            v = (hw & 1) ? dp2a_hi(hc[c][t], word, v) : dp2a_lo(hc[c][t], word, v);
+                        }
+                        out[c] = min(v >> 7, 32767);
+                    }
+                } else {
+                    uint32_t pw[9];                                          // sample pair s: (U_s, U_s+1, V_s, V_s+1)
+#pragma unroll
+                    for (int sp = 0; sp < 9; sp++)
+                        pw[sp] = (sp & 1) ? __byte_perm(w[sp >> 1], w[(sp >> 1) + 1], 0x5342) : __byte_perm(w[sp >> 1], 0u, 0x3120);
+#pragma unroll
+                    for (int c = 0; c < NCOL; c++) {
+                        const int off = 3 * (c >> 1) + (c & 1);
+                        int u = 0, v = 0;
+#pragma unroll
+                        for (int t = 0; t < HP; t++) {
+                            u = dp2a_lo(hc[c][t], pw[off + 2 * t], u);
+                            v = dp2a_hi(hc[c][t], pw[off + 2 * t], v);
+                        }
+                        out[4 * (c >> 1) + (c & 1)] = min(u >> 7, 32767);
+                        out[4 * (c >> 1) + 2 + (c & 1)] = min(v >> 7, 32767);
+                    }
+                }
+                return;
+            }
 #pragma unroll
             for (int g = 0; g < NP; g++) {
                 uint32_t w[NW], al[NAW];
@@ -307,6 +387,18 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             }
         };
         auto vstore = [&](const int (&acc)[NM]) {                            // clamp, pack and store output row y
+            if constexpr (HS != 0) {
+                static_assert(!HS || NM == 8, "HS lanes hold eight results per row");
+                if (!UV) {
+                    const uint32_t lo = pack_sat_u8x4(acc[3] >> 19, acc[2] >> 19, acc[1] >> 19, acc[0] >> 19);
+                    const uint32_t hi = pack_sat_u8x4(acc[7] >> 19, acc[6] >> 19, acc[5] >> 19, acc[4] >> 19);
+                    st_u32x2(dptr, lo, hi);
+                } else {
+                    st_u32(dptr, pack_sat_u8x4(acc[5] >> 19, acc[4] >> 19, acc[1] >> 19, acc[0] >> 19));
+                    st_u32(dptr + a.dst_plane2, pack_sat_u8x4(acc[7] >> 19, acc[6] >> 19, acc[3] >> 19, acc[2] >> 19));
+                }
+                return;
+            }
 #pragma unroll
             for (int g = 0; g < NP; g++) {
                 if (!UV) {
@@ -341,7 +433,7 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 #pragma unroll 1
             for (int gis = 0; gis < ng;) {
 #pragma unroll
-                for (int g = 0; g < NP; g++) ga[g] = addr[g] + goff;
+                for (int g = 0; g < (HS ? 1 : NP); g++) ga[g] = addr[g] + goff;
                 int adv = 1;                                                 // groups this iteration consumes
                 if (MASK && gis + SG <= ng && vrel == FIRSTK && y >= a.reg_lo && y + SG * NOUT <= ylim) {
                     // ---- a whole stage of regular groups: the schedule is static (no branch, no table fetch), the
@@ -406,7 +498,7 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 #pragma unroll 1
                 for (int b = 0; b < a.n_boxes; b++)
                     tma_load_3d(wbase + soff + (size_t)b * a.box_bytes, &tmap, &bars[s],
-                                a.box_x0[strip * a.n_boxes + b] >> 2, rs + (ld + nst) * stage_rows, f);
+                                (HS ? hs_xa : a.box_x0[strip * a.n_boxes + b]) >> 2, rs + (ld + nst) * stage_rows, f);
             }
             s++;
             soff += (uint32_t)a.stage_bytes;
@@ -435,9 +527,9 @@ int upload(const void *h, size_t n, void **d) {
     return VT_OK;
 }
 
-template <int HP, int TV, bool UV, int MASK, int Q>
+template <int HP, int TV, bool UV, int MASK, int Q, int HS = 0>
 int launch_t(const vt_scale_plan::Pair &s, const CUtensorMap &tm, PairArgs a, int rows_total, cudaStream_t st) {
-    auto k = scale_pair_kernel<HP, TV, UV, MASK, Q>;
+    auto k = scale_pair_kernel<HP, TV, UV, MASK, Q, HS>;
     static int smem_set = 0, blocks_per_sm = 0;
     const int smem = s.warp_smem * 4;
     static std::mutex mu;
@@ -486,8 +578,10 @@ int launch_t(const vt_scale_plan::Pair &s, const CUtensorMap &tm, PairArgs a, in
 }
 
 template <bool UV>
-int dispatch(int hp, int tv, const vt_scale_plan::Pair &s, const CUtensorMap &tm, const PairArgs &a, int rows,
+int dispatch(int hp, int tv, bool hs, const vt_scale_plan::Pair &s, const CUtensorMap &tm, const PairArgs &a, int rows,
              cudaStream_t st) {
+    // static horizontal pattern + static vertical schedule (exact 3:2 both ways: 1080p -> 720p)
+    if (hs && s.mask == 0x36 && s.n_phases == 2 && hp == 3 && tv == 6) return launch_t<3, 6, UV, 0x36, 2, 1>(s, tm, a, rows, st);
     // static vertical schedules (exact 3:2, 2:1 and 3:1 ratios)
     if (s.mask == 0x36 && s.n_phases == 2 && hp == 3 && tv == 6) return launch_t<3, 6, UV, 0x36, 2>(s, tm, a, rows, st);
     if (s.mask == 0xAA && s.n_phases == 1 && hp == 4 && tv == 8) return launch_t<4, 8, UV, 0xAA, 1>(s, tm, a, rows, st);
@@ -671,7 +765,36 @@ int build_pair(vt_scale_plan *p, int c) {
         for (int j = 0; j < vtaps; j++) t[(s.tv - vtaps) + j] = vco[(size_t)y * vtaps + j];
         t[s.tv] = vpos[y] + vtaps - 1;
     }
+    // ---- static horizontal pattern (the kernel's HS parameter): exact 3:2, every column's taps inside the six-sample
+    // window that starts at 3*(x/2) - 2 + (x&1).  libswscale's edge columns (clamped position, taps folded onto the
+    // border sample) fit because the folded coefficients land on in-range samples of that same window; the samples
+    // left of column 0 / right of the last column are TMA zero fill and carry zero coefficients.
+    s.hs = false;
+    const int ncol = 2 * s.np, gran = uv ? 4 : 8;
+    std::vector<int32_t> bx_hs((size_t)s.n_strips);
+    std::vector<uint32_t> lt_hs((size_t)s.n_strips * 32 * ncol * 3, 0);
+    bool hs = s.hp == 3 && s.tv == 6 && s.mask == 0x36 && s.n_phases == 2 && s.n_boxes == 1 && dw % gran == 0 &&
+              !getenv("VT_PAIR_NO_HS");
+    for (int strip = 0; hs && strip < s.n_strips; strip++) {
+        bx_hs[strip] = bpp * (3 * scol[strip] / 2) - 4;
+        for (int lane = 0; hs && lane < 32; lane++)
+            for (int cidx = 0; hs && cidx < ncol; cidx++) {
+                const int x = scol[strip] + ncol * lane + cidx;
+                const int nominal = 3 * (x >> 1) - 2 + (x & 1);
+                uint32_t *t = &lt_hs[(((size_t)strip * 32 + lane) * ncol + cidx) * 3];
+                for (int j = 0; j < ht; j++) {
+                    const uint32_t v = (uint16_t)hco[(size_t)x * ht + j];
+                    if (!v) continue;
+                    const int tap = hpos[x] + j - nominal;
+                    if (tap < 0 || tap >= 6) { hs = false; break; }
+                    t[tap / 2] |= (tap & 1) ? (v << 16) : v;
+                }
+            }
+    }
     int rc = upload(bx.data(), bx.size() * 4, (void **)&s.box_x0);
+    if (rc == VT_OK && hs) rc = upload(bx_hs.data(), bx_hs.size() * 4, (void **)&s.box_x0_hs);
+    if (rc == VT_OK && hs) rc = upload(lt_hs.data(), lt_hs.size() * 4, (void **)&s.lane_tab_hs);
+    s.hs = hs && rc == VT_OK;
     if (rc == VT_OK) rc = upload(scol.data(), scol.size() * 4, (void **)&s.strip_col);
     if (rc == VT_OK) rc = upload(lt.data(), lt.size() * 4, (void **)&s.lane_tab);
     if (rc != VT_OK) return rc;
@@ -684,8 +807,10 @@ void free_pair(vt_scale_plan *p) {
         cudaFree(p->pair[c].box_x0);
         cudaFree(p->pair[c].strip_col);
         cudaFree(p->pair[c].lane_tab);
-        p->pair[c].box_x0 = p->pair[c].strip_col = nullptr;
-        p->pair[c].lane_tab = nullptr;
+        cudaFree(p->pair[c].box_x0_hs);
+        cudaFree(p->pair[c].lane_tab_hs);
+        p->pair[c].box_x0 = p->pair[c].strip_col = p->pair[c].box_x0_hs = nullptr;
+        p->pair[c].lane_tab = p->pair[c].lane_tab_hs = nullptr;
     }
 }
 
@@ -700,8 +825,12 @@ int launch_pair(const vt_scale_plan *p, int c, const uint8_t *src, int pitch, si
     int rc = make_tmap_u32_3d(&tm, base, row_bytes, rows, n_frames, pitch, src_fs, s.tile_w, s.stage_rows);
     if (rc) return rc;
     PairArgs a;
-    a.lane_tab = s.lane_tab;
-    a.box_x0 = s.box_x0;
+    // the adjacent-column layout stores 8 (luma) / 4 (chroma) bytes per lane: needs the planes aligned accordingly
+    const size_t ysz = (size_t)p->dw * p->dh, csz = (size_t)p->cdw * p->cdh;
+    const bool hs = s.hs && (uv ? ((uintptr_t)dst % 4 == 0 && dst_fs % 4 == 0 && ysz % 4 == 0 && csz % 4 == 0)
+                                : ((uintptr_t)dst % 8 == 0 && dst_fs % 8 == 0));
+    a.lane_tab = hs ? s.lane_tab_hs : s.lane_tab;
+    a.box_x0 = hs ? s.box_x0_hs : s.box_x0;
     a.strip_col = s.strip_col;
     a.dst = uv ? dst + (size_t)p->dw * p->dh : dst;
     a.dst_fs = dst_fs;
@@ -725,7 +854,7 @@ int launch_pair(const vt_scale_plan *p, int c, const uint8_t *src, int pitch, si
     a.align_r0 = s.align_r0;
     for (int i = 0; i < 24; i++) a.sc[i] = s.sc[i];
     const int dh = uv ? p->cdh : p->dh;
-    return uv ? dispatch<true>(s.hp, s.tv, s, tm, a, dh, st) : dispatch<false>(s.hp, s.tv, s, tm, a, dh, st);
+    return uv ? dispatch<true>(s.hp, s.tv, hs, s, tm, a, dh, st) : dispatch<false>(s.hp, s.tv, hs, s, tm, a, dh, st);
 }
 
 }  // namespace vt

@@ -35,6 +35,11 @@ struct vt_scale_plan {
         // static vertical schedule (0 = none): see find_static_schedule()
         int mask = 0, n_phases = 1, align_p = 1, align_r0 = 0, reg_lo = 0, reg_hi = 0;
         int sc[24] = {0};
+        // static horizontal pattern (exact 3:2): a lane owns 8 ADJACENT output columns (luma) / 4 (chroma); every
+        // column's tap alignment is then a compile-time constant.  Tables beside the generic ones; see build_pair()
+        bool hs = false;
+        int32_t *box_x0_hs = nullptr;  // n_strips: first source byte of the strip's single TMA box (multiple of 4, may be < 0)
+        uint32_t *lane_tab_hs = nullptr;  // (n_strips*32) x (columns per lane * hp) coefficient pairs
     } pair[2];
 };
 
