@@ -166,15 +166,47 @@ __device__ __forceinline__ void static_for(F &&f) {
 __host__ __device__ constexpr int popc_c(unsigned v) { return v ? (int)(v & 1u) + popc_c(v >> 1) : 0; }
 __host__ __device__ constexpr int ctz_c(unsigned v) { return (v & 1u) ? 0 : 1 + ctz_c(v >> 1); }
 
+// ---- static horizontal patterns (the kernel's HS parameter): 1 = exact 3:2, 2 = exact 2:1, 3 = exact 3:1 --------------
+// First source sample of output column x's nominal tap window (libswscale's interior positions for these ratios).
+__host__ __device__ constexpr int hs_nominal(int hs, int x) {
+    return hs == 1 ? 3 * (x >> 1) - 2 + (x & 1) : hs == 2 ? 2 * x - 3 : 3 * x - 4;
+}
+// Samples between the lane's (4-byte aligned) window start and its first column's nominal window.
+__host__ __device__ constexpr int hs_pre(int hs, bool uv) { return uv ? (hs == 2 ? 1 : 0) : (hs == 1 ? 2 : hs == 2 ? 1 : 0); }
+// Offset (samples) of column c's first tap inside the lane's window.
+__host__ __device__ constexpr int hs_off(int hs, bool uv, int c) { return hs_nominal(hs, c) - hs_nominal(hs, 0) + hs_pre(hs, uv); }
+// Source bytes a lane advances per lane index: its columns x ratio (x 2 bytes per chroma sample).
+__host__ __device__ constexpr int hs_lane_stride(int hs, bool uv, int ncol) {
+    return (hs == 1 ? 3 * ncol / 2 : hs == 2 ? 2 * ncol : 3 * ncol) * (uv ? 2 : 1);
+}
+// 32-bit words a lane fetches per source row.
+__host__ __device__ constexpr int hs_words(int hs, bool uv, int ncol, int hp) {
+    int hi = 0;
+    for (int c = 0; c < ncol; c++) {
+        const int off = hs_off(hs, uv, c);
+        int last = 0;
+        if (uv) {
+            const int sp = off + 2 * (hp - 1);                  // last sample pair (sp, sp+1): bytes 2sp .. 2sp+3
+            last = (sp & 1) ? (sp >> 1) + 1 : (sp >> 1);
+        } else {
+            const int hw = (off >> 1) + hp - 1;                 // last halfword of the (byte-shifted, if off is odd) stream
+            last = (off & 1) ? (hw >> 1) + 1 : (hw >> 1);
+        }
+        hi = last > hi ? last : hi;
+    }
+    return hi + 1;
+}
+
 // HP  dp2a pairs of the even column (taps padded to 2*HP); the odd column uses HP+1 pairs (rotated coefficients)
 // TV  vertical taps (front padded); UV: the source is NV12's interleaved chroma plane, a lane produces U and V
 // MASK, Q  static vertical schedule for ratios whose vertical phases repeat inside a group of TV source rows
 //     (3:2, 2:1, 3:1): bit k of MASK = "an output row's window ends at row k of every regular group", Q = number of
 //     distinct coefficient sets.  Regular groups then run without any per-row branch or table fetch (coefficients
 //     are constant-bank operands of the IMADs); picture edges and MASK == 0 plans take the table-driven path.
-// HS  static horizontal pattern (exact 3:2 ratio, HP == 3): a lane owns 2*NP ADJACENT output columns, i.e. a 12-byte
-//     step of the source per lane.  Column c's first tap then sits at a fixed byte offset of the lane's window
-//     (luma 2,3,5,6,8,9,11,12; chroma samples 0,1,3,4), so the alignment of every tap pair is a compile-time choice
+// HS  static horizontal pattern (1: exact 3:2 with HP 3, 2: exact 2:1 with HP 4, 3: exact 3:1 with HP 6): a lane owns
+//     2*NP ADJACENT output columns, i.e. a fixed step of the source per lane.  Column c's first tap then sits at a
+//     fixed offset of the lane's window (3:2 luma: bytes 2,3,5,6,8,9,11,12; chroma: samples 0,1,3,4), so the
+//     alignment of every tap pair is a compile-time choice
 //     between the loaded words and ONE byte-shifted copy of them (luma), or one byte permute per sample pair that
 //     serves U (dp2a.lo) and V (dp2a.hi) at once (chroma).  Five loads per source row per lane instead of twelve,
 //     no per-pair shifts or selectors, and the lane's output bytes leave as one 8-byte (2 x 4-byte) store.
@@ -241,7 +273,7 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         // boundary (measured: 4-byte starts fault) but may start left of column 0 (zero fill), so round down
         const int x0 = a.box_x0[strip];
         hs_xa = x0 & ~15;
-        addr[0] = wsm + 12u * (uint32_t)lane + (uint32_t)(x0 - hs_xa);
+        addr[0] = wsm + (uint32_t)hs_lane_stride(HS, UV, NCOL) * (uint32_t)lane + (uint32_t)(x0 - hs_xa);
     }
 #pragma unroll
     for (int g = 0; g < (HS ? 0 : NP); g++) {
@@ -260,7 +292,7 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         for (int i = 0; i < HP; i++) cb[g][i] = wd[1 + HP + i];
         selx[g] = wd[1 + 2 * HP];
     }
-    const size_t strip_byte = (size_t)a.strip_col[strip] + (HS ? (UV ? 4 : 8) : 2) * lane;
+    const size_t strip_byte = (size_t)a.strip_col[strip] + (HS ? NCOL : 2) * lane;
     // Work units are (frame, segment) pairs in frame-major order; a warp takes a CONTIGUOUS run of them, so vertically
     // adjacent segments of one frame merge into one item (one ring warm-up, one pipeline start) and the unit size only
     // sets the balancing granularity.
@@ -317,17 +349,18 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         uint32_t ga[NP];
         auto hpass = [&](int k, int (&out)[NM]) {                            // horizontal pass of the group's row k
             if constexpr (HS != 0) {
+                constexpr int NWD = hs_words(HS, UV, NCOL, HP);
                 const uint32_t ra = ga[0] + (uint32_t)k * PAIR_TILE_W;
-                uint32_t w[5];
+                uint32_t w[NWD];
 #pragma unroll
-                for (int i = 0; i < 5; i++) w[i] = lds_u32(ra + 4u * i);
+                for (int i = 0; i < NWD; i++) w[i] = lds_u32(ra + 4u * i);
                 if constexpr (!UV) {
-                    uint32_t s1[4];                                          // the same bytes, one byte further on
+                    uint32_t s1[NWD - 1];                                    // the same bytes, one byte further on
 #pragma unroll
-                    for (int i = 0; i < 4; i++) s1[i] = __funnelshift_r(w[i], w[i + 1], 8);
+                    for (int i = 0; i < NWD - 1; i++) s1[i] = __funnelshift_r(w[i], w[i + 1], 8);   // (unused ones fold away)
 #pragma unroll
                     for (int c = 0; c < NCOL; c++) {
-                        const int off = 2 + 3 * (c >> 1) + (c & 1), h = off >> 1;
+                        const int off = hs_off(HS, false, c), h = off >> 1;
                         int v = 0;
 #pragma unroll
                         for (int t = 0; t < HP; t++) {
@@ -338,13 +371,16 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                         out[c] = min(v >> 7, 32767);
                     }
                 } else {
-                    uint32_t pw[9];                                          // sample pair s: (U_s, U_s+1, V_s, V_s+1)
+                    constexpr int NPW = hs_off(HS, true, NCOL - 1) + 2 * (HP - 1) + 1;
+                    uint32_t pw[NPW];                                        // sample pair s: (U_s, U_s+1, V_s, V_s+1)
 #pragma unroll
-                    for (int sp = 0; sp < 9; sp++)
-                        pw[sp] = (sp & 1) ? __byte_perm(w[sp >> 1], w[(sp >> 1) + 1], 0x5342) : __byte_perm(w[sp >> 1], 0u, 0x3120);
+                    for (int sp = 0; sp < NPW; sp++) {
+                        const int wi = sp >> 1;
+                        pw[sp] = (sp & 1) ? __byte_perm(w[wi], w[wi + 1 < NWD ? wi + 1 : wi], 0x5342) : __byte_perm(w[wi], 0u, 0x3120);
+                    }
 #pragma unroll
                     for (int c = 0; c < NCOL; c++) {
-                        const int off = 3 * (c >> 1) + (c & 1);
+                        const int off = hs_off(HS, true, c);
                         int u = 0, v = 0;
 #pragma unroll
                         for (int t = 0; t < HP; t++) {
@@ -387,8 +423,7 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             }
         };
         auto vstore = [&](const int (&acc)[NM]) {                            // clamp, pack and store output row y
-            if constexpr (HS != 0) {
-                static_assert(!HS || NM == 8, "HS lanes hold eight results per row");
+            if constexpr (HS != 0 && NM == 8) {
                 if (!UV) {
                     const uint32_t lo = pack_sat_u8x4(acc[3] >> 19, acc[2] >> 19, acc[1] >> 19, acc[0] >> 19);
                     const uint32_t hi = pack_sat_u8x4(acc[7] >> 19, acc[6] >> 19, acc[5] >> 19, acc[4] >> 19);
@@ -399,6 +434,11 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 }
                 return;
             }
+            if constexpr (HS != 0 && NM == 4 && !UV) {
+                st_u32(dptr, pack_sat_u8x4(acc[3] >> 19, acc[2] >> 19, acc[1] >> 19, acc[0] >> 19));
+                return;
+            }
+            // (HS chroma with one column pair per lane stores its two 16-bit halves exactly like the generic layout)
 #pragma unroll
             for (int g = 0; g < NP; g++) {
                 if (!UV) {
@@ -582,6 +622,8 @@ int dispatch(int hp, int tv, bool hs, const vt_scale_plan::Pair &s, const CUtens
              cudaStream_t st) {
     // static horizontal pattern + static vertical schedule (exact 3:2 both ways: 1080p -> 720p)
     if (hs && s.mask == 0x36 && s.n_phases == 2 && hp == 3 && tv == 6) return launch_t<3, 6, UV, 0x36, 2, 1>(s, tm, a, rows, st);
+    if (hs && s.mask == 0xAA && s.n_phases == 1 && hp == 4 && tv == 8) return launch_t<4, 8, UV, 0xAA, 1, 2>(s, tm, a, rows, st);
+    if (hs && s.mask == 0x924 && s.n_phases == 1 && hp == 6 && tv == 12) return launch_t<6, 12, UV, 0x924, 1, 3>(s, tm, a, rows, st);
     // static vertical schedules (exact 3:2, 2:1 and 3:1 ratios)
     if (s.mask == 0x36 && s.n_phases == 2 && hp == 3 && tv == 6) return launch_t<3, 6, UV, 0x36, 2>(s, tm, a, rows, st);
     if (s.mask == 0xAA && s.n_phases == 1 && hp == 4 && tv == 8) return launch_t<4, 8, UV, 0xAA, 1>(s, tm, a, rows, st);
@@ -770,23 +812,28 @@ int build_pair(vt_scale_plan *p, int c) {
     // border sample) fit because the folded coefficients land on in-range samples of that same window; the samples
     // left of column 0 / right of the last column are TMA zero fill and carry zero coefficients.
     s.hs = false;
-    const int ncol = 2 * s.np, gran = uv ? 4 : 8;
+    const int ncol = 2 * s.np;                                   // adjacent output columns per lane
+    const int hsid = (s.hp == 3 && s.tv == 6 && s.mask == 0x36 && s.n_phases == 2) ? 1
+                   : (s.hp == 4 && s.tv == 8 && s.mask == 0xAA && s.n_phases == 1) ? 2
+                   : (s.hp == 6 && s.tv == 12 && s.mask == 0x924 && s.n_phases == 1) ? 3 : 0;
     std::vector<int32_t> bx_hs((size_t)s.n_strips);
-    std::vector<uint32_t> lt_hs((size_t)s.n_strips * 32 * ncol * 3, 0);
-    bool hs = s.hp == 3 && s.tv == 6 && s.mask == 0x36 && s.n_phases == 2 && s.n_boxes == 1 && dw % gran == 0 &&
-              !getenv("VT_PAIR_NO_HS");
+    std::vector<uint32_t> lt_hs((size_t)s.n_strips * 32 * ncol * s.hp, 0);
+    bool hs = hsid && s.n_boxes == 1 && dw % (uv ? std::max(ncol, 2) : std::max(ncol, 4)) == 0 && !getenv("VT_PAIR_NO_HS");
+    if (hs && hs_lane_stride(hsid, uv, ncol) * 31 + 4 * hs_words(hsid, uv, ncol, s.hp) + 12 > (int)PAIR_TILE_W) hs = false;
     for (int strip = 0; hs && strip < s.n_strips; strip++) {
-        bx_hs[strip] = bpp * (3 * scol[strip] / 2) - 4;
+        if (scol[strip] % ncol) { hs = false; break; }
+        bx_hs[strip] = bpp * (hs_nominal(hsid, scol[strip]) - hs_pre(hsid, uv));
+        if (bx_hs[strip] & 3) { hs = false; break; }             // lanes fetch aligned 32-bit words
         for (int lane = 0; hs && lane < 32; lane++)
             for (int cidx = 0; hs && cidx < ncol; cidx++) {
                 const int x = scol[strip] + ncol * lane + cidx;
-                const int nominal = 3 * (x >> 1) - 2 + (x & 1);
-                uint32_t *t = &lt_hs[(((size_t)strip * 32 + lane) * ncol + cidx) * 3];
+                const int nominal = hs_nominal(hsid, x);
+                uint32_t *t = &lt_hs[(((size_t)strip * 32 + lane) * ncol + cidx) * s.hp];
                 for (int j = 0; j < ht; j++) {
                     const uint32_t v = (uint16_t)hco[(size_t)x * ht + j];
                     if (!v) continue;
                     const int tap = hpos[x] + j - nominal;
-                    if (tap < 0 || tap >= 6) { hs = false; break; }
+                    if (tap < 0 || tap >= 2 * s.hp) { hs = false; break; }
                     t[tap / 2] |= (tap & 1) ? (v << 16) : v;
                 }
             }
@@ -825,7 +872,7 @@ int launch_pair(const vt_scale_plan *p, int c, const uint8_t *src, int pitch, si
     int rc = make_tmap_u32_3d(&tm, base, row_bytes, rows, n_frames, pitch, src_fs, s.tile_w, s.stage_rows);
     if (rc) return rc;
     PairArgs a;
-    // the adjacent-column layout stores 8 (luma) / 4 (chroma) bytes per lane: needs the planes aligned accordingly
+    // the adjacent-column layout stores up to 8 (luma) / 4 (chroma) bytes per lane: needs the planes aligned accordingly
     const size_t ysz = (size_t)p->dw * p->dh, csz = (size_t)p->cdw * p->cdh;
     const bool hs = s.hs && (uv ? ((uintptr_t)dst % 4 == 0 && dst_fs % 4 == 0 && ysz % 4 == 0 && csz % 4 == 0)
                                 : ((uintptr_t)dst % 8 == 0 && dst_fs % 8 == 0));
