@@ -106,7 +106,7 @@ template <int U>
 __global__ void __launch_bounds__(SC_THREADS, 3)
 score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, int w, int h,
              const uint8_t *__restrict__ prev0, int rows_per_block, int chunks_per_frame, int chunks_per_block,
-             unsigned long long *__restrict__ sad_out, uint32_t *__restrict__ hist_out) {
+             int merge_k, int merge_p, unsigned long long *__restrict__ sad_out, uint32_t *__restrict__ hist_out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t s0 = smem_u32(smem_raw);
@@ -136,18 +136,39 @@ score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, i
     const uint32_t base = warp_cnt | ((uint32_t)lane << 2);
     const int rpw = rows_per_block / SC_WARPS;   // consecutive rows owned by each warp
 
+    // Rows whose width is not a multiple of 512 pixels end in a partial pass with idle lanes.  With merge_k > 1 a warp
+    // walks merge_k rows at a time and packs their leftover groups into merge_p full-width passes (virtual index
+    // v = pass*32 + lane -> row v / rem, group v % rem): 1280 -> 2 rows share one pass, 1920 -> 4 rows share three.
+    constexpr int MAXP = 3;
+    const int nfull_all = (w & 15) ? ngroups - 1 : ngroups;   // groups that need no byte mask
+    const int gfull = nfull_all & ~31;                        // groups covered by full passes
+    const int rem = ngroups - gfull;
+    int moff[MAXP];                                           // byte offset from the first row of the group, < 0 = idle
+#pragma unroll
+    for (int j = 0; j < MAXP; j++) {
+        const int v = j * 32 + lane;
+        moff[j] = -1;
+        if (U > 0 && merge_k > 1 && j < merge_p && v < merge_k * rem)
+            moff[j] = (v / rem) * pitch + (gfull + v % rem) * 16;
+    }
+
     uint32_t sad = 0;
     for (int chunk = chunk0; chunk < chunk1; chunk++) {
     const int r0 = chunk * rows_per_block;
     const int r1 = min(h, r0 + rows_per_block);
     int budget = 0;                     // upper bound on pixels a lane has counted since the last flush
-    for (int rr = 0; rr < rpw; rr++) {
-        const int row = r0 + warp * rpw + rr;
-        if (row >= r1) break;
+    const int rstep = (U > 0 && merge_k > 1) ? merge_k : 1;
+    for (int rr = 0; rr < rpw; rr += rstep) {
+        const int row_a = r0 + warp * rpw + rr;
+        if (row_a >= r1) break;
+        const int nrows = min(rstep, min(r1 - row_a, rpw - rr));
+        const bool merged = rstep > 1 && nrows == rstep;
+        for (int ri = 0; ri < nrows; ri++) {
+        const int row = row_a + ri;
         const uint8_t *crow = cur + (size_t)row * pitch;
         const uint8_t *prow = prv + (size_t)row * pitch;
         if constexpr (U > 0) {
-            const int nfull = tail ? ngroups - 1 : ngroups;   // groups that need no byte mask
+            const int nfull = nfull_all;
             int g0 = 0;
             for (; g0 + 32 * U <= nfull; g0 += 32 * U) {     // blocks of U full passes: all loads first
                 uint4 c[U ? U : 1], p[U ? U : 1];
@@ -180,7 +201,7 @@ score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, i
                 hist_word(c.z, base);
                 hist_word(c.w, base);
             }
-            if (g0 + lane < ngroups) {                       // the partial pass; its last group may be ragged
+            if (!merged && g0 + lane < ngroups) {            // the partial pass; its last group may be ragged
                 uint4 c = ld_stream_u4(crow + (size_t)(g0 + lane) * 16);
                 uint4 p = ld_stream_u4(prow + (size_t)(g0 + lane) * 16);
                 if (tail && g0 + lane == ngroups - 1) {
@@ -253,6 +274,36 @@ score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, i
             }
         }
         }
+        }
+        if constexpr (U > 0) {
+            if (merged) {                                    // the rows' leftover groups, packed into full-width passes
+                const uint8_t *ca = cur + (size_t)row_a * pitch;
+                const uint8_t *pa = prv + (size_t)row_a * pitch;
+                uint4 c[MAXP], p[MAXP];
+#pragma unroll
+                for (int j = 0; j < MAXP; j++) {
+                    c[j] = make_uint4(0, 0, 0, 0);
+                    p[j] = c[j];
+                    if (j < merge_p && moff[j] >= 0) {
+                        c[j] = ld_stream_u4(ca + moff[j]);
+                        p[j] = ld_stream_u4(pa + moff[j]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < MAXP; j++) {
+                    if (j < merge_p && moff[j] >= 0) {
+                        sad = sad4(c[j].x, p[j].x, sad);
+                        sad = sad4(c[j].y, p[j].y, sad);
+                        sad = sad4(c[j].z, p[j].z, sad);
+                        sad = sad4(c[j].w, p[j].w, sad);
+                        hist_word(c[j].x, base);
+                        hist_word(c[j].y, base);
+                        hist_word(c[j].z, base);
+                        hist_word(c[j].w, base);
+                    }
+                }
+            }
+        }
     }
     flush_counters(warp_cnt, bhist, lane);
     }
@@ -318,6 +369,30 @@ int launch_score(const uint8_t *luma, int pitch, size_t frame_stride, int w, int
     int rpw = 255 / px_per_lane_row;
     if (rpw < 1) rpw = 1;
     if (rpw > 8) rpw = 8;
+    // Row merging (see the kernel): k rows share ceil(k * rem / 32) passes for their leftover groups.  Pick the k <= 8
+    // with the fewest passes per row whose pixel count per lane still fits the byte counters.
+    int merge_k = 1, merge_p = 0;
+    {
+        const int ng = (w + 15) >> 4, fullp = ng / 32, rem = ng - 32 * fullp;
+        static const bool off = getenv("VT_SCORE_NO_MERGE") != nullptr;
+        if (aligned && !off && (w & 15) == 0 && rem > 0 && fullp >= 1 && fullp + 1 <= 15) {
+            double best = fullp + 1.0;
+            for (int k = 2; k <= 8; k++) {
+                const int pk = (k * rem + 31) / 32;
+                if (pk > 3 || 16 * (k * fullp + pk) > 255) continue;
+                const double cost = (double)(k * fullp + pk) / k;
+                if (cost < best - 1e-9) { best = cost; merge_k = k; merge_p = pk; }
+            }
+            if (merge_k > 1) {
+                // a warp's last group may be cut by the picture's bottom edge; its rows then run unmerged
+                const int G = 16 * (merge_k * fullp + merge_p), cut = (merge_k - 1) * 16 * (fullp + 1);
+                int groups = 1;
+                while ((groups + 1) * merge_k <= 8 && (groups + 1) * G <= 255 && groups * G + cut <= 255) groups++;
+                if (cut > 255) merge_k = 1, merge_p = 0;
+                else rpw = merge_k * groups;
+            }
+        }
+    }
     const int rows_per_block = aligned ? rpw * SC_WARPS : 32;
     const int chunks = (h + rows_per_block - 1) / rows_per_block;
     // chunks per block: keep about six waves of blocks, fold the rest into fewer global atomics
@@ -347,7 +422,7 @@ int launch_score(const uint8_t *luma, int pitch, size_t frame_stride, int w, int
         auto kern = u == 0 ? score_kernel<0> : u == 1 ? score_kernel<1> : u == 2 ? score_kernel<2>
                   : u == 3 ? score_kernel<3> : score_kernel<4>;
         kern<<<(unsigned)blocks, SC_THREADS, SC_SMEM, st>>>(luma, pitch, frame_stride, w, h, prev0, rows_per_block, chunks,
-                                                            cpb, (unsigned long long *)sad, hist);
+                                                            cpb, merge_k, merge_p, (unsigned long long *)sad, hist);
         VT_LAUNCHED("score_kernel");
     } else {
         score_generic_kernel<<<(unsigned)blocks, 256, 0, st>>>(luma, pitch, frame_stride, w, h, prev0, rows_per_block,
