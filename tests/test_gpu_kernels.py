@@ -19,6 +19,9 @@ def _nv12_batch(rng, n, w, h, pitch, lo=0, hi=256):
 
 @pytest.mark.parametrize("w,h,pitch,n", [(1280, 720, 1280, 3), (1920, 1080, 2048, 2), (3840, 2160, 3840, 2),
                                          (1000, 562, 1024, 3), (333, 77, 397, 4), (16, 16, 16, 2),
+                                         # widths whose rows share leftover passes (k rows merged), heights that cut a group
+                                         (1280, 723, 1280, 2), (1920, 1083, 1920, 2), (768, 37, 768, 3),
+                                         (528, 61, 560, 2), (3840, 53, 3840, 2), (1040, 7, 1040, 2),
                                          (8640, 24, 8704, 2),      # rows wider than 8160: counters flush mid-row
                                          (7680, 4320, 7680, 1)])   # 8K: the largest picture NVDEC would hand over
 def test_sad_hist_matches_oracle(cuda, oracle_c, w, h, pitch, n):

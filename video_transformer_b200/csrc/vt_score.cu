@@ -12,6 +12,7 @@
 // neighbour.  A flush sums each row over the 32 lanes with rotated (conflict-free) word reads and adds the
 // four bins of the row to the block histogram.  SAD is VABSDIFF4 + IDP.4A on the same 128-bit loads.
 #include <algorithm>
+#include <type_traits>
 
 #include "vt_common.cuh"
 
@@ -163,6 +164,75 @@ score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, i
         if (row_a >= r1) break;
         const int nrows = min(rstep, min(r1 - row_a, rpw - rr));
         const bool merged = rstep > 1 && nrows == rstep;
+        if constexpr (U > 0) {
+            if (merged) {
+                // Full passes of the group's rows as ONE sequence of virtual passes, walked in blocks of U (then 2, then
+                // 1) with all loads of a block issued before its first counter update; then the packed leftover passes.
+                const uint8_t *ca = cur + (size_t)row_a * pitch;
+                const uint8_t *pa = prv + (size_t)row_a * pitch;
+                const int fullp = gfull >> 5, total = nrows * fullp;
+                size_t off = (size_t)lane * 16;
+                int pir = 0;                                 // pass inside the current row
+                auto block = [&](auto nbc) {
+                    constexpr int NB = decltype(nbc)::value;
+                    uint4 c[NB], p[NB];
+#pragma unroll
+                    for (int k = 0; k < NB; k++) {
+                        c[k] = ld_stream_u4(ca + off);
+                        p[k] = ld_stream_u4(pa + off);
+                        off += 512;
+                        if (++pir == fullp) {
+                            pir = 0;
+                            off += (size_t)pitch - (size_t)fullp * 512;
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < NB; k++) {
+                        sad = sad4(c[k].x, p[k].x, sad);
+                        sad = sad4(c[k].y, p[k].y, sad);
+                        sad = sad4(c[k].z, p[k].z, sad);
+                        sad = sad4(c[k].w, p[k].w, sad);
+                        hist_word(c[k].x, base);
+                        hist_word(c[k].y, base);
+                        hist_word(c[k].z, base);
+                        hist_word(c[k].w, base);
+                    }
+                };
+                int q = 0;
+                for (; q + U <= total; q += U) block(std::integral_constant<int, (U > 0 ? U : 1)>{});
+                if constexpr (U >= 3) {
+                    if (q + 2 <= total) {
+                        block(std::integral_constant<int, 2>{});
+                        q += 2;
+                    }
+                }
+                for (; q < total; q++) block(std::integral_constant<int, 1>{});
+                uint4 c[MAXP], p[MAXP];
+#pragma unroll
+                for (int j = 0; j < MAXP; j++) {
+                    c[j] = make_uint4(0, 0, 0, 0);
+                    p[j] = c[j];
+                    if (j < merge_p && moff[j] >= 0) {
+                        c[j] = ld_stream_u4(ca + moff[j]);
+                        p[j] = ld_stream_u4(pa + moff[j]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < MAXP; j++) {
+                    if (j < merge_p && moff[j] >= 0) {
+                        sad = sad4(c[j].x, p[j].x, sad);
+                        sad = sad4(c[j].y, p[j].y, sad);
+                        sad = sad4(c[j].z, p[j].z, sad);
+                        sad = sad4(c[j].w, p[j].w, sad);
+                        hist_word(c[j].x, base);
+                        hist_word(c[j].y, base);
+                        hist_word(c[j].z, base);
+                        hist_word(c[j].w, base);
+                    }
+                }
+                continue;
+            }
+        }
         for (int ri = 0; ri < nrows; ri++) {
         const int row = row_a + ri;
         const uint8_t *crow = cur + (size_t)row * pitch;
@@ -201,7 +271,7 @@ score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, i
                 hist_word(c.z, base);
                 hist_word(c.w, base);
             }
-            if (!merged && g0 + lane < ngroups) {            // the partial pass; its last group may be ragged
+            if (g0 + lane < ngroups) {                       // the partial pass; its last group may be ragged
                 uint4 c = ld_stream_u4(crow + (size_t)(g0 + lane) * 16);
                 uint4 p = ld_stream_u4(prow + (size_t)(g0 + lane) * 16);
                 if (tail && g0 + lane == ngroups - 1) {
@@ -275,35 +345,6 @@ score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, i
         }
         }
         }
-        if constexpr (U > 0) {
-            if (merged) {                                    // the rows' leftover groups, packed into full-width passes
-                const uint8_t *ca = cur + (size_t)row_a * pitch;
-                const uint8_t *pa = prv + (size_t)row_a * pitch;
-                uint4 c[MAXP], p[MAXP];
-#pragma unroll
-                for (int j = 0; j < MAXP; j++) {
-                    c[j] = make_uint4(0, 0, 0, 0);
-                    p[j] = c[j];
-                    if (j < merge_p && moff[j] >= 0) {
-                        c[j] = ld_stream_u4(ca + moff[j]);
-                        p[j] = ld_stream_u4(pa + moff[j]);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < MAXP; j++) {
-                    if (j < merge_p && moff[j] >= 0) {
-                        sad = sad4(c[j].x, p[j].x, sad);
-                        sad = sad4(c[j].y, p[j].y, sad);
-                        sad = sad4(c[j].z, p[j].z, sad);
-                        sad = sad4(c[j].w, p[j].w, sad);
-                        hist_word(c[j].x, base);
-                        hist_word(c[j].y, base);
-                        hist_word(c[j].z, base);
-                        hist_word(c[j].w, base);
-                    }
-                }
-            }
-        }
     }
     flush_counters(warp_cnt, bhist, lane);
     }
@@ -370,18 +411,24 @@ int launch_score(const uint8_t *luma, int pitch, size_t frame_stride, int w, int
     if (rpw < 1) rpw = 1;
     if (rpw > 8) rpw = 8;
     // Row merging (see the kernel): k rows share ceil(k * rem / 32) passes for their leftover groups.  Pick the k <= 8
-    // with the fewest passes per row whose pixel count per lane still fits the byte counters.
+    // with the fewest passes per row whose pixel count per lane still fits the byte counters; among equals the largest
+    // (measured on B200 at 1280 wide: k = 2 0.74, k = 6 0.82 of the roofline), walked in blocks of three passes
+    // (blocks of three beat four at every width measured: 0.85 against 0.80 at 1920 and 3840).
     int merge_k = 1, merge_p = 0;
     {
         const int ng = (w + 15) >> 4, fullp = ng / 32, rem = ng - 32 * fullp;
         static const bool off = getenv("VT_SCORE_NO_MERGE") != nullptr;
         if (aligned && !off && (w & 15) == 0 && rem > 0 && fullp >= 1 && fullp + 1 <= 15) {
             double best = fullp + 1.0;
+            static const int k_force = getenv("VT_SCORE_K") ? atoi(getenv("VT_SCORE_K")) : 0;   // A/B measurements
             for (int k = 2; k <= 8; k++) {
+                if (k_force && k != k_force) continue;
                 const int pk = (k * rem + 31) / 32;
                 if (pk > 3 || 16 * (k * fullp + pk) > 255) continue;
                 const double cost = (double)(k * fullp + pk) / k;
-                if (cost < best - 1e-9) { best = cost; merge_k = k; merge_p = pk; }
+                if (cost <= best + 1e-9 && (cost < best - 1e-9 || merge_k > 1)) {   // ties: the larger group (measured)
+                    best = cost; merge_k = k; merge_p = pk;
+                }
             }
             if (merge_k > 1) {
                 // a warp's last group may be cut by the picture's bottom edge; its rows then run unmerged
@@ -409,7 +456,9 @@ int launch_score(const uint8_t *luma, int pitch, size_t frame_stride, int w, int
     if (aligned) {
         const int ngroups = (w + 15) >> 4;
         const int npass = (ngroups + 31) / 32;
-        const int u = npass > 15 ? 0 : std::max(1, std::min(4, (w >> 4) / 32));
+        int u = npass > 15 ? 0 : merge_k > 1 ? std::min(3, merge_k * (ngroups / 32)) : std::max(1, std::min(4, (w >> 4) / 32));
+        static const int u_force = getenv("VT_SCORE_U") ? atoi(getenv("VT_SCORE_U")) : 0;   // A/B measurements
+        if (u_force > 0 && u > 0) u = std::min(4, u_force);
         static bool attr_done = false;
         if (!attr_done) {
             VT_CUDA(cudaFuncSetAttribute(score_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
