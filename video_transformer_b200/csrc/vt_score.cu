@@ -103,7 +103,9 @@ __device__ __noinline__ void flush_counters_cold(uint32_t warp_cnt, uint32_t *bh
 // walked as  [blocks of U full passes] [single full passes] [one partial pass with the byte mask of a ragged width];
 // only the last step carries predicates.  U = 0 keeps the fully general loop (rows wider than 4080 pixels per lane
 // budget, i.e. more than 15 passes, where the counters must be flushed inside a row).
-template <int U>
+// RAG = merged rows whose last group is ragged (width not a multiple of 16): a separate instantiation, because the
+// byte masks in the merged passes cost the common case 3 % even when they are never applied.
+template <int U, bool RAG>
 __global__ void __launch_bounds__(SC_THREADS, 3)
 score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, int w, int h,
              const uint8_t *__restrict__ prev0, int rows_per_block, int chunks_per_frame, int chunks_per_block,
@@ -145,12 +147,16 @@ score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, i
     const int gfull = nfull_all & ~31;                        // groups covered by full passes
     const int rem = ngroups - gfull;
     int moff[MAXP];                                           // byte offset from the first row of the group, < 0 = idle
+    bool mrag[MAXP];                                          // this lane's group is the row's ragged last one
 #pragma unroll
     for (int j = 0; j < MAXP; j++) {
         const int v = j * 32 + lane;
         moff[j] = -1;
-        if (U > 0 && merge_k > 1 && j < merge_p && v < merge_k * rem)
+        mrag[j] = false;
+        if (U > 0 && merge_k > 1 && j < merge_p && v < merge_k * rem) {
             moff[j] = (v / rem) * pitch + (gfull + v % rem) * 16;
+            mrag[j] = RAG && (v % rem == rem - 1);
+        }
     }
 
     uint32_t sad = 0;
@@ -216,6 +222,21 @@ score_kernel(const uint8_t *__restrict__ luma, int pitch, size_t frame_stride, i
                         c[j] = ld_stream_u4(ca + moff[j]);
                         p[j] = ld_stream_u4(pa + moff[j]);
                     }
+                }
+#pragma unroll
+                if constexpr (RAG) {                         // bytes past the width count as zeros
+#pragma unroll
+                    for (int j = 0; j < MAXP; j++)
+                        if (mrag[j]) {
+                            uint32_t m[4];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const int nb = tail - 4 * q;
+                                m[q] = nb >= 4 ? 0xffffffffu : (nb <= 0 ? 0u : ((1u << (8 * nb)) - 1u));
+                            }
+                            c[j].x &= m[0]; c[j].y &= m[1]; c[j].z &= m[2]; c[j].w &= m[3];
+                            p[j].x &= m[0]; p[j].y &= m[1]; p[j].z &= m[2]; p[j].w &= m[3];
+                        }
                 }
 #pragma unroll
                 for (int j = 0; j < MAXP; j++) {
@@ -418,7 +439,7 @@ int launch_score(const uint8_t *luma, int pitch, size_t frame_stride, int w, int
     {
         const int ng = (w + 15) >> 4, fullp = ng / 32, rem = ng - 32 * fullp;
         static const bool off = getenv("VT_SCORE_NO_MERGE") != nullptr;
-        if (aligned && !off && (w & 15) == 0 && rem > 0 && fullp >= 1 && fullp + 1 <= 15) {
+        if (aligned && !off && rem > 0 && fullp >= 1 && fullp + 1 <= 15) {
             double best = fullp + 1.0;
             static const int k_force = getenv("VT_SCORE_K") ? atoi(getenv("VT_SCORE_K")) : 0;   // A/B measurements
             for (int k = 2; k <= 8; k++) {
@@ -459,17 +480,20 @@ int launch_score(const uint8_t *luma, int pitch, size_t frame_stride, int w, int
         int u = npass > 15 ? 0 : merge_k > 1 ? std::min(3, merge_k * (ngroups / 32)) : std::max(1, std::min(4, (w >> 4) / 32));
         static const int u_force = getenv("VT_SCORE_U") ? atoi(getenv("VT_SCORE_U")) : 0;   // A/B measurements
         if (u_force > 0 && u > 0) u = std::min(4, u_force);
+        const bool rag = merge_k > 1 && (w & 15);
+        typedef void (*kern_t)(const uint8_t *, int, size_t, int, int, const uint8_t *, int, int, int, int, int,
+                               unsigned long long *, uint32_t *);
+        static const kern_t table[2][5] = {
+            {score_kernel<0, false>, score_kernel<1, false>, score_kernel<2, false>, score_kernel<3, false>, score_kernel<4, false>},
+            {score_kernel<0, false>, score_kernel<1, true>, score_kernel<2, true>, score_kernel<3, true>, score_kernel<4, true>}};
         static bool attr_done = false;
         if (!attr_done) {
-            VT_CUDA(cudaFuncSetAttribute(score_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
-            VT_CUDA(cudaFuncSetAttribute(score_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
-            VT_CUDA(cudaFuncSetAttribute(score_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
-            VT_CUDA(cudaFuncSetAttribute(score_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
-            VT_CUDA(cudaFuncSetAttribute(score_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
+            for (int r = 0; r < 2; r++)
+                for (int i = 0; i < 5; i++)
+                    VT_CUDA(cudaFuncSetAttribute(table[r][i], cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
             attr_done = true;
         }
-        auto kern = u == 0 ? score_kernel<0> : u == 1 ? score_kernel<1> : u == 2 ? score_kernel<2>
-                  : u == 3 ? score_kernel<3> : score_kernel<4>;
+        kern_t kern = table[rag ? 1 : 0][u];
         kern<<<(unsigned)blocks, SC_THREADS, SC_SMEM, st>>>(luma, pitch, frame_stride, w, h, prev0, rows_per_block, chunks,
                                                             cpb, merge_k, merge_p, (unsigned long long *)sad, hist);
         VT_LAUNCHED("score_kernel");
