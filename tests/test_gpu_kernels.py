@@ -23,6 +23,7 @@ def _nv12_batch(rng, n, w, h, pitch, lo=0, hi=256):
                                          (1280, 723, 1280, 2), (1920, 1083, 1920, 2), (768, 37, 768, 3),
                                          (528, 61, 560, 2), (3840, 53, 3840, 2), (1040, 7, 1040, 2),
                                          (854, 480, 896, 3), (1366, 49, 1376, 2), (2001, 19, 2016, 2),   # merged AND ragged
+                                         (2560, 1440, 2560, 2), (1024, 47, 1024, 2), (512, 100, 512, 3),  # multiples of 512
                                          (8640, 24, 8704, 2),      # rows wider than 8160: counters flush mid-row
                                          (7680, 4320, 7680, 1)])   # 8K: the largest picture NVDEC would hand over
 def test_sad_hist_matches_oracle(cuda, oracle_c, w, h, pitch, n):

@@ -439,17 +439,24 @@ int launch_score(const uint8_t *luma, int pitch, size_t frame_stride, int w, int
     {
         const int ng = (w + 15) >> 4, fullp = ng / 32, rem = ng - 32 * fullp;
         static const bool off = getenv("VT_SCORE_NO_MERGE") != nullptr;
-        if (aligned && !off && rem > 0 && fullp >= 1 && fullp + 1 <= 15) {
-            double best = fullp + 1.0;
+        if (aligned && !off && fullp >= 1 && fullp + 1 <= 15) {
+            double best = fullp + (rem ? 1.0 : 0.0);
             static const int k_force = getenv("VT_SCORE_K") ? atoi(getenv("VT_SCORE_K")) : 0;   // A/B measurements
             for (int k = 2; k <= 8; k++) {
-                if (k_force && k != k_force) continue;
+                if (rem == 0 || (k_force && k != k_force)) continue;
                 const int pk = (k * rem + 31) / 32;
                 if (pk > 3 || 16 * (k * fullp + pk) > 255) continue;
                 const double cost = (double)(k * fullp + pk) / k;
                 if (cost <= best + 1e-9 && (cost < best - 1e-9 || merge_k > 1)) {   // ties: the larger group (measured)
                     best = cost; merge_k = k; merge_p = pk;
                 }
+            }
+            if (rem == 0) {
+                // no leftover groups, but walking k rows as one run of passes still keeps three loads in flight across
+                // row ends: the largest k that fits, preferring runs that are whole blocks of three
+                for (int k = 2; k <= 8; k++)
+                    if (16 * k * fullp <= 255 && (merge_k == 1 || (k * fullp) % 3 == 0 || (merge_k * fullp) % 3 != 0)) merge_k = k;
+                merge_p = 0;
             }
             if (merge_k > 1) {
                 // a warp's last group may be cut by the picture's bottom edge; its rows then run unmerged
