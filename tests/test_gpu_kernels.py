@@ -156,7 +156,11 @@ def test_gather_frames(cuda):
 
 
 @pytest.mark.parametrize("sw,sh,pitch,dw,dh", [(1280, 720, 1280, 768, 768), (1920, 1080, 2048, 768, 768),
-                                               (640, 360, 640, 640, 360), (322, 182, 336, 160, 90)])
+                                               (640, 360, 640, 640, 360), (322, 182, 336, 160, 90),
+                                               (1920, 1080, 1920, 1280, 720), (854, 480, 896, 768, 768),
+                                               (640, 360, 640, 1280, 720),          # upscale: 4-tap banks
+                                               (1280, 720, 1283, 768, 768),         # pitch not a multiple of 4: general kernels
+                                               (3840, 2160, 3840, 768, 768)])       # 20 horizontal taps: general kernels
 def test_nv12_to_rgb24_scaled_bit_exact(cuda, oracle_c, sw, sh, pitch, dw, dh):
     """K1b / config 5: NV12 -> RGB24 with scaling equals the oracle (itself bit-exact against libswscale)."""
     rng = np.random.default_rng(sw + dw)

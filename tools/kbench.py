@@ -84,3 +84,12 @@ if "convert" in ks:
     out2 = torch.empty((F, sw * sh * 3 // 2), dtype=torch.uint8, device=dev)
     run("nv12_to_yuv420p", lambda: _lib.check(L.vt_nv12_to_yuv420p(c_void_p(surf.data_ptr()), pitch, rows * pitch, sw, sh,
         c_void_p(out2.data_ptr()), sw * sh * 3 // 2, F, sp)), sw * sh * 3)
+if "rgb" in ks:
+    # config 5's product: NV12 -> 768x768 RGB24 (scaled) and NV12 -> RGB24 at the source size
+    Fr = min(F, 64)
+    rp = ops.RgbPlan(sw, sh, 768, 768, ops.SWS_BICUBIC)
+    orgb = torch.empty((Fr, 768, 768, 3), dtype=torch.uint8, device=dev)
+    F_save = F
+    F = Fr
+    run("nv12_to_rgb24_768", lambda: rp.scale_nv12(surf.view(-1), pitch, Fr, rows * pitch, out=orgb), sw * sh * 3 // 2 + 768 * 768 * 3)
+    F = F_save

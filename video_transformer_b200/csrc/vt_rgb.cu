@@ -12,10 +12,16 @@
 //       off(c,k) = ((clip_u8(c)*k) >> 16) - (k >> 9).
 // oracle/vt_oracle.c:vto_yuv_to_rgb24 is the CPU restatement, pinned bit-for-bit against libswscale 9.1.100.
 //
-// This is a low-volume path (one frame per second of video), so it is three simple kernels per chunk of frames:
-// horizontal taps into 15-bit intermediates (luma, U, V), then one kernel that runs the three vertical filters
-// and the matrix per pixel pair and writes 6 bytes.  HBM traffic is dominated by the intermediates.
+// This is a low-volume path (one frame per second of video): per chunk of frames, horizontal taps into 15-bit
+// intermediates (one launch for luma, one for U and V together), then one kernel that runs the three vertical filters
+// and the matrix per pixel pair and writes 6 bytes.  The fast kernels (word-aligned surfaces, taps <= 16) take the
+// horizontal taps two at a time through dp2a on funnel-shifted 32-bit words -- interleaved chroma gives U and V from
+// the same permuted word -- and unroll the vertical taps; 32-bit arithmetic throughout (every product fits).  The
+// first version (byte loads, 64-bit index math) executed 7.9 M warp-instructions per 768x768 picture; the general
+// kernels below are kept for surfaces that are not 4-byte aligned and for banks with more than 16 taps.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -29,6 +35,10 @@ struct vt_rgb_plan {
     int32_t *lhp, *lvp, *chp, *cvp;           // first source sample of every output sample
     int chunk;                                // frames per launch group
     int16_t *my, *mu, *mv;                    // intermediates for `chunk` frames
+    // fast kernels: coefficient PAIRS per output sample, padded to hpl / hpc pairs; vertical banks padded to vtl / vtc
+    int hpl, hpc, vtl, vtc;                   // 0 = that bank is outside what the fast kernels take
+    uint32_t *lhc2, *chc2;                    // dw x hpl, cdw x hpc
+    int16_t *lvc2, *cvc2;                     // dh x vtl, dh x vtc
 };
 
 namespace vt {
@@ -47,6 +57,95 @@ rgb_hscale_kernel(const uint8_t *__restrict__ src, int pitch, size_t src_fs, int
     for (int j = 0; j < taps; j++) v += (int)s[(size_t)j * step] * (int)c[j];
     v >>= 7;
     mid[(size_t)blockIdx.z * mid_fs + (size_t)r * dw + x] = (int16_t)min(v, 32767);
+}
+
+__device__ __forceinline__ int rgb_dp2a_lo(uint32_t coef_pair, uint32_t pix, int acc) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(coef_pair), "r"(pix), "r"(acc));
+    return d;
+}
+__device__ __forceinline__ int rgb_dp2a_hi(uint32_t coef_pair, uint32_t pix, int acc) {
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(coef_pair), "r"(pix), "r"(acc));
+    return d;
+}
+
+// HP coefficient pairs of one output sample, fetched with the widest aligned loads (rows of the table are HP words)
+template <int HP>
+__device__ __forceinline__ void rgb_load_pairs(const uint32_t *__restrict__ t, uint32_t (&c)[HP]) {
+    if constexpr (HP % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < HP / 4; i++) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(t) + i);
+            c[4 * i] = q.x; c[4 * i + 1] = q.y; c[4 * i + 2] = q.z; c[4 * i + 3] = q.w;
+        }
+    } else if constexpr (HP % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < HP / 2; i++) {
+            const uint2 q = __ldg(reinterpret_cast<const uint2 *>(t) + i);
+            c[2 * i] = q.x; c[2 * i + 1] = q.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < HP; i++) c[i] = __ldg(t + i);
+    }
+}
+
+// Horizontal taps, luma: one thread per output sample, HP coefficient pairs.  The taps' bytes are fetched as aligned
+// 32-bit words (clamped to the row's last word: bytes past the taps carry zero coefficients) and funnel-shifted into
+// place; each dp2a multiplies two pixels by two 14-bit coefficients.
+template <int HP>
+__global__ void __launch_bounds__(256)
+rgb_hscale_luma_fast(const uint8_t *__restrict__ src, int pitch, size_t src_fs, int16_t *__restrict__ mid, size_t mid_fs,
+                     int dw, const uint32_t *__restrict__ coef2, const int32_t *__restrict__ pos) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= dw) return;
+    constexpr int NAW = (HP + 1) / 2, NW = NAW + 1;
+    const uint32_t *row = reinterpret_cast<const uint32_t *>(src + (size_t)blockIdx.z * src_fs + (size_t)blockIdx.y * pitch);
+    const int a = __ldg(pos + x);
+    const int w0 = a >> 2, wl = (pitch >> 2) - 1;
+    const uint32_t sh = (uint32_t)(a & 3) * 8u;
+    uint32_t w[NW], c[HP];
+#pragma unroll
+    for (int i = 0; i < NW; i++) w[i] = __ldg(row + min(w0 + i, wl));
+    rgb_load_pairs<HP>(coef2 + (size_t)x * HP, c);
+    int v = 0;
+#pragma unroll
+    for (int i = 0; i < HP; i++) {
+        const uint32_t al = __funnelshift_r(w[i >> 1], w[(i >> 1) + 1], sh);
+        v = (i & 1) ? rgb_dp2a_hi(c[i], al, v) : rgb_dp2a_lo(c[i], al, v);
+    }
+    mid[(size_t)blockIdx.z * mid_fs + (size_t)blockIdx.y * dw + x] = (int16_t)min(v >> 7, 32767);
+}
+
+// Horizontal taps, NV12 chroma: one thread per output sample produces U and V.  Sample pair (t, t+1) is one aligned
+// word U_t V_t U_t+1 V_t+1 after the funnel shift; a byte permute makes it (U_t, U_t+1, V_t, V_t+1), so dp2a.lo is
+// the U taps and dp2a.hi the V taps with the same coefficient pair.
+template <int HP>
+__global__ void __launch_bounds__(256)
+rgb_hscale_chroma_fast(const uint8_t *__restrict__ src, int pitch, size_t src_fs, int16_t *__restrict__ mu,
+                       int16_t *__restrict__ mv, size_t mid_fs, int cdw, const uint32_t *__restrict__ coef2,
+                       const int32_t *__restrict__ pos) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= cdw) return;
+    const uint32_t *row = reinterpret_cast<const uint32_t *>(src + (size_t)blockIdx.z * src_fs + (size_t)blockIdx.y * pitch);
+    const int a = 2 * __ldg(pos + x);                  // byte offset of the first U sample
+    const int w0 = a >> 2, wl = (pitch >> 2) - 1;
+    const uint32_t sh = (uint32_t)(a & 3) * 8u;        // 0 or 16
+    uint32_t w[HP + 1], c[HP];
+#pragma unroll
+    for (int i = 0; i < HP + 1; i++) w[i] = __ldg(row + min(w0 + i, wl));
+    rgb_load_pairs<HP>(coef2 + (size_t)x * HP, c);
+    int u = 0, v = 0;
+#pragma unroll
+    for (int i = 0; i < HP; i++) {
+        const uint32_t pw = __byte_perm(__funnelshift_r(w[i], w[i + 1], sh), 0u, 0x3120);
+        u = rgb_dp2a_lo(c[i], pw, u);
+        v = rgb_dp2a_hi(c[i], pw, v);
+    }
+    const size_t o = (size_t)blockIdx.z * mid_fs + (size_t)blockIdx.y * cdw + x;
+    mu[o] = (int16_t)min(u >> 7, 32767);
+    mv[o] = (int16_t)min(v >> 7, 32767);
 }
 
 struct RgbConst {
@@ -98,6 +197,61 @@ rgb_vscale_kernel(const int16_t *__restrict__ my, const int16_t *__restrict__ mu
     }
 }
 
+
+// Vertical taps + matrix, fast form: LVT / CVT taps unrolled (banks padded with zero coefficients; padded taps read a
+// clamped row), luma intermediates of a pixel pair fetched as one 32-bit word, 32-bit arithmetic (the largest product,
+// 255 * cbu, is below 2^25), three 16-bit stores per pair.
+__device__ __forceinline__ int rgb_t32(int idx, int cy) { return max(0, min(255, (idx * cy - (400 << 16) + 0x8000) >> 16)); }
+
+template <int LVT, int CVT>
+__global__ void __launch_bounds__(256)
+rgb_vscale_fast(const int16_t *__restrict__ my, const int16_t *__restrict__ mu, const int16_t *__restrict__ mv,
+                size_t my_fs, size_t mc_fs, int dw, int cdw, int sh, int csh, const int16_t *__restrict__ lvc2,
+                const int32_t *__restrict__ lvp, const int16_t *__restrict__ cvc2, const int32_t *__restrict__ cvp,
+                uint8_t *__restrict__ dst, size_t dst_fs, RgbConst k) {
+    const int xp = blockIdx.x * blockDim.x + threadIdx.x;    // pair index; dw is even, so every pair has two pixels
+    const int y = blockIdx.y;
+    if (xp >= cdw) return;
+    const uint32_t *yy = reinterpret_cast<const uint32_t *>(my + (size_t)blockIdx.z * my_fs) + xp;
+    const int16_t *uu = mu + (size_t)blockIdx.z * mc_fs + xp;
+    const int16_t *vv = mv + (size_t)blockIdx.z * mc_fs + xp;
+    const int lr = __ldg(lvp + y), cr = __ldg(cvp + y), hw = dw >> 1;
+    uint32_t wy[LVT];
+    int su[CVT], sv[CVT];
+#pragma unroll
+    for (int j = 0; j < LVT; j++) wy[j] = __ldg(yy + min(lr + j, sh - 1) * hw);
+#pragma unroll
+    for (int j = 0; j < CVT; j++) {
+        const int o = min(cr + j, csh - 1) * cdw;
+        su[j] = __ldg(uu + o);
+        sv[j] = __ldg(vv + o);
+    }
+    int y0 = 1 << 18, y1 = 1 << 18, u = 1 << 18, v = 1 << 18;
+#pragma unroll
+    for (int j = 0; j < LVT; j++) {
+        const int c = __ldg(lvc2 + y * LVT + j);
+        y0 += ((int)(wy[j] << 16) >> 16) * c;
+        y1 += ((int)wy[j] >> 16) * c;
+    }
+#pragma unroll
+    for (int j = 0; j < CVT; j++) {
+        const int c = __ldg(cvc2 + y * CVT + j);
+        u += su[j] * c;
+        v += sv[j] * c;
+    }
+    y0 >>= 19; y1 >>= 19; u >>= 19; v >>= 19;
+    const int uc = max(0, min(255, u)), vc = max(0, min(255, v));
+    const int r_off = ((vc * k.crv) >> 16) - (k.crv >> 9);
+    const int g_off = ((uc * k.cgu) >> 16) - (k.cgu >> 9) + ((vc * k.cgv) >> 16) - (k.cgv >> 9);
+    const int b_off = ((uc * k.cbu) >> 16) - (k.cbu >> 9);
+    const int r0 = rgb_t32(y0 + 326 + r_off, k.cy), g0 = rgb_t32(y0 + 326 + g_off, k.cy), b0 = rgb_t32(y0 + 326 + b_off, k.cy);
+    const int r1 = rgb_t32(y1 + 326 + r_off, k.cy), g1 = rgb_t32(y1 + 326 + g_off, k.cy), b1 = rgb_t32(y1 + 326 + b_off, k.cy);
+    unsigned short *d = reinterpret_cast<unsigned short *>(dst + (size_t)blockIdx.z * dst_fs + ((size_t)y * dw + 2 * xp) * 3);
+    d[0] = (unsigned short)(r0 | (g0 << 8));
+    d[1] = (unsigned short)(b0 | (r1 << 8));
+    d[2] = (unsigned short)(g1 | (b1 << 8));
+}
+
 }  // namespace vt
 
 namespace {
@@ -108,7 +262,8 @@ int upload(const void *h, size_t n, void **d) {
     return VT_OK;
 }
 
-int bank(int src, int dst, int flags, int one, int16_t **coef_dev, int32_t **pos_dev, int *taps) {
+int bank(int src, int dst, int flags, int one, int16_t **coef_dev, int32_t **pos_dev, int *taps,
+         std::vector<int16_t> *coef_host) {
     int cap = vt_sws_max_taps(src, dst, flags);
     if (cap < 0) return cap;
     cap = std::max(cap, 4);
@@ -116,6 +271,8 @@ int bank(int src, int dst, int flags, int one, int16_t **coef_dev, int32_t **pos
     std::vector<int32_t> pos((size_t)dst, 0);
     int rc = vt_sws_make_filter(src, dst, flags, one, coef.data(), pos.data(), taps);
     if (rc) return rc;
+    coef.resize((size_t)dst * *taps);
+    *coef_host = coef;
     rc = upload(coef.data(), (size_t)dst * *taps * sizeof(int16_t), (void **)coef_dev);
     if (rc == VT_OK) rc = upload(pos.data(), (size_t)dst * sizeof(int32_t), (void **)pos_dev);
     return rc;
@@ -140,10 +297,42 @@ extern "C" int vt_rgb_plan_create(int sw, int sh, int dw, int dh, int flags, vt_
     *p = vt_rgb_plan{};
     p->sw = sw; p->sh = sh; p->dw = dw; p->dh = dh; p->flags = flags;
     p->csw = (sw + 1) / 2; p->csh = (sh + 1) / 2; p->cdw = (dw + 1) / 2;
-    int rc = bank(sw, dw, flags, 1 << 14, &p->lhc, &p->lhp, &p->lht);
-    if (rc == VT_OK) rc = bank(sh, dh, flags, 1 << 12, &p->lvc, &p->lvp, &p->lvt);
-    if (rc == VT_OK) rc = bank(p->csw, p->cdw, flags, 1 << 14, &p->chc, &p->chp, &p->cht);
-    if (rc == VT_OK) rc = bank(p->csh, dh, flags, 1 << 12, &p->cvc, &p->cvp, &p->cvt);
+    std::vector<int16_t> hl, vl, hc, vc;
+    int rc = bank(sw, dw, flags, 1 << 14, &p->lhc, &p->lhp, &p->lht, &hl);
+    if (rc == VT_OK) rc = bank(sh, dh, flags, 1 << 12, &p->lvc, &p->lvp, &p->lvt, &vl);
+    if (rc == VT_OK) rc = bank(p->csw, p->cdw, flags, 1 << 14, &p->chc, &p->chp, &p->cht, &hc);
+    if (rc == VT_OK) rc = bank(p->csh, dh, flags, 1 << 12, &p->cvc, &p->cvp, &p->cvt, &vc);
+    // tables of the fast kernels: horizontal coefficient pairs, vertical banks padded to an instantiated tap count
+    auto pad_hp = [](int taps) { const int hp = (taps + 1) / 2; return hp <= 2 ? 2 : hp <= 3 ? 3 : hp <= 4 ? 4 : hp <= 6 ? 6 : hp <= 8 ? 8 : 0; };
+    auto pad_vt = [](int taps) { return taps <= 4 ? 4 : taps <= 6 ? 6 : taps <= 8 ? 8 : 0; };
+    auto pairs = [](const std::vector<int16_t> &c, int n, int taps, int hp) {
+        std::vector<uint32_t> t((size_t)n * hp, 0);
+        for (int x = 0; x < n; x++)
+            for (int j = 0; j < taps; j++) {
+                const uint32_t v = (uint16_t)c[(size_t)x * taps + j];
+                t[(size_t)x * hp + j / 2] |= (j & 1) ? (v << 16) : v;
+            }
+        return t;
+    };
+    auto padded = [](const std::vector<int16_t> &c, int n, int taps, int vt) {
+        std::vector<int16_t> t((size_t)n * vt, 0);
+        for (int y = 0; y < n; y++)
+            for (int j = 0; j < taps; j++) t[(size_t)y * vt + j] = c[(size_t)y * taps + j];
+        return t;
+    };
+    if (rc == VT_OK) {
+        p->hpl = pad_hp(p->lht); p->hpc = pad_hp(p->cht); p->vtl = pad_vt(p->lvt); p->vtc = pad_vt(p->cvt);
+        if (p->hpl && p->hpc && p->vtl && p->vtc) {
+            const auto a = pairs(hl, dw, p->lht, p->hpl), b = pairs(hc, p->cdw, p->cht, p->hpc);
+            const auto c = padded(vl, dh, p->lvt, p->vtl), d = padded(vc, dh, p->cvt, p->vtc);
+            rc = upload(a.data(), a.size() * 4, (void **)&p->lhc2);
+            if (rc == VT_OK) rc = upload(b.data(), b.size() * 4, (void **)&p->chc2);
+            if (rc == VT_OK) rc = upload(c.data(), c.size() * 2, (void **)&p->lvc2);
+            if (rc == VT_OK) rc = upload(d.data(), d.size() * 2, (void **)&p->cvc2);
+        } else {
+            p->hpl = p->hpc = p->vtl = p->vtc = 0;
+        }
+    }
     // intermediates: as many frames per launch group as fit 256 MB
     const size_t per_frame = ((size_t)dw * sh + 2 * (size_t)p->cdw * p->csh) * sizeof(int16_t);
     p->chunk = (int)std::max<size_t>(1, std::min<size_t>(32, ((size_t)256 << 20) / per_frame));
@@ -164,6 +353,7 @@ extern "C" void vt_rgb_plan_destroy(vt_rgb_plan *p) {
     cudaFree(p->lhc); cudaFree(p->lvc); cudaFree(p->chc); cudaFree(p->cvc);
     cudaFree(p->lhp); cudaFree(p->lvp); cudaFree(p->chp); cudaFree(p->cvp);
     cudaFree(p->my); cudaFree(p->mu); cudaFree(p->mv);
+    cudaFree(p->lhc2); cudaFree(p->chc2); cudaFree(p->lvc2); cudaFree(p->cvc2);
     delete p;
 }
 
@@ -181,11 +371,33 @@ extern "C" int vt_scale_nv12_to_rgb24(const vt_rgb_plan *p, const uint8_t *src, 
     k.cgu = (int)cdiv(-25675LL * 65536 + 0x8000, k.cy);
     k.cgv = (int)cdiv(-53279LL * 65536 + 0x8000, k.cy);
     const size_t my_fs = (size_t)p->dw * p->sh, mc_fs = (size_t)p->cdw * p->csh;
+    // VT_RGB_KERNEL=generic selects the general kernels (A/B measurements and their own parity test)
+    static const char *force = getenv("VT_RGB_KERNEL");
+    const bool fast = p->hpl && !(force && !strcmp(force, "generic")) && (uintptr_t)src % 4 == 0 && pitch % 4 == 0 &&
+                      src_fs % 4 == 0 && (uintptr_t)dst % 2 == 0 && dst_fs % 2 == 0;
     for (int f0 = 0; f0 < n_frames; f0 += p->chunk) {
         const int nf = std::min(p->chunk, n_frames - f0);
         const uint8_t *s = src + (size_t)f0 * src_fs;
         const uint8_t *uv = s + (size_t)pitch * p->sh;
         dim3 b(256);
+        uint8_t *d = dst + (size_t)f0 * dst_fs;
+        if (fast) {
+            const dim3 gl((p->dw + 255) / 256, p->sh, nf), gc((p->cdw + 255) / 256, p->csh, nf), gv((p->cdw + 255) / 256, p->dh, nf);
+#define VT_HL(H) case H: vt::rgb_hscale_luma_fast<H><<<gl, b, 0, st>>>(s, pitch, src_fs, p->my, my_fs, p->dw, p->lhc2, p->lhp); break
+            switch (p->hpl) { VT_HL(2); VT_HL(3); VT_HL(4); VT_HL(6); VT_HL(8); }
+#undef VT_HL
+            VT_LAUNCHED("rgb_hscale_luma_fast");
+#define VT_HC(H) case H: vt::rgb_hscale_chroma_fast<H><<<gc, b, 0, st>>>(uv, pitch, src_fs, p->mu, p->mv, mc_fs, p->cdw, p->chc2, p->chp); break
+            switch (p->hpc) { VT_HC(2); VT_HC(3); VT_HC(4); VT_HC(6); VT_HC(8); }
+#undef VT_HC
+            VT_LAUNCHED("rgb_hscale_chroma_fast");
+#define VT_V(L, C) if (p->vtl == L && p->vtc == C) vt::rgb_vscale_fast<L, C><<<gv, b, 0, st>>>(p->my, p->mu, p->mv, my_fs, mc_fs, \
+        p->dw, p->cdw, p->sh, p->csh, p->lvc2, p->lvp, p->cvc2, p->cvp, d, dst_fs, k)
+            VT_V(4, 4); VT_V(4, 6); VT_V(4, 8); VT_V(6, 4); VT_V(6, 6); VT_V(6, 8); VT_V(8, 4); VT_V(8, 6); VT_V(8, 8);
+#undef VT_V
+            VT_LAUNCHED("rgb_vscale_fast");
+            continue;
+        }
         vt::rgb_hscale_kernel<<<dim3((p->dw + 255) / 256, p->sh, nf), b, 0, st>>>(s, pitch, src_fs, p->sh, 1, 0, p->my, my_fs,
                                                                              p->dw, p->lhc, p->lhp, p->lht);
         VT_LAUNCHED("rgb_hscale_kernel");
@@ -197,7 +409,7 @@ extern "C" int vt_scale_nv12_to_rgb24(const vt_rgb_plan *p, const uint8_t *src, 
         VT_LAUNCHED("rgb_hscale_kernel");
         vt::rgb_vscale_kernel<<<dim3((p->cdw + 255) / 256, p->dh, nf), b, 0, st>>>(
             p->my, p->mu, p->mv, my_fs, mc_fs, p->dw, p->cdw, p->dh, p->lvc, p->lvp, p->lvt, p->cvc, p->cvp, p->cvt,
-            dst + (size_t)f0 * dst_fs, dst_fs, k);
+            d, dst_fs, k);
         VT_LAUNCHED("rgb_vscale_kernel");
     }
     return VT_OK;
