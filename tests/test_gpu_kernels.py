@@ -92,6 +92,15 @@ def test_scale_plane_generic_bit_exact(cuda, oracle_c, flags, sw, sh, dw, dh):
     (3840, 2160, 3840, 1920, 1080, ops.SWS_BICUBIC),    # 1080 output rows: the vertical table spans two launches
     (1920, 1080, 1920, 1280, 720, ops.SWS_BICUBIC | 0),
     (640, 480, 640, 320, 240, ops.SWS_AREA),
+    # exact 3:2 / 2:1 / 3:1 with strips that do not tile the width (adjacent-column layout, last strip slid left)
+    (1440, 1080, 1536, 960, 720, ops.SWS_BICUBIC),
+    (960, 540, 1024, 640, 360, ops.SWS_BICUBIC),
+    (1620, 1080, 1664, 1080, 720, ops.SWS_BICUBIC),
+    (1920, 1080, 1920, 960, 540, ops.SWS_BICUBIC),
+    (1920, 1080, 2048, 640, 360, ops.SWS_BICUBIC),
+    (2880, 1620, 3072, 960, 540, ops.SWS_BICUBIC),
+    (810, 540, 896, 540, 360, ops.SWS_BICUBIC),         # 3:2 but the width is not a multiple of 8: pair layout
+    (960, 540, 1024, 640, 360, ops.SWS_BILINEAR),
 ])
 def test_scale_nv12_to_yuv420p_bit_exact(cuda, oracle_c, sw, sh, pitch, dw, dh, flags):
     rng = np.random.default_rng(sw * 3 + dw)
