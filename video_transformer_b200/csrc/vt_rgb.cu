@@ -94,28 +94,42 @@ __device__ __forceinline__ void rgb_load_pairs(const uint32_t *__restrict__ t, u
 // Horizontal taps, luma: one thread per output sample, HP coefficient pairs.  The taps' bytes are fetched as aligned
 // 32-bit words (clamped to the row's last word: bytes past the taps carry zero coefficients) and funnel-shifted into
 // place; each dp2a multiplies two pixels by two 14-bit coefficients.
+constexpr int RGB_RPT = 8;     // source rows per thread of the horizontal kernels: position, shift and coefficients are
+                               // fetched once and the per-row work is loads + dp2a (the one-row form spent 40 of its 62
+                               // instructions on indices)
 template <int HP>
 __global__ void __launch_bounds__(256)
-rgb_hscale_luma_fast(const uint8_t *__restrict__ src, int pitch, size_t src_fs, int16_t *__restrict__ mid, size_t mid_fs,
-                     int dw, const uint32_t *__restrict__ coef2, const int32_t *__restrict__ pos) {
+rgb_hscale_luma_fast(const uint8_t *__restrict__ src, int pitch, size_t src_fs, int rows, int16_t *__restrict__ mid,
+                     size_t mid_fs, int dw, const uint32_t *__restrict__ coef2, const int32_t *__restrict__ pos) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= dw) return;
     constexpr int NAW = (HP + 1) / 2, NW = NAW + 1;
-    const uint32_t *row = reinterpret_cast<const uint32_t *>(src + (size_t)blockIdx.z * src_fs + (size_t)blockIdx.y * pitch);
+    const int r0 = blockIdx.y * RGB_RPT, nr = min(RGB_RPT, rows - r0);
     const int a = __ldg(pos + x);
-    const int w0 = a >> 2, wl = (pitch >> 2) - 1;
+    const int w0 = a >> 2, wl = (pitch >> 2) - 1, pw = pitch >> 2;
     const uint32_t sh = (uint32_t)(a & 3) * 8u;
-    uint32_t w[NW], c[HP];
+    int wi[NW];
 #pragma unroll
-    for (int i = 0; i < NW; i++) w[i] = __ldg(row + min(w0 + i, wl));
+    for (int i = 0; i < NW; i++) wi[i] = min(w0 + i, wl);
+    uint32_t c[HP];
     rgb_load_pairs<HP>(coef2 + (size_t)x * HP, c);
-    int v = 0;
+    const uint32_t *row = reinterpret_cast<const uint32_t *>(src + (size_t)blockIdx.z * src_fs + (size_t)r0 * pitch);
+    int16_t *mo = mid + (size_t)blockIdx.z * mid_fs + (size_t)r0 * dw + x;
+#pragma unroll 4
+    for (int r = 0; r < nr; r++) {
+        uint32_t w[NW];
 #pragma unroll
-    for (int i = 0; i < HP; i++) {
-        const uint32_t al = __funnelshift_r(w[i >> 1], w[(i >> 1) + 1], sh);
-        v = (i & 1) ? rgb_dp2a_hi(c[i], al, v) : rgb_dp2a_lo(c[i], al, v);
+        for (int i = 0; i < NW; i++) w[i] = __ldg(row + wi[i]);
+        int v = 0;
+#pragma unroll
+        for (int i = 0; i < HP; i++) {
+            const uint32_t al = __funnelshift_r(w[i >> 1], w[(i >> 1) + 1], sh);
+            v = (i & 1) ? rgb_dp2a_hi(c[i], al, v) : rgb_dp2a_lo(c[i], al, v);
+        }
+        *mo = (int16_t)min(v >> 7, 32767);
+        row += pw;
+        mo += dw;
     }
-    mid[(size_t)blockIdx.z * mid_fs + (size_t)blockIdx.y * dw + x] = (int16_t)min(v >> 7, 32767);
 }
 
 // Horizontal taps, NV12 chroma: one thread per output sample produces U and V.  Sample pair (t, t+1) is one aligned
@@ -123,29 +137,39 @@ rgb_hscale_luma_fast(const uint8_t *__restrict__ src, int pitch, size_t src_fs, 
 // the U taps and dp2a.hi the V taps with the same coefficient pair.
 template <int HP>
 __global__ void __launch_bounds__(256)
-rgb_hscale_chroma_fast(const uint8_t *__restrict__ src, int pitch, size_t src_fs, int16_t *__restrict__ mu,
+rgb_hscale_chroma_fast(const uint8_t *__restrict__ src, int pitch, size_t src_fs, int rows, int16_t *__restrict__ mu,
                        int16_t *__restrict__ mv, size_t mid_fs, int cdw, const uint32_t *__restrict__ coef2,
                        const int32_t *__restrict__ pos) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= cdw) return;
-    const uint32_t *row = reinterpret_cast<const uint32_t *>(src + (size_t)blockIdx.z * src_fs + (size_t)blockIdx.y * pitch);
+    const int r0 = blockIdx.y * RGB_RPT, nr = min(RGB_RPT, rows - r0);
     const int a = 2 * __ldg(pos + x);                  // byte offset of the first U sample
-    const int w0 = a >> 2, wl = (pitch >> 2) - 1;
+    const int w0 = a >> 2, wl = (pitch >> 2) - 1, pw = pitch >> 2;
     const uint32_t sh = (uint32_t)(a & 3) * 8u;        // 0 or 16
-    uint32_t w[HP + 1], c[HP];
+    int wi[HP + 1];
 #pragma unroll
-    for (int i = 0; i < HP + 1; i++) w[i] = __ldg(row + min(w0 + i, wl));
+    for (int i = 0; i < HP + 1; i++) wi[i] = min(w0 + i, wl);
+    uint32_t c[HP];
     rgb_load_pairs<HP>(coef2 + (size_t)x * HP, c);
-    int u = 0, v = 0;
+    const uint32_t *row = reinterpret_cast<const uint32_t *>(src + (size_t)blockIdx.z * src_fs + (size_t)r0 * pitch);
+    size_t o = (size_t)blockIdx.z * mid_fs + (size_t)r0 * cdw + x;
+#pragma unroll 4
+    for (int r = 0; r < nr; r++) {
+        uint32_t w[HP + 1];
 #pragma unroll
-    for (int i = 0; i < HP; i++) {
-        const uint32_t pw = __byte_perm(__funnelshift_r(w[i], w[i + 1], sh), 0u, 0x3120);
-        u = rgb_dp2a_lo(c[i], pw, u);
-        v = rgb_dp2a_hi(c[i], pw, v);
+        for (int i = 0; i < HP + 1; i++) w[i] = __ldg(row + wi[i]);
+        int u = 0, v = 0;
+#pragma unroll
+        for (int i = 0; i < HP; i++) {
+            const uint32_t pw4 = __byte_perm(__funnelshift_r(w[i], w[i + 1], sh), 0u, 0x3120);
+            u = rgb_dp2a_lo(c[i], pw4, u);
+            v = rgb_dp2a_hi(c[i], pw4, v);
+        }
+        mu[o] = (int16_t)min(u >> 7, 32767);
+        mv[o] = (int16_t)min(v >> 7, 32767);
+        row += pw;
+        o += cdw;
     }
-    const size_t o = (size_t)blockIdx.z * mid_fs + (size_t)blockIdx.y * cdw + x;
-    mu[o] = (int16_t)min(u >> 7, 32767);
-    mv[o] = (int16_t)min(v >> 7, 32767);
 }
 
 struct RgbConst {
@@ -250,6 +274,88 @@ rgb_vscale_fast(const int16_t *__restrict__ my, const int16_t *__restrict__ mu, 
     d[0] = (unsigned short)(r0 | (g0 << 8));
     d[1] = (unsigned short)(b0 | (r1 << 8));
     d[2] = (unsigned short)(g1 | (b1 << 8));
+}
+
+// The same for EIGHT pixels per thread (output width a multiple of 8): one 128-bit load per luma tap row, one 64-bit
+// load per chroma tap row and channel, and the matrix's clamp comes free with the byte pack (cvt.pack.sat, two
+// values per instruction; the affine part of T() is folded per channel and pixel pair:
+// (Y + 326 + off) * cy + K = Y * cy + A_channel).  24 output bytes leave as three 64-bit stores.
+__device__ __forceinline__ uint32_t rgb_pack4(int b3, int b2, int b1, int b0) {   // sat_u8 of each, b0 in the low byte
+    uint32_t t, d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(b3), "r"(b2), "r"(0u));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(b1), "r"(b0), "r"(t));
+    return d;
+}
+
+template <int LVT, int CVT>
+__global__ void __launch_bounds__(128)
+rgb_vscale_fast8(const int16_t *__restrict__ my, const int16_t *__restrict__ mu, const int16_t *__restrict__ mv,
+                 size_t my_fs, size_t mc_fs, int dw, int cdw, int sh, int csh, const int16_t *__restrict__ lvc2,
+                 const int32_t *__restrict__ lvp, const int16_t *__restrict__ cvc2, const int32_t *__restrict__ cvp,
+                 uint8_t *__restrict__ dst, size_t dst_fs, RgbConst k) {
+    const int xq = blockIdx.x * blockDim.x + threadIdx.x;    // group of 8 pixels = 4 chroma samples
+    const int y = blockIdx.y;
+    const int nq = dw >> 3;
+    if (xq >= nq) return;
+    const uint4 *yy = reinterpret_cast<const uint4 *>(my + (size_t)blockIdx.z * my_fs) + xq;
+    const uint2 *uu = reinterpret_cast<const uint2 *>(mu + (size_t)blockIdx.z * mc_fs) + xq;
+    const uint2 *vv = reinterpret_cast<const uint2 *>(mv + (size_t)blockIdx.z * mc_fs) + xq;
+    const int lr = __ldg(lvp + y), cr = __ldg(cvp + y);
+    uint4 wy[LVT];
+    uint2 wu[CVT], wv[CVT];
+#pragma unroll
+    for (int j = 0; j < LVT; j++) wy[j] = __ldg(yy + min(lr + j, sh - 1) * nq);
+#pragma unroll
+    for (int j = 0; j < CVT; j++) {
+        const int o = min(cr + j, csh - 1) * nq;
+        wu[j] = __ldg(uu + o);
+        wv[j] = __ldg(vv + o);
+    }
+    int ya[8], ua[4], va[4];
+#pragma unroll
+    for (int i = 0; i < 8; i++) ya[i] = 1 << 18;
+#pragma unroll
+    for (int i = 0; i < 4; i++) ua[i] = va[i] = 1 << 18;
+#pragma unroll
+    for (int j = 0; j < LVT; j++) {
+        const int c = __ldg(lvc2 + y * LVT + j);
+        const uint32_t w[4] = {wy[j].x, wy[j].y, wy[j].z, wy[j].w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            ya[2 * i] += ((int)(w[i] << 16) >> 16) * c;
+            ya[2 * i + 1] += ((int)w[i] >> 16) * c;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < CVT; j++) {
+        const int c = __ldg(cvc2 + y * CVT + j);
+        ua[0] += ((int)(wu[j].x << 16) >> 16) * c; ua[1] += ((int)wu[j].x >> 16) * c;
+        ua[2] += ((int)(wu[j].y << 16) >> 16) * c; ua[3] += ((int)wu[j].y >> 16) * c;
+        va[0] += ((int)(wv[j].x << 16) >> 16) * c; va[1] += ((int)wv[j].x >> 16) * c;
+        va[2] += ((int)(wv[j].y << 16) >> 16) * c; va[3] += ((int)wv[j].y >> 16) * c;
+    }
+    const int base = 326 * k.cy - (400 << 16) + 0x8000;
+    int px[24];                                              // (T's argument) >> 16 per output byte, before the clamp
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int uc = max(0, min(255, ua[q] >> 19)), vc = max(0, min(255, va[q] >> 19));
+        const int r_off = ((vc * k.crv) >> 16) - (k.crv >> 9);
+        const int g_off = ((uc * k.cgu) >> 16) - (k.cgu >> 9) + ((vc * k.cgv) >> 16) - (k.cgv >> 9);
+        const int b_off = ((uc * k.cbu) >> 16) - (k.cbu >> 9);
+        const int ar = r_off * k.cy + base, ag = g_off * k.cy + base, ab = b_off * k.cy + base;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int yv = ya[2 * q + e] >> 19;
+            px[6 * q + 3 * e] = (yv * k.cy + ar) >> 16;
+            px[6 * q + 3 * e + 1] = (yv * k.cy + ag) >> 16;
+            px[6 * q + 3 * e + 2] = (yv * k.cy + ab) >> 16;
+        }
+    }
+    uint2 *d = reinterpret_cast<uint2 *>(dst + (size_t)blockIdx.z * dst_fs + ((size_t)y * dw + 8 * (size_t)xq) * 3);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        d[i] = make_uint2(rgb_pack4(px[8 * i + 3], px[8 * i + 2], px[8 * i + 1], px[8 * i]),
+                          rgb_pack4(px[8 * i + 7], px[8 * i + 6], px[8 * i + 5], px[8 * i + 4]));
 }
 
 }  // namespace vt
@@ -382,18 +488,25 @@ extern "C" int vt_scale_nv12_to_rgb24(const vt_rgb_plan *p, const uint8_t *src, 
         dim3 b(256);
         uint8_t *d = dst + (size_t)f0 * dst_fs;
         if (fast) {
-            const dim3 gl((p->dw + 255) / 256, p->sh, nf), gc((p->cdw + 255) / 256, p->csh, nf), gv((p->cdw + 255) / 256, p->dh, nf);
-#define VT_HL(H) case H: vt::rgb_hscale_luma_fast<H><<<gl, b, 0, st>>>(s, pitch, src_fs, p->my, my_fs, p->dw, p->lhc2, p->lhp); break
+            const dim3 gl((p->dw + 255) / 256, (p->sh + vt::RGB_RPT - 1) / vt::RGB_RPT, nf),
+                gc((p->cdw + 255) / 256, (p->csh + vt::RGB_RPT - 1) / vt::RGB_RPT, nf), gv((p->cdw + 255) / 256, p->dh, nf);
+#define VT_HL(H) case H: vt::rgb_hscale_luma_fast<H><<<gl, b, 0, st>>>(s, pitch, src_fs, p->sh, p->my, my_fs, p->dw, p->lhc2, p->lhp); break
             switch (p->hpl) { VT_HL(2); VT_HL(3); VT_HL(4); VT_HL(6); VT_HL(8); }
 #undef VT_HL
             VT_LAUNCHED("rgb_hscale_luma_fast");
-#define VT_HC(H) case H: vt::rgb_hscale_chroma_fast<H><<<gc, b, 0, st>>>(uv, pitch, src_fs, p->mu, p->mv, mc_fs, p->cdw, p->chc2, p->chp); break
+#define VT_HC(H) case H: vt::rgb_hscale_chroma_fast<H><<<gc, b, 0, st>>>(uv, pitch, src_fs, p->csh, p->mu, p->mv, mc_fs, p->cdw, p->chc2, p->chp); break
             switch (p->hpc) { VT_HC(2); VT_HC(3); VT_HC(4); VT_HC(6); VT_HC(8); }
 #undef VT_HC
             VT_LAUNCHED("rgb_hscale_chroma_fast");
-#define VT_V(L, C) if (p->vtl == L && p->vtc == C) vt::rgb_vscale_fast<L, C><<<gv, b, 0, st>>>(p->my, p->mu, p->mv, my_fs, mc_fs, \
-        p->dw, p->cdw, p->sh, p->csh, p->lvc2, p->lvp, p->cvc2, p->cvp, d, dst_fs, k)
-            VT_V(4, 4); VT_V(4, 6); VT_V(4, 8); VT_V(6, 4); VT_V(6, 6); VT_V(6, 8); VT_V(8, 4); VT_V(8, 6); VT_V(8, 8);
+            // eight pixels per thread when the rows of the output and of the intermediates are 8-byte aligned
+            const bool wide = p->dw % 8 == 0 && (uintptr_t)d % 8 == 0 && dst_fs % 8 == 0;
+            const dim3 gv8((p->dw / 8 + 127) / 128, p->dh, nf);
+#define VT_V(L, C) if (p->vtl == L && p->vtc == C) { \
+        if (wide) vt::rgb_vscale_fast8<L, C><<<gv8, 128, 0, st>>>(p->my, p->mu, p->mv, my_fs, mc_fs, p->dw, p->cdw, p->sh, p->csh, \
+                                                                p->lvc2, p->lvp, p->cvc2, p->cvp, d, dst_fs, k); \
+        else vt::rgb_vscale_fast<L, C><<<gv, b, 0, st>>>(p->my, p->mu, p->mv, my_fs, mc_fs, p->dw, p->cdw, p->sh, p->csh, \
+                                                        p->lvc2, p->lvp, p->cvc2, p->cvp, d, dst_fs, k); }
+            VT_V(4, 4) VT_V(4, 6) VT_V(4, 8) VT_V(6, 4) VT_V(6, 6) VT_V(6, 8) VT_V(8, 4) VT_V(8, 6) VT_V(8, 8)
 #undef VT_V
             VT_LAUNCHED("rgb_vscale_fast");
             continue;
