@@ -21,6 +21,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 #include <cstring>
@@ -33,6 +34,15 @@
 // 8 no stores
 #ifndef VT_ABLATE
 #define VT_ABLATE 0
+#endif
+// VT_PAIR_TIMES (measurement builds, tools/build_variant.sh times -DVT_PAIR_TIMES=1): with VT_PAIR_DEBUG_TIMES=file every
+// warp records its start and end time (tools/pair_times.py reads the file).  What it showed: the SM's schedulers favour
+// the oldest warp -- with equal static shares the five warps of a scheduler finish at 0.37, 0.51, 0.68, 0.84 and 0.96 of
+// the kernel's duration -- and that this costs nothing: handing the work out dynamically (ticketed, shrinking chunks;
+// all warps then end within 5 % of each other) made the kernel 10 % SLOWER, because every extra item pays a ring
+// warm-up while one or two warps per scheduler already keep the multiply pipe as busy as five do.
+#ifndef VT_PAIR_TIMES
+#define VT_PAIR_TIMES 0
 #endif
 
 namespace vt {
@@ -65,6 +75,7 @@ struct PairArgs {
     // static vertical schedule (kernels instantiated with MASK != 0): output rows [reg_lo, reg_hi) repeat one pattern
     // of window ends and coefficient sets every align_p source rows; segments start on rows = align_r0 (mod align_p)
     int reg_lo, reg_hi, align_p, align_r0;
+    unsigned long long *dbg_times;     // VT_PAIR_TIMES builds: per warp {start, end} globaltimer (null otherwise)
     int sc[24];                        // [phase][TV] front-padded coefficients of the pattern's output rows
 };
 
@@ -251,6 +262,13 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     if (gw >= warps_per_strip * a.n_strips) return;
     const int strip = gw % a.n_strips;
     const int total = a.n_frames * a.n_segs;
+#if VT_PAIR_TIMES
+    if (a.dbg_times && lane == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        a.dbg_times[2 * gw] = t;
+    }
+#endif
     // this lane's column pairs
     // per pair: tile address, byte shift, even column's HP coefficient pairs; odd column: HP-1 pairs on the aligned
     // halfwords 1..HP-1, one pair on the two leftover samples, and the byte selector that fetches those two samples
@@ -549,6 +567,13 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         }
     item_done:;
     }
+#if VT_PAIR_TIMES
+    if (a.dbg_times && lane == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        a.dbg_times[2 * gw + 1] = t;
+    }
+#endif
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
@@ -611,8 +636,21 @@ int launch_t(const vt_scale_plan::Pair &s, const CUtensorMap &tm, PairArgs a, in
         }
         a.seg_rows = best_rows;
         a.n_segs = (rows + a.seg_rows - 1) / a.seg_rows;
+        static const char *dbg_path = VT_PAIR_TIMES ? getenv("VT_PAIR_DEBUG_TIMES") : nullptr;   // per-warp start/end times
+        if (dbg_path && !a.dbg_times) cudaMalloc((void **)&a.dbg_times, sizeof(unsigned long long) * 2 * grid * 4);
         k<<<grid, 128, smem, st>>>(tm, a, vt_host);
         VT_LAUNCHED("scale_pair_kernel");
+        if (dbg_path) {
+            std::vector<unsigned long long> h((size_t)2 * grid * 4);
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h.data(), a.dbg_times, h.size() * 8, cudaMemcpyDeviceToHost);
+            if (FILE *f = fopen(dbg_path, UV ? "ab" : "wb")) {
+                fwrite(h.data(), 8, h.size(), f);
+                fclose(f);
+            }
+            cudaFree(a.dbg_times);
+            a.dbg_times = nullptr;
+        }
     }
     return VT_OK;
 }
@@ -895,6 +933,7 @@ int launch_pair(const vt_scale_plan *p, int c, const uint8_t *src, int pitch, si
     a.n_stages = s.n_stages;
     a.warp_smem = s.warp_smem;
     a.round_bias = 1 << 18;
+    a.dbg_times = nullptr;
     a.reg_lo = s.reg_lo;
     a.reg_hi = s.reg_hi;
     a.align_p = s.align_p;
