@@ -350,13 +350,24 @@ def main():
         done += cnt
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
+    e2e_h2d, e2e_d2h = eng.h2d_bytes, eng.d2h_bytes
     clocks = sampler.stop() if rank == 0 else None
     barrier()
+    # the same pass with the frames handed over on the device (no D2H of frames): what a GPU-resident consumer sees
+    t0 = time.perf_counter()
+    done = 0
+    for r in range(reps):
+        cnt = min(n_e2e, K * F - done)
+        eng.run(0, cnt, None, device_sink=lambda chunk, k0: None)
+        done += cnt
+    torch.cuda.synchronize(dev)
+    dsink_s = time.perf_counter() - t0
+    barrier()
 
-    t = torch.tensor([dev_ms, e2e_s * 1000.0], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_s * 1000.0, dsink_s * 1000.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    dev_ms_max, e2e_ms_max, dsink_ms_max = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -375,8 +386,11 @@ def main():
         "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic", "config": _config(dw, world),
         "segments_per_sec": segs_per_s,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": eng.h2d_bytes // max(K, 1),
-                "d2h_bytes_per_step": eng.d2h_bytes // max(K, 1)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_h2d // max(K, 1),
+                "d2h_bytes_per_step": e2e_d2h // max(K, 1)},
+        "e2e_device_sink": {"value": world * K * F / (dsink_ms_max * 1e-3), "unit": UNIT,
+                            "note": "host bitstream in, frames consumed on the device (SegmentIngestor.run(device_sink=...)), "
+                                    "scores to host; not the contract's e2e"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": ach[dominant], "peak": peak, "unit": "GB/s",
                      "frac": ach[dominant] / peak,

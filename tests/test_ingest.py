@@ -173,3 +173,30 @@ def test_config3_4k_scene_cuts_scores_only(cuda, oracle_c, tmp_path):
     assert set(meta["cuts"]) <= set(res.cuts.tolist())
     for k in (0, 7, 35):
         assert np.array_equal(res.hist[k], oracle_c.sad_hist(exp[k][0], None)[1])
+
+
+def test_device_sink_hands_over_the_same_frames_without_a_host_copy(cuda, tmp_path):
+    """A consumer on the GPU takes each batch on the compute stream; frames equal the host-sink frames and the pass
+    copies only scores to the host."""
+    import torch
+    from video_transformer_b200 import ingest
+    src, meta = _clip(tmp_path, 640, 480, 50, 10, cuts=[23])
+    idx = container.probe(src)
+    opts = ingest.IngestOptions(target_height=240, batch_frames=8, scene_threshold=0.05)
+    host = []
+    ref = ingest.SegmentIngestor(idx, opts).run(3, 47, lambda chunk, k0: host.append((k0, chunk.numpy().copy())))
+    eng = ingest.SegmentIngestor(idx, opts)
+    dev = torch.zeros((44, eng.frame_bytes), dtype=torch.uint8, device="cuda")
+    seen = []
+
+    def on_device(chunk, k0):
+        assert chunk.is_cuda
+        dev[k0 - 3:k0 - 3 + chunk.shape[0]].copy_(chunk, non_blocking=True)   # enqueued on the compute stream
+        seen.append((k0, chunk.shape[0]))
+
+    res = eng.run(3, 47, None, device_sink=on_device)
+    torch.cuda.synchronize()
+    assert [k for k, _ in seen] == [k for k, _ in host] and sum(n for _, n in seen) == 44
+    assert np.array_equal(dev.cpu().numpy(), np.concatenate([c for _, c in host]))
+    assert np.array_equal(res.sad, ref.sad) and res.cuts.tolist() == ref.cuts.tolist()
+    assert eng.d2h_bytes == 50 * 0 + sum(min(8, 47 - b) for b in range(0, 47, 8)) * (8 + 1024)   # scores only

@@ -192,8 +192,14 @@ class SegmentIngestor:
         pay[first_idr - b0:] = self.payload[first_idr:b1] - np.uint64(lo)
         return pay, nbytes
 
-    def run(self, first: int, last: int, sink=None) -> IngestResult:
-        """Process pictures [first, last).  Output frames go to sink(chunk_host_tensor, first_picture)."""
+    def run(self, first: int, last: int, sink=None, device_sink=None) -> IngestResult:
+        """Process pictures [first, last).  Output frames go to sink(chunk_host_tensor, first_picture).
+
+        device_sink(chunk_device_tensor, first_picture), if given, receives every batch's frames ON THE DEVICE instead:
+        it is called with the compute stream current, right after the kernels that produce the chunk were enqueued,
+        so whatever it enqueues on the current stream is ordered after them and before the buffers are reused; the
+        frames are then not copied to the host at all (scores still are).  This is the hand-off for a consumer that
+        lives on the GPU (the model's own input pipeline): the D2H copy is what bounds the host-buffer path."""
         n_total = self.idx.n_frames
         if not (0 <= first < last <= n_total):
             raise ValueError("picture range [%d,%d) outside the stream (%d pictures)" % (first, last, n_total))
@@ -228,7 +234,7 @@ class SegmentIngestor:
                 k0 = lo - b0
                 sad_all[lo - r0:hi - r0] = slot["sad_host"].numpy()[k0:k0 + hi - lo].view(np.uint64)
                 hist_all[lo - r0:hi - r0] = slot["hist_host"].numpy()[k0:k0 + hi - lo].view(np.uint32)
-            if sink is not None and self.opts.keep_frames:
+            if sink is not None and self.opts.keep_frames and device_sink is None:
                 keep = slot["kept"]
                 if keep is None:                              # every picture from max(b0, first) on, in place
                     lo = max(b0, first)
@@ -301,12 +307,20 @@ class SegmentIngestor:
                     else:
                         check(L.vt_nv12_to_yuv420p(c_void_p(src_t.data_ptr()), self.pitch, self.surface_bytes, self.w,
                                                    self.h, c_void_p(slot["out"].data_ptr()), self.frame_bytes, n_conv, st))
+                if device_sink is not None and self.opts.keep_frames:
+                    if kept is not None:
+                        if len(kept):
+                            device_sink(slot["out"][:len(kept)], kept[0])
+                    elif b1 > max(b0, first):
+                        device_sink(slot["out"][max(b0, first) - b0:nb], max(b0, first))
                 slot["ev_cmp"].record(self.s_cmp)
                 prev_surface = surf[nb - 1]
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(slot["ev_cmp"])
                 lo = max(b0, first)
-                if self.opts.keep_frames and kept is not None:
+                if device_sink is not None:
+                    pass                                  # frames were handed over on the device
+                elif self.opts.keep_frames and kept is not None:
                     if len(kept):
                         slot["out_host"][:len(kept)].copy_(slot["out"][:len(kept)], non_blocking=True)
                         self.d2h_bytes += len(kept) * self.frame_bytes
