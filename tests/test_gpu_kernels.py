@@ -247,3 +247,23 @@ def test_bad_arguments_return_error_codes_not_crashes(cuda, vtlib):
     assert b"odd output width" in vtlib.vt_last_error()
     plan = ops.ScalePlan(64, 48, 32, 24)
     assert vtlib.vt_scale_nv12_to_yuv420p(plan._h, p, 32, 64 * 72, p, 32 * 24 * 3 // 2, 1, None) == _lib.VT_ERR_INVALID   # pitch < width
+
+
+@pytest.mark.parametrize("offset", [4, 2])
+def test_scale_into_a_destination_that_is_not_8_byte_aligned(cuda, oracle_c, offset):
+    """The adjacent-column layout stores 8 bytes per lane; a destination aligned to 4 (or 2) bytes must take the pair
+    layout (or the general kernels) and still be bit-exact."""
+    sw, sh, pitch, dw, dh, n = 1920, 1080, 1920, 1280, 720, 2
+    rng = np.random.default_rng(99)
+    buf = _nv12_batch(rng, n, sw, sh, pitch)
+    plan = ops.ScalePlan(sw, sh, dw, dh, ops.SWS_BICUBIC)
+    fb = plan.out_frame_bytes
+    raw = torch.zeros(n * fb + 64, dtype=torch.uint8, device=cuda)
+    out = raw[offset:offset + n * fb].view(n, fb)
+    plan.scale_nv12(torch.from_numpy(buf).to(cuda).view(-1), pitch, n, out=out)
+    got = out.cpu().numpy()
+    for f in range(n):
+        y, u, v = oracle_c.nv12_to_yuv420p(buf[f].reshape(-1), sw, sh, pitch)
+        ey, eu, ev = oracle_c.scale_yuv420p(y, u, v, dw, dh, oracle_c.BICUBIC)
+        assert np.array_equal(got[f], np.concatenate([ey.reshape(-1), eu.reshape(-1), ev.reshape(-1)])), f
+    assert int(raw[:offset].sum()) == 0 and int(raw[offset + n * fb:].sum()) == 0    # nothing written outside
