@@ -144,6 +144,18 @@ int vt_h264_pcm_decode(const uint8_t *bitstream_dev, const uint64_t *payload_off
                        int height, const uint8_t *prev_dev, uint8_t *nv12_dev, int pitch, size_t frame_stride,
                        void *stream);
 
+/* ---- the fused production entry: one call per batch of pictures -------------------------------------------
+ * decode (K0) -> SAD + histogram on the decoded luma (K3) -> frames at the output size (K2 when `plan` is given,
+ * else K1 same-size conversion), all enqueued on `stream`.  This is the whole per-batch body of the ingest pass
+ * (src/analyzer/content_analyzer.py:193-211 is the reference's decode -> scale loop); hosts in any language drive the
+ * path with this one call plus their own copies.
+ *   prev_dev  : the surface that precedes picture 0 of the batch (NULL for the first batch of a stream)
+ *   out_dev   : n_frames x out_frame_bytes planar YUV420P, or NULL to skip the frame output (scores only) */
+int vt_ingest_batch_pcm(const vt_scale_plan *plan, const uint8_t *bitstream_dev, const uint64_t *payload_off,
+                        int n_frames, int width, int height, const uint8_t *prev_dev, uint8_t *nv12_dev, int pitch,
+                        size_t surface_bytes, uint64_t *sad_dev, uint32_t *hist_dev, uint8_t *out_dev,
+                        size_t out_frame_bytes, void *stream);
+
 /* NVDEC availability: VT_OK when libnvcuvid.so.1 loads and cuvidGetDecoderCaps reports H.264 8-bit 4:2:0
  * support; VT_ERR_NVDEC otherwise (message in vt_last_error()). */
 int vt_nvdec_probe(int *n_engines, int *max_w, int *max_h);

@@ -51,6 +51,8 @@ SIGNATURES = {
                                       c_int, c_void_p]),
     "vt_h264_pcm_decode": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_size_t,
                                    c_void_p]),
+    "vt_ingest_batch_pcm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_size_t,
+                                    c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vt_nvdec_probe": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
 }
 

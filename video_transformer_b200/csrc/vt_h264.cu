@@ -496,3 +496,16 @@ extern "C" int vt_h264_pcm_decode(const uint8_t *bs_dev, const uint64_t *payload
     }
     return VT_OK;
 }
+
+// The per-batch body of the ingest pass as one C call (see include/vtseg.h).
+extern "C" int vt_ingest_batch_pcm(const vt_scale_plan *plan, const uint8_t *bs_dev, const uint64_t *payload_off,
+                                   int n_frames, int width, int height, const uint8_t *prev_dev, uint8_t *nv12_dev,
+                                   int pitch, size_t surface_bytes, uint64_t *sad_dev, uint32_t *hist_dev,
+                                   uint8_t *out_dev, size_t out_frame_bytes, void *stream) {
+    int rc = vt_h264_pcm_decode(bs_dev, payload_off, n_frames, width, height, prev_dev, nv12_dev, pitch, surface_bytes, stream);
+    if (rc) return rc;
+    rc = vt_sad_hist_u8(nv12_dev, pitch, surface_bytes, width, height, prev_dev, n_frames, sad_dev, hist_dev, stream);
+    if (rc || !out_dev) return rc;
+    if (plan) return vt_scale_nv12_to_yuv420p(plan, nv12_dev, pitch, surface_bytes, out_dev, out_frame_bytes, n_frames, stream);
+    return vt_nv12_to_yuv420p(nv12_dev, pitch, surface_bytes, width, height, out_dev, out_frame_bytes, n_frames, stream);
+}

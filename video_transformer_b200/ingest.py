@@ -291,12 +291,22 @@ class SegmentIngestor:
                 self.s_cmp.wait_event(slot["ev_in"])
                 st = c_void_p(self.s_cmp.cuda_stream)
                 surf = slot["surf"]
-                check(L.vt_h264_pcm_decode(c_void_p(slot["bs_dev"].data_ptr()), pay.ctypes.data, nb, self.w, self.h,
-                                           c_void_p(prev_surface.data_ptr()) if prev_surface is not None else None,
-                                           c_void_p(surf.data_ptr()), self.pitch, self.surface_bytes, st))
-                check(L.vt_sad_hist_u8(c_void_p(surf.data_ptr()), self.pitch, self.surface_bytes, self.w, self.h,
-                                       c_void_p(prev_surface.data_ptr()) if prev_surface is not None else None, nb,
-                                       c_void_p(slot["sad"].data_ptr()), c_void_p(slot["hist"].data_ptr()), st))
+                prev_p = c_void_p(prev_surface.data_ptr()) if prev_surface is not None else None
+                # the common case (every picture kept, planar output) is ONE C call per batch: decode -> score -> frames
+                fused = self.opts.sample_every == 1 and self.rgb_plan is None
+                if fused:
+                    check(L.vt_ingest_batch_pcm(self.plan._h if self.plan is not None else None,
+                                                c_void_p(slot["bs_dev"].data_ptr()), pay.ctypes.data, nb, self.w, self.h,
+                                                prev_p, c_void_p(surf.data_ptr()), self.pitch, self.surface_bytes,
+                                                c_void_p(slot["sad"].data_ptr()), c_void_p(slot["hist"].data_ptr()),
+                                                c_void_p(slot["out"].data_ptr()) if self.opts.keep_frames else None,
+                                                self.frame_bytes, st))
+                else:
+                    check(L.vt_h264_pcm_decode(c_void_p(slot["bs_dev"].data_ptr()), pay.ctypes.data, nb, self.w, self.h,
+                                               prev_p, c_void_p(surf.data_ptr()), self.pitch, self.surface_bytes, st))
+                    check(L.vt_sad_hist_u8(c_void_p(surf.data_ptr()), self.pitch, self.surface_bytes, self.w, self.h,
+                                           prev_p, nb, c_void_p(slot["sad"].data_ptr()),
+                                           c_void_p(slot["hist"].data_ptr()), st))
                 kept = None
                 src_t, n_conv, out_row0 = surf, nb, 0
                 if self.opts.keep_frames and self.opts.sample_every > 1:
@@ -311,7 +321,7 @@ class SegmentIngestor:
                                                  c_void_p(slot["sel_surf"].data_ptr()), st))
                         src_t = slot["sel_surf"]
                 slot["kept"] = kept
-                if self.opts.keep_frames and n_conv:
+                if self.opts.keep_frames and n_conv and not fused:
                     if self.rgb_plan is not None:
                         check(L.vt_scale_nv12_to_rgb24(self.rgb_plan._h, c_void_p(src_t.data_ptr()), self.pitch,
                                                        self.surface_bytes, c_void_p(slot["out"].data_ptr()),
