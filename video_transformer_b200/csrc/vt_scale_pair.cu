@@ -162,7 +162,18 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t phase) {
 constexpr uint32_t PAIR_TILE_W = VT_PAIR_WIDE ? 448 : 256;   // bytes per row of every TMA box (32-bit elements: up to 1024 B)
 
 __host__ __device__ constexpr int pair_np(int hp, int tv) { return (VT_PAIR_WIDE && hp <= 3 && tv <= 8) ? 4 : 2; }   // luma pairs per lane
-__host__ __device__ constexpr int pair_min_blocks(int hp, int tv) { return (hp <= 4 && tv <= 8) ? VT_PAIR_BLOCKS : 3; }
+#ifndef VT_PAIR_SG8
+#define VT_PAIR_SG8 2                    // groups per stage / static block for 8 vertical taps: 2 (16-row boxes, three
+                                         // blocks per SM) measured 8-12 % faster than 1 (8-row boxes, five blocks)
+#endif
+#ifndef VT_PAIR_SG12
+#define VT_PAIR_SG12 1                   // the same for 12 vertical taps: 2 (24-row boxes, two blocks per SM) measured 5-8 % slower
+#endif
+__host__ __device__ constexpr int pair_sg(int tv) { return tv <= 6 ? 2 : (tv <= 8 ? VT_PAIR_SG8 : VT_PAIR_SG12); }
+__host__ __device__ constexpr int pair_min_blocks(int hp, int tv) {
+    return (hp <= 4 && tv <= 6) ? VT_PAIR_BLOCKS : (hp <= 4 && tv <= 8) ? (VT_PAIR_SG8 == 2 ? 3 : VT_PAIR_BLOCKS)
+                                                 : (tv > 8 && VT_PAIR_SG12 == 2 ? 2 : 3);
+}
 
 // compile-time loop: f(std::integral_constant<int, K>) for K = I .. N-1 (the row index must be a constant expression
 // so that ring slots, mask bits and coefficient offsets fold into the instructions)
@@ -236,7 +247,7 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     constexpr int VS = VCfg<TV>::STRIDE;
     constexpr int NOUT = popc_c((unsigned)MASK);      // output rows per regular group
     constexpr int FIRSTK = MASK ? ctz_c((unsigned)MASK) : 0;
-    constexpr int SG = TV <= 6 ? 2 : 1;               // groups per static block (= groups per TMA stage)
+    constexpr int SG = pair_sg(TV);                   // groups per static block (= groups per TMA stage)
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform for the compiler
@@ -782,7 +793,7 @@ int build_pair(vt_scale_plan *p, int c) {
     // row blocks then in flight); box height and alignment hardly matter.
     const int nb = pair_min_blocks(s.hp, s.tv);
     s.n_stages = 2;
-    s.groups_per_stage = s.tv <= 6 ? 2 : 1;
+    s.groups_per_stage = pair_sg(s.tv);
     if (getenv("VT_PAIR_RG") && getenv("VT_PAIR_NST")) {                    // geometry experiments
         s.groups_per_stage = atoi(getenv("VT_PAIR_RG"));
         s.n_stages = atoi(getenv("VT_PAIR_NST"));
