@@ -26,12 +26,14 @@ namespace vt {
 // ---- generic two-kernel path -----------------------------------------------------------------------------
 // channel_step = 1 for planar sources, 2 for the interleaved UV plane of NV12 (channel_off picks U or V).
 __global__ void __launch_bounds__(256)
-hscale_generic_kernel(const uint8_t *__restrict__ src, int src_pitch, int sh, int channel_step, int channel_off,
-                      int16_t *__restrict__ mid, int dw, const int16_t *__restrict__ coef,
-                      const int32_t *__restrict__ pos, int taps) {
+hscale_generic_kernel(const uint8_t *__restrict__ src, int src_pitch, size_t src_fs, int sh, int channel_step,
+                      int channel_off, int16_t *__restrict__ mid, size_t mid_fs, int dw,
+                      const int16_t *__restrict__ coef, const int32_t *__restrict__ pos, int taps) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
     if (x >= dw || r >= sh) return;
+    src += (size_t)blockIdx.z * src_fs;                              // blockIdx.z = picture of the chunk
+    mid += (size_t)blockIdx.z * mid_fs;
     const uint8_t *s = src + (size_t)r * src_pitch + (size_t)pos[x] * channel_step + channel_off;
     const int16_t *c = coef + (size_t)x * taps;
     int v = 0;
@@ -41,11 +43,13 @@ hscale_generic_kernel(const uint8_t *__restrict__ src, int src_pitch, int sh, in
 }
 
 __global__ void __launch_bounds__(256)
-vscale_generic_kernel(const int16_t *__restrict__ mid, int dw, uint8_t *__restrict__ dst, int dst_pitch, int dh,
-                      const int16_t *__restrict__ coef, const int32_t *__restrict__ pos, int taps) {
+vscale_generic_kernel(const int16_t *__restrict__ mid, size_t mid_fs, int dw, uint8_t *__restrict__ dst, int dst_pitch,
+                      size_t dst_fs, int dh, const int16_t *__restrict__ coef, const int32_t *__restrict__ pos, int taps) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     if (x >= dw || y >= dh) return;
+    mid += (size_t)blockIdx.z * mid_fs;
+    dst += (size_t)blockIdx.z * dst_fs;
     int v;
     if (taps == 1) {
         v = (mid[(size_t)pos[y] * dw + x] + 64) >> 7;
@@ -59,17 +63,23 @@ vscale_generic_kernel(const int16_t *__restrict__ mid, int dw, uint8_t *__restri
     dst[(size_t)y * dst_pitch + x] = (uint8_t)max(0, min(255, v));
 }
 
+// n_frames pictures src_fs / dst_fs bytes apart, in chunks of p->scratch_frames (one launch pair per chunk)
 int scale_plane_generic(const vt_scale_plan *p, int chroma, const uint8_t *src, int src_pitch, int channel_step,
-                        int channel_off, uint8_t *dst, int dst_pitch, cudaStream_t st) {
+                        int channel_off, uint8_t *dst, int dst_pitch, int n_frames, size_t src_fs, size_t dst_fs,
+                        cudaStream_t st) {
     const int c = chroma ? 1 : 0;
     const int sh = c ? p->csh : p->sh, dw = c ? p->cdw : p->dw, dh = c ? p->cdh : p->dh;
-    dim3 b(256), gh((dw + 255) / 256, sh), gv((dw + 255) / 256, dh);
-    hscale_generic_kernel<<<gh, b, 0, st>>>(src, src_pitch, sh, channel_step, channel_off, p->scratch, dw,
-                                            p->hcoef[c], p->hpos[c], p->htaps[c]);
-    VT_LAUNCHED("hscale_generic_kernel");
-    vscale_generic_kernel<<<gv, b, 0, st>>>(p->scratch, dw, dst, dst_pitch, dh, p->vcoef[c], p->vpos[c],
-                                            p->vtaps[c]);
-    VT_LAUNCHED("vscale_generic_kernel");
+    const size_t mid_fs = (size_t)p->dw * p->sh;                     // scratch is laid out for the larger (luma) plane
+    for (int f0 = 0; f0 < n_frames; f0 += p->scratch_frames) {
+        const int nf = std::min(p->scratch_frames, n_frames - f0);
+        dim3 b(256), gh((dw + 255) / 256, sh, nf), gv((dw + 255) / 256, dh, nf);
+        hscale_generic_kernel<<<gh, b, 0, st>>>(src + (size_t)f0 * src_fs, src_pitch, src_fs, sh, channel_step, channel_off,
+                                                p->scratch, mid_fs, dw, p->hcoef[c], p->hpos[c], p->htaps[c]);
+        VT_LAUNCHED("hscale_generic_kernel");
+        vscale_generic_kernel<<<gv, b, 0, st>>>(p->scratch, mid_fs, dw, dst + (size_t)f0 * dst_fs, dst_pitch, dst_fs, dh,
+                                                p->vcoef[c], p->vpos[c], p->vtaps[c]);
+        VT_LAUNCHED("vscale_generic_kernel");
+    }
     return VT_OK;
 }
 
@@ -198,7 +208,9 @@ extern "C" int vt_scale_plan_create(int sw, int sh, int dw, int dh, int flags, v
         if (rc == VT_OK) rc = upload(p->h_vcoef[c].data(), p->h_vcoef[c].size() * 2, (void **)&p->vcoef[c]);
         if (rc == VT_OK) rc = upload(p->h_vpos[c].data(), p->h_vpos[c].size() * 4, (void **)&p->vpos[c]);
     }
-    if (rc == VT_OK && cudaMalloc((void **)&p->scratch, (size_t)dw * sh * sizeof(int16_t)) != cudaSuccess)
+    // intermediates of the two-pass kernels: as many pictures per launch as fit 128 MB (at most 32)
+    p->scratch_frames = (int)std::max<size_t>(1, std::min<size_t>(32, ((size_t)128 << 20) / ((size_t)dw * sh * sizeof(int16_t))));
+    if (rc == VT_OK && cudaMalloc((void **)&p->scratch, (size_t)p->scratch_frames * dw * sh * sizeof(int16_t)) != cudaSuccess)
         rc = VT_ERR_NOMEM;
     for (int c = 0; c < 2 && rc == VT_OK; c++) rc = vt::build_pair(p, c);
     if (rc != VT_OK) {
@@ -226,7 +238,7 @@ extern "C" int vt_scale_plane_u8(const vt_scale_plan *plan, int chroma, const ui
         vt::set_error("vt_scale_plane_u8: null argument");
         return VT_ERR_INVALID;
     }
-    return vt::scale_plane_generic(plan, chroma, src, src_pitch, 1, 0, dst, dst_pitch, (cudaStream_t)stream);
+    return vt::scale_plane_generic(plan, chroma, src, src_pitch, 1, 0, dst, dst_pitch, 1, 0, 0, (cudaStream_t)stream);
 }
 
 extern "C" int vt_scale_nv12_to_yuv420p(const vt_scale_plan *p, const uint8_t *src, int src_pitch, size_t src_fs,
@@ -241,22 +253,20 @@ extern "C" int vt_scale_nv12_to_yuv420p(const vt_scale_plan *p, const uint8_t *s
                          ((uintptr_t)dst % 4 == 0) && (dst_fs % 4 == 0) && (p->sw % 2 == 0) && (p->sh % 2 == 0);
     // VT_SCALE_KERNEL=generic selects the two-pass kernels (A/B measurements only)
     static const char *force = getenv("VT_SCALE_KERNEL");
-    if (aligned && !(force && !strcmp(force, "generic")) && p->pair[0].ok && p->pair[1].ok) {
-        int rc = vt::launch_pair(p, 0, src, src_pitch, src_fs, dst, dst_fs, n_frames, st);
-        if (rc) return rc;
-        return vt::launch_pair(p, 1, src, src_pitch, src_fs, dst, dst_fs, n_frames, st);
-    }
-    for (int f = 0; f < n_frames; f++) {
-        const uint8_t *s = src + (size_t)f * src_fs;
-        uint8_t *d = dst + (size_t)f * dst_fs;
-        int rc = vt::scale_plane_generic(p, 0, s, src_pitch, 1, 0, d, p->dw, st);
-        if (rc) return rc;
-        const uint8_t *uv = s + (size_t)src_pitch * p->sh;
-        rc = vt::scale_plane_generic(p, 1, uv, src_pitch, 2, 0, d + ysz, p->cdw, st);
-        if (rc) return rc;
-        rc = vt::scale_plane_generic(p, 1, uv, src_pitch, 2, 1, d + ysz + csz, p->cdw, st);
-        if (rc) return rc;
-    }
+    // Each plane kind takes the pair kernel when its plan has one (even plane width, taps within the instantiated
+    // range ...) and the batched two-pass kernels otherwise -- e.g. 1920x1080 -> 854x480: luma streams, the 427-wide
+    // chroma planes (odd width: rows are not 2-byte aligned) go through the general kernels.
+    const bool fast = aligned && !(force && !strcmp(force, "generic"));
+    int rc;
+    if (fast && p->pair[0].ok) rc = vt::launch_pair(p, 0, src, src_pitch, src_fs, dst, dst_fs, n_frames, st);
+    else rc = vt::scale_plane_generic(p, 0, src, src_pitch, 1, 0, dst, p->dw, n_frames, src_fs, dst_fs, st);
+    if (rc) return rc;
+    if (fast && p->pair[1].ok) return vt::launch_pair(p, 1, src, src_pitch, src_fs, dst, dst_fs, n_frames, st);
+    const uint8_t *uv = src + (size_t)src_pitch * p->sh;
+    rc = vt::scale_plane_generic(p, 1, uv, src_pitch, 2, 0, dst + ysz, p->cdw, n_frames, src_fs, dst_fs, st);
+    if (rc) return rc;
+    rc = vt::scale_plane_generic(p, 1, uv, src_pitch, 2, 1, dst + ysz + csz, p->cdw, n_frames, src_fs, dst_fs, st);
+    if (rc) return rc;
     return VT_OK;
 }
 

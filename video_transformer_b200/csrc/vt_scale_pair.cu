@@ -50,11 +50,13 @@ namespace vt {
 template <int TV>
 struct VCfg {
     static constexpr int STRIDE = (TV + 1 + 3) & ~3;  // coefficients[TV] (front padded), last source row, padding
-    static constexpr int ROWS = 28672 / (STRIDE * 4); // output rows one launch can cover (parameter space is 32 KB)
+    static constexpr int ROWS = 28672 / (STRIDE * 2); // output rows one launch can cover (parameter space is 32 KB)
 };
+// 16-bit entries (coefficients are 13-bit, source rows < 32768): 720 rows of a 12-tap plan or 1080 rows of an 8-tap plan
+// fit one launch
 template <int TV>
 struct __align__(16) VTab {
-    int32_t t[VCfg<TV>::ROWS * VCfg<TV>::STRIDE];
+    int16_t t[VCfg<TV>::ROWS * VCfg<TV>::STRIDE];
 };
 
 struct PairArgs {
@@ -623,7 +625,7 @@ int launch_t(const vt_scale_plan::Pair &s, const CUtensorMap &tm, PairArgs a, in
     const int cap = VCfg<TV>::ROWS - 1;      // the kernel reads one table entry ahead
     for (int yb = 0; yb < rows_total; yb += cap) {
         const int ye = std::min(rows_total, yb + cap);
-        std::memcpy(vt_host.t, s.vtab.data() + (size_t)yb * s.vstride, (size_t)(ye - yb) * s.vstride * sizeof(int32_t));
+        for (size_t i = 0, n = (size_t)(ye - yb) * s.vstride; i < n; i++) vt_host.t[i] = (int16_t)s.vtab[(size_t)yb * s.vstride + i];
         a.y_begin = yb;
         a.y_end = ye;
         const int rows = ye - yb;
@@ -763,6 +765,7 @@ int build_pair(vt_scale_plan *p, int c) {
     s.np = uv ? pair_np(s.hp, s.tv) / 2 : pair_np(s.hp, s.tv);
     s.strip_cols = s.np * 64;
     if ((dw & 1) || (p->dw & 1) || dw < s.strip_cols) return VT_OK;
+    if ((c ? p->csh : p->sh) > 32767) return VT_OK;              // the vertical table holds source rows as int16
     for (int x = 0; x + 1 < dw; x++)
         if (hpos[x + 1] < hpos[x]) return VT_OK;
     for (int x = 0; x + 1 < dw; x += 2)

@@ -13,7 +13,8 @@ struct vt_scale_plan {
     int32_t *hpos[2];
     int16_t *vcoef[2];  // dh x vtaps
     int32_t *vpos[2];
-    int16_t *scratch;  // generic path: dw x sh int16
+    int16_t *scratch;  // generic path: scratch_frames x (dw x sh) int16
+    int scratch_frames;
     // host copies (table construction for the pair kernel)
     std::vector<int16_t> h_hcoef[2], h_vcoef[2];
     std::vector<int32_t> h_hpos[2], h_vpos[2];
