@@ -101,10 +101,16 @@ def test_scale_plane_generic_bit_exact(cuda, oracle_c, flags, sw, sh, dw, dh):
     (2880, 1620, 3072, 960, 540, ops.SWS_BICUBIC),
     (810, 540, 896, 540, 360, ops.SWS_BICUBIC),         # 3:2 but the width is not a multiple of 8: pair layout
     (960, 540, 1024, 640, 360, ops.SWS_BILINEAR),
+    # planes the pair kernel does not take: narrower than a strip / odd chroma width -> fast two-pass kernels;
+    # more than 16 horizontal taps -> general two-pass kernels (both batched over the pictures)
+    (322, 182, 336, 160, 90, ops.SWS_BICUBIC),
+    (640, 360, 640, 200, 112, ops.SWS_BILINEAR),
+    (1920, 1080, 1920, 426, 240, ops.SWS_BICUBIC),
+    (1280, 720, 1280, 1280, 360, ops.SWS_BICUBIC),      # horizontal taps of 1, vertical 2:1
 ])
 def test_scale_nv12_to_yuv420p_bit_exact(cuda, oracle_c, sw, sh, pitch, dw, dh, flags):
     rng = np.random.default_rng(sw * 3 + dw)
-    n = 2
+    n = 2 if sw * sh > 640 * 360 else 35              # small shapes: more pictures than one two-pass chunk (32)
     buf = _nv12_batch(rng, n, sw, sh, pitch)
     plan = ops.ScalePlan(sw, sh, dw, dh, flags)
     out = plan.scale_nv12(torch.from_numpy(buf).to(cuda).view(-1), pitch, n).cpu().numpy()

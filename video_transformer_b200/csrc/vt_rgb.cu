@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "vt_common.cuh"
+#include "vt_hscale_fast.cuh"
 
 struct vt_rgb_plan {
     int sw, sh, dw, dh, flags;
@@ -57,119 +58,6 @@ rgb_hscale_kernel(const uint8_t *__restrict__ src, int pitch, size_t src_fs, int
     for (int j = 0; j < taps; j++) v += (int)s[(size_t)j * step] * (int)c[j];
     v >>= 7;
     mid[(size_t)blockIdx.z * mid_fs + (size_t)r * dw + x] = (int16_t)min(v, 32767);
-}
-
-__device__ __forceinline__ int rgb_dp2a_lo(uint32_t coef_pair, uint32_t pix, int acc) {
-    int d;
-    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(coef_pair), "r"(pix), "r"(acc));
-    return d;
-}
-__device__ __forceinline__ int rgb_dp2a_hi(uint32_t coef_pair, uint32_t pix, int acc) {
-    int d;
-    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(coef_pair), "r"(pix), "r"(acc));
-    return d;
-}
-
-// HP coefficient pairs of one output sample, fetched with the widest aligned loads (rows of the table are HP words)
-template <int HP>
-__device__ __forceinline__ void rgb_load_pairs(const uint32_t *__restrict__ t, uint32_t (&c)[HP]) {
-    if constexpr (HP % 4 == 0) {
-#pragma unroll
-        for (int i = 0; i < HP / 4; i++) {
-            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(t) + i);
-            c[4 * i] = q.x; c[4 * i + 1] = q.y; c[4 * i + 2] = q.z; c[4 * i + 3] = q.w;
-        }
-    } else if constexpr (HP % 2 == 0) {
-#pragma unroll
-        for (int i = 0; i < HP / 2; i++) {
-            const uint2 q = __ldg(reinterpret_cast<const uint2 *>(t) + i);
-            c[2 * i] = q.x; c[2 * i + 1] = q.y;
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < HP; i++) c[i] = __ldg(t + i);
-    }
-}
-
-// Horizontal taps, luma: one thread per output sample, HP coefficient pairs.  The taps' bytes are fetched as aligned
-// 32-bit words (clamped to the row's last word: bytes past the taps carry zero coefficients) and funnel-shifted into
-// place; each dp2a multiplies two pixels by two 14-bit coefficients.
-constexpr int RGB_RPT = 8;     // source rows per thread of the horizontal kernels: position, shift and coefficients are
-                               // fetched once and the per-row work is loads + dp2a (the one-row form spent 40 of its 62
-                               // instructions on indices)
-template <int HP>
-__global__ void __launch_bounds__(256)
-rgb_hscale_luma_fast(const uint8_t *__restrict__ src, int pitch, size_t src_fs, int rows, int16_t *__restrict__ mid,
-                     size_t mid_fs, int dw, const uint32_t *__restrict__ coef2, const int32_t *__restrict__ pos) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= dw) return;
-    constexpr int NAW = (HP + 1) / 2, NW = NAW + 1;
-    const int r0 = blockIdx.y * RGB_RPT, nr = min(RGB_RPT, rows - r0);
-    const int a = __ldg(pos + x);
-    const int w0 = a >> 2, wl = (pitch >> 2) - 1, pw = pitch >> 2;
-    const uint32_t sh = (uint32_t)(a & 3) * 8u;
-    int wi[NW];
-#pragma unroll
-    for (int i = 0; i < NW; i++) wi[i] = min(w0 + i, wl);
-    uint32_t c[HP];
-    rgb_load_pairs<HP>(coef2 + (size_t)x * HP, c);
-    const uint32_t *row = reinterpret_cast<const uint32_t *>(src + (size_t)blockIdx.z * src_fs + (size_t)r0 * pitch);
-    int16_t *mo = mid + (size_t)blockIdx.z * mid_fs + (size_t)r0 * dw + x;
-#pragma unroll 4
-    for (int r = 0; r < nr; r++) {
-        uint32_t w[NW];
-#pragma unroll
-        for (int i = 0; i < NW; i++) w[i] = __ldg(row + wi[i]);
-        int v = 0;
-#pragma unroll
-        for (int i = 0; i < HP; i++) {
-            const uint32_t al = __funnelshift_r(w[i >> 1], w[(i >> 1) + 1], sh);
-            v = (i & 1) ? rgb_dp2a_hi(c[i], al, v) : rgb_dp2a_lo(c[i], al, v);
-        }
-        *mo = (int16_t)min(v >> 7, 32767);
-        row += pw;
-        mo += dw;
-    }
-}
-
-// Horizontal taps, NV12 chroma: one thread per output sample produces U and V.  Sample pair (t, t+1) is one aligned
-// word U_t V_t U_t+1 V_t+1 after the funnel shift; a byte permute makes it (U_t, U_t+1, V_t, V_t+1), so dp2a.lo is
-// the U taps and dp2a.hi the V taps with the same coefficient pair.
-template <int HP>
-__global__ void __launch_bounds__(256)
-rgb_hscale_chroma_fast(const uint8_t *__restrict__ src, int pitch, size_t src_fs, int rows, int16_t *__restrict__ mu,
-                       int16_t *__restrict__ mv, size_t mid_fs, int cdw, const uint32_t *__restrict__ coef2,
-                       const int32_t *__restrict__ pos) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= cdw) return;
-    const int r0 = blockIdx.y * RGB_RPT, nr = min(RGB_RPT, rows - r0);
-    const int a = 2 * __ldg(pos + x);                  // byte offset of the first U sample
-    const int w0 = a >> 2, wl = (pitch >> 2) - 1, pw = pitch >> 2;
-    const uint32_t sh = (uint32_t)(a & 3) * 8u;        // 0 or 16
-    int wi[HP + 1];
-#pragma unroll
-    for (int i = 0; i < HP + 1; i++) wi[i] = min(w0 + i, wl);
-    uint32_t c[HP];
-    rgb_load_pairs<HP>(coef2 + (size_t)x * HP, c);
-    const uint32_t *row = reinterpret_cast<const uint32_t *>(src + (size_t)blockIdx.z * src_fs + (size_t)r0 * pitch);
-    size_t o = (size_t)blockIdx.z * mid_fs + (size_t)r0 * cdw + x;
-#pragma unroll 4
-    for (int r = 0; r < nr; r++) {
-        uint32_t w[HP + 1];
-#pragma unroll
-        for (int i = 0; i < HP + 1; i++) w[i] = __ldg(row + wi[i]);
-        int u = 0, v = 0;
-#pragma unroll
-        for (int i = 0; i < HP; i++) {
-            const uint32_t pw4 = __byte_perm(__funnelshift_r(w[i], w[i + 1], sh), 0u, 0x3120);
-            u = rgb_dp2a_lo(c[i], pw4, u);
-            v = rgb_dp2a_hi(c[i], pw4, v);
-        }
-        mu[o] = (int16_t)min(u >> 7, 32767);
-        mv[o] = (int16_t)min(v >> 7, 32767);
-        row += pw;
-        o += cdw;
-    }
 }
 
 struct RgbConst {
@@ -488,13 +376,13 @@ extern "C" int vt_scale_nv12_to_rgb24(const vt_rgb_plan *p, const uint8_t *src, 
         dim3 b(256);
         uint8_t *d = dst + (size_t)f0 * dst_fs;
         if (fast) {
-            const dim3 gl((p->dw + 255) / 256, (p->sh + vt::RGB_RPT - 1) / vt::RGB_RPT, nf),
-                gc((p->cdw + 255) / 256, (p->csh + vt::RGB_RPT - 1) / vt::RGB_RPT, nf), gv((p->cdw + 255) / 256, p->dh, nf);
-#define VT_HL(H) case H: vt::rgb_hscale_luma_fast<H><<<gl, b, 0, st>>>(s, pitch, src_fs, p->sh, p->my, my_fs, p->dw, p->lhc2, p->lhp); break
+            const dim3 gl((p->dw + 255) / 256, (p->sh + vt::HS_RPT - 1) / vt::HS_RPT, nf),
+                gc((p->cdw + 255) / 256, (p->csh + vt::HS_RPT - 1) / vt::HS_RPT, nf), gv((p->cdw + 255) / 256, p->dh, nf);
+#define VT_HL(H) case H: vt::hscale_luma_fast<H><<<gl, b, 0, st>>>(s, pitch, src_fs, p->sh, p->my, my_fs, p->dw, p->lhc2, p->lhp); break
             switch (p->hpl) { VT_HL(2); VT_HL(3); VT_HL(4); VT_HL(6); VT_HL(8); }
 #undef VT_HL
             VT_LAUNCHED("rgb_hscale_luma_fast");
-#define VT_HC(H) case H: vt::rgb_hscale_chroma_fast<H><<<gc, b, 0, st>>>(uv, pitch, src_fs, p->csh, p->mu, p->mv, mc_fs, p->cdw, p->chc2, p->chp); break
+#define VT_HC(H) case H: vt::hscale_chroma_fast<H><<<gc, b, 0, st>>>(uv, pitch, src_fs, p->csh, p->mu, p->mv, mc_fs, p->cdw, p->chc2, p->chp); break
             switch (p->hpc) { VT_HC(2); VT_HC(3); VT_HC(4); VT_HC(6); VT_HC(8); }
 #undef VT_HC
             VT_LAUNCHED("rgb_hscale_chroma_fast");

@@ -19,6 +19,7 @@
 #include <mutex>
 #include <vector>
 
+#include "vt_hscale_fast.cuh"
 #include "vt_scale_plan.cuh"
 
 namespace vt {
@@ -61,6 +62,76 @@ vscale_generic_kernel(const int16_t *__restrict__ mid, size_t mid_fs, int dw, ui
         v >>= 19;
     }
     dst[(size_t)y * dst_pitch + x] = (uint8_t)max(0, min(255, v));
+}
+
+// Vertical taps, VT unrolled (bank padded with zero coefficients; padded taps read a clamped row), 32-bit indices.
+template <int VT>
+__global__ void __launch_bounds__(256)
+vscale_fast_kernel(const int16_t *__restrict__ mid, size_t mid_fs, int dw, int sh, uint8_t *__restrict__ dst, int dst_pitch,
+                   size_t dst_fs, const int16_t *__restrict__ vc2, const int32_t *__restrict__ vpos) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= dw) return;
+    const int16_t *m = mid + (size_t)blockIdx.z * mid_fs + x;
+    const int r0 = __ldg(vpos + y);
+    int t[VT];
+#pragma unroll
+    for (int j = 0; j < VT; j++) t[j] = __ldg(m + min(r0 + j, sh - 1) * dw);
+    int v = 1 << 18;
+#pragma unroll
+    for (int j = 0; j < VT; j++) v += t[j] * (int)__ldg(vc2 + y * VT + j);
+    dst[(size_t)blockIdx.z * dst_fs + (size_t)y * dst_pitch + x] = (uint8_t)max(0, min(255, v >> 19));
+}
+
+static int pad_vt2(int taps) { return taps < 2 ? 0 : taps <= 4 ? 4 : taps <= 6 ? 6 : taps <= 8 ? 8 : taps <= 12 ? 12 : taps <= 16 ? 16 : 0; }
+
+template <int VT>
+static void launch_vfast(const vt_scale_plan *p, int c, const int16_t *mid, size_t mid_fs, uint8_t *dst, size_t dst_fs, int nf,
+                         cudaStream_t st) {
+    const int sh = c ? p->csh : p->sh, dw = c ? p->cdw : p->dw, dh = c ? p->cdh : p->dh;
+    vscale_fast_kernel<VT><<<dim3((dw + 255) / 256, dh, nf), 256, 0, st>>>(mid, mid_fs, dw, sh, dst, dw, dst_fs, p->vc2[c], p->vpos[c]);
+}
+static int vfast(const vt_scale_plan *p, int c, const int16_t *mid, size_t mid_fs, uint8_t *dst, size_t dst_fs, int nf,
+                 cudaStream_t st) {
+    switch (p->vt2[c]) {
+        case 4: launch_vfast<4>(p, c, mid, mid_fs, dst, dst_fs, nf, st); break;
+        case 6: launch_vfast<6>(p, c, mid, mid_fs, dst, dst_fs, nf, st); break;
+        case 8: launch_vfast<8>(p, c, mid, mid_fs, dst, dst_fs, nf, st); break;
+        case 12: launch_vfast<12>(p, c, mid, mid_fs, dst, dst_fs, nf, st); break;
+        default: launch_vfast<16>(p, c, mid, mid_fs, dst, dst_fs, nf, st); break;
+    }
+    VT_LAUNCHED("vscale_fast_kernel");
+    return VT_OK;
+}
+
+// One plane kind of n_frames NV12 pictures through the dp2a horizontal kernels (vt_hscale_fast.cuh) and the unrolled
+// vertical kernel: luma -> dst_a; chroma -> U into dst_a and V into dst_b from ONE horizontal pass over the interleaved
+// plane.  Requires can_fast(): word-aligned surfaces, taps within the instantiated range.
+int scale_plane_fast(const vt_scale_plan *p, int c, const uint8_t *src, int pitch, size_t src_fs, uint8_t *dst_a,
+                     uint8_t *dst_b, size_t dst_fs, int n_frames, cudaStream_t st) {
+    const int sh = c ? p->csh : p->sh, dw = c ? p->cdw : p->dw;
+    const size_t mid_fs = (size_t)dw * sh;
+    int16_t *ma = p->scratch, *mb = p->scratch + (size_t)p->scratch_frames * mid_fs;   // chroma: 2 * cdw*csh <= dw*sh
+    for (int f0 = 0; f0 < n_frames; f0 += p->scratch_frames) {
+        const int nf = std::min(p->scratch_frames, n_frames - f0);
+        const uint8_t *s = src + (size_t)f0 * src_fs;
+        const dim3 g((dw + 255) / 256, (sh + HS_RPT - 1) / HS_RPT, nf);
+        if (!c) {
+#define VT_H(H) case H: hscale_luma_fast<H><<<g, 256, 0, st>>>(s, pitch, src_fs, sh, ma, mid_fs, dw, p->hc2[0], p->hpos[0]); break
+            switch (p->hp2[0]) { VT_H(2); VT_H(3); VT_H(4); VT_H(6); VT_H(8); }
+#undef VT_H
+            VT_LAUNCHED("hscale_luma_fast");
+            if (int rc = vfast(p, 0, ma, mid_fs, dst_a + (size_t)f0 * dst_fs, dst_fs, nf, st)) return rc;
+        } else {
+#define VT_H(H) case H: hscale_chroma_fast<H><<<g, 256, 0, st>>>(s, pitch, src_fs, sh, ma, mb, mid_fs, dw, p->hc2[1], p->hpos[1]); break
+            switch (p->hp2[1]) { VT_H(2); VT_H(3); VT_H(4); VT_H(6); VT_H(8); }
+#undef VT_H
+            VT_LAUNCHED("hscale_chroma_fast");
+            if (int rc = vfast(p, 1, ma, mid_fs, dst_a + (size_t)f0 * dst_fs, dst_fs, nf, st)) return rc;
+            if (int rc = vfast(p, 1, mb, mid_fs, dst_b + (size_t)f0 * dst_fs, dst_fs, nf, st)) return rc;
+        }
+    }
+    return VT_OK;
 }
 
 // n_frames pictures src_fs / dst_fs bytes apart, in chunks of p->scratch_frames (one launch pair per chunk)
@@ -196,7 +267,10 @@ extern "C" int vt_scale_plan_create(int sw, int sh, int dw, int dh, int flags, v
     if (!p) return VT_ERR_NOMEM;
     p->sw = sw; p->sh = sh; p->dw = dw; p->dh = dh; p->flags = flags;
     p->csw = (sw + 1) >> 1; p->csh = (sh + 1) >> 1; p->cdw = (dw + 1) >> 1; p->cdh = (dh + 1) >> 1;
-    for (int c = 0; c < 2; c++) { p->hcoef[c] = p->vcoef[c] = nullptr; p->hpos[c] = p->vpos[c] = nullptr; }
+    for (int c = 0; c < 2; c++) {
+        p->hcoef[c] = p->vcoef[c] = nullptr; p->hpos[c] = p->vpos[c] = nullptr;
+        p->hc2[c] = nullptr; p->vc2[c] = nullptr; p->hp2[c] = p->vt2[c] = 0;
+    }
     p->scratch = nullptr;
     int rc = VT_OK;
     for (int c = 0; c < 2 && rc == VT_OK; c++) {
@@ -212,6 +286,25 @@ extern "C" int vt_scale_plan_create(int sw, int sh, int dw, int dh, int flags, v
     p->scratch_frames = (int)std::max<size_t>(1, std::min<size_t>(32, ((size_t)128 << 20) / ((size_t)dw * sh * sizeof(int16_t))));
     if (rc == VT_OK && cudaMalloc((void **)&p->scratch, (size_t)p->scratch_frames * dw * sh * sizeof(int16_t)) != cudaSuccess)
         rc = VT_ERR_NOMEM;
+    for (int c = 0; c < 2 && rc == VT_OK; c++) {               // tables of the fast two-pass kernels
+        const int n = c ? p->cdw : dw, nv = c ? p->cdh : dh, ht = p->htaps[c], vtp = p->vtaps[c];
+        p->hp2[c] = vt::hscale_fast_pairs(ht);
+        p->vt2[c] = vt::pad_vt2(vtp);
+        p->hc2[c] = nullptr;
+        p->vc2[c] = nullptr;
+        if (!p->hp2[c] || !p->vt2[c]) { p->hp2[c] = p->vt2[c] = 0; continue; }
+        std::vector<uint32_t> pairs((size_t)n * p->hp2[c], 0);
+        for (int x = 0; x < n; x++)
+            for (int j = 0; j < ht; j++) {
+                const uint32_t v = (uint16_t)p->h_hcoef[c][(size_t)x * ht + j];
+                pairs[(size_t)x * p->hp2[c] + j / 2] |= (j & 1) ? (v << 16) : v;
+            }
+        std::vector<int16_t> vpad((size_t)nv * p->vt2[c], 0);
+        for (int y = 0; y < nv; y++)
+            for (int j = 0; j < vtp; j++) vpad[(size_t)y * p->vt2[c] + j] = p->h_vcoef[c][(size_t)y * vtp + j];
+        rc = upload(pairs.data(), pairs.size() * 4, (void **)&p->hc2[c]);
+        if (rc == VT_OK) rc = upload(vpad.data(), vpad.size() * 2, (void **)&p->vc2[c]);
+    }
     for (int c = 0; c < 2 && rc == VT_OK; c++) rc = vt::build_pair(p, c);
     if (rc != VT_OK) {
         vt::set_error("vt_scale_plan_create: failed (%d) for %dx%d -> %dx%d flags=0x%x", rc, sw, sh, dw, dh, flags);
@@ -226,6 +319,7 @@ extern "C" void vt_scale_plan_destroy(vt_scale_plan *p) {
     if (!p) return;
     for (int c = 0; c < 2; c++) {
         cudaFree(p->hcoef[c]); cudaFree(p->hpos[c]); cudaFree(p->vcoef[c]); cudaFree(p->vpos[c]);
+        cudaFree(p->hc2[c]); cudaFree(p->vc2[c]);
     }
     vt::free_pair(p);
     cudaFree(p->scratch);
@@ -257,12 +351,17 @@ extern "C" int vt_scale_nv12_to_yuv420p(const vt_scale_plan *p, const uint8_t *s
     // range ...) and the batched two-pass kernels otherwise -- e.g. 1920x1080 -> 854x480: luma streams, the 427-wide
     // chroma planes (odd width: rows are not 2-byte aligned) go through the general kernels.
     const bool fast = aligned && !(force && !strcmp(force, "generic"));
+    // (the fast two-pass kernels need word-aligned surfaces only; `aligned` is stricter)
+    const bool fast2 = fast && !(force && !strcmp(force, "twopass-general"));
+    const uint8_t *uv = src + (size_t)src_pitch * p->sh;
     int rc;
     if (fast && p->pair[0].ok) rc = vt::launch_pair(p, 0, src, src_pitch, src_fs, dst, dst_fs, n_frames, st);
+    else if (fast2 && p->hp2[0]) rc = vt::scale_plane_fast(p, 0, src, src_pitch, src_fs, dst, nullptr, dst_fs, n_frames, st);
     else rc = vt::scale_plane_generic(p, 0, src, src_pitch, 1, 0, dst, p->dw, n_frames, src_fs, dst_fs, st);
     if (rc) return rc;
     if (fast && p->pair[1].ok) return vt::launch_pair(p, 1, src, src_pitch, src_fs, dst, dst_fs, n_frames, st);
-    const uint8_t *uv = src + (size_t)src_pitch * p->sh;
+    if (fast2 && p->hp2[1])
+        return vt::scale_plane_fast(p, 1, uv, src_pitch, src_fs, dst + ysz, dst + ysz + csz, dst_fs, n_frames, st);
     rc = vt::scale_plane_generic(p, 1, uv, src_pitch, 2, 0, dst + ysz, p->cdw, n_frames, src_fs, dst_fs, st);
     if (rc) return rc;
     rc = vt::scale_plane_generic(p, 1, uv, src_pitch, 2, 1, dst + ysz + csz, p->cdw, n_frames, src_fs, dst_fs, st);

@@ -15,6 +15,11 @@ struct vt_scale_plan {
     int32_t *vpos[2];
     int16_t *scratch;  // generic path: scratch_frames x (dw x sh) int16
     int scratch_frames;
+    // fast two-pass kernels (planes the pair kernel does not take): coefficient PAIRS per output sample padded to hp2
+    // pairs, vertical bank padded to vt2 taps; 0 = outside the instantiated range (general kernels)
+    int hp2[2], vt2[2];
+    uint32_t *hc2[2];
+    int16_t *vc2[2];
     // host copies (table construction for the pair kernel)
     std::vector<int16_t> h_hcoef[2], h_vcoef[2];
     std::vector<int32_t> h_hpos[2], h_vpos[2];
