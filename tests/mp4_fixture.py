@@ -1,0 +1,184 @@
+"""Test-side MP4 writer, independent of the product's container code: builds files the product did not write.
+
+Video: H.264 samples given as lists of NAL units (so a sample can carry AUD + SEI + slice), optional `ctts` offsets and
+an edit list; audio: a second trak of 16-bit little-endian PCM (`sowt`), one PCM frame per sample, chunked.  Chunks of
+the two tracks are interleaved in `mdat`, `moov` goes first or last, chunk offsets are `stco` or `co64`.
+"""
+import struct
+
+import numpy as np
+
+
+def box(kind, payload):
+    return struct.pack(">I4s", 8 + len(payload), kind) + payload
+
+
+def full(kind, version, flags, payload):
+    return box(kind, struct.pack(">I", (version << 24) | flags) + payload)
+
+
+MATRIX = struct.pack(">9I", 0x10000, 0, 0, 0, 0x10000, 0, 0, 0, 0x40000000)
+
+
+def _runs(values):
+    out = []
+    for v in values:
+        if out and out[-1][1] == v:
+            out[-1][0] += 1
+        else:
+            out.append([1, v])
+    return out
+
+
+def write_av_mp4(path, *, sps, pps, video_samples, keyframes, width, height, timescale=15360, delta=512,
+                 ctts=None, video_media_time=0, audio_rate=48000, audio_channels=2, audio_pcm=None,
+                 audio_chunk=1024, video_chunk=5, moov_first=False, co64=False, movie_timescale=1000,
+                 audio_empty_edit=0):
+    """video_samples: list of lists of NAL byte strings (no start codes / lengths).  audio_pcm: int16 array
+    [n, channels] or None.  Returns a dict describing what was written (sample byte strings per track)."""
+    vs = [b"".join(struct.pack(">I", len(n)) + n for n in nals) for nals in video_samples]
+    n_v = len(vs)
+    a_bytes = b""
+    n_a = 0
+    bpf = 2 * audio_channels
+    if audio_pcm is not None:
+        a_bytes = np.ascontiguousarray(audio_pcm, "<i2").tobytes()
+        n_a = len(a_bytes) // bpf
+    # chunk plan: video chunks of `video_chunk` samples, audio chunks of `audio_chunk` PCM frames, interleaved by time
+    v_chunks = [(i, min(i + video_chunk, n_v)) for i in range(0, n_v, video_chunk)]
+    a_chunks = [(i, min(i + audio_chunk, n_a)) for i in range(0, n_a, audio_chunk)]
+    order = [(a * delta / timescale, 0, ci) for ci, (a, b) in enumerate(v_chunks)] + \
+            [(a / audio_rate, 1, ci) for ci, (a, b) in enumerate(a_chunks)]
+    order.sort()
+
+    def moov(base):
+        pos = base
+        v_off, a_off = [0] * len(v_chunks), [0] * len(a_chunks)
+        for _t, trk, ci in order:
+            if trk == 0:
+                v_off[ci] = pos
+                pos += sum(len(s) for s in vs[v_chunks[ci][0]:v_chunks[ci][1]])
+            else:
+                a_off[ci] = pos
+                pos += (a_chunks[ci][1] - a_chunks[ci][0]) * bpf
+        v_media = n_v * delta
+        v_movie = (v_media - video_media_time) * movie_timescale // timescale
+        avcc = struct.pack(">BBBBBB", 1, sps[1], sps[2], sps[3], 0xFF, 0xE1) + struct.pack(">H", len(sps)) + sps + \
+            struct.pack(">BH", 1, len(pps)) + pps
+        avc1 = struct.pack(">6xH", 1) + bytes(16) + struct.pack(">HH", width, height) + \
+            struct.pack(">IIIH", 0x00480000, 0x00480000, 0, 1) + bytes(32) + struct.pack(">Hh", 0x18, -1) + \
+            box(b"avcC", avcc) + box(b"pasp", struct.pack(">II", 1, 1))
+        stbl = full(b"stsd", 0, 0, struct.pack(">I", 1) + box(b"avc1", avc1))
+        stbl += full(b"stts", 0, 0, struct.pack(">III", 1, n_v, delta))
+        if ctts is not None:
+            r = _runs(list(ctts))
+            stbl += full(b"ctts", 0, 0, struct.pack(">I", len(r)) + b"".join(struct.pack(">II", c, v) for c, v in r))
+        sync = [i + 1 for i, k in enumerate(keyframes) if k]
+        stbl += full(b"stss", 0, 0, struct.pack(">I", len(sync)) + struct.pack(">%dI" % len(sync), *sync))
+        r = _runs([b - a for a, b in v_chunks])
+        ent, first = b"", 1
+        for c, v in r:
+            ent += struct.pack(">III", first, v, 1)
+            first += c
+        stbl += full(b"stsc", 0, 0, struct.pack(">I", len(r)) + ent)
+        stbl += full(b"stsz", 0, 0, struct.pack(">II", 0, n_v) + b"".join(struct.pack(">I", len(s)) for s in vs))
+        if co64:
+            stbl += full(b"co64", 0, 0, struct.pack(">I", len(v_off)) + struct.pack(">%dQ" % len(v_off), *v_off))
+        else:
+            stbl += full(b"stco", 0, 0, struct.pack(">I", len(v_off)) + struct.pack(">%dI" % len(v_off), *v_off))
+        dinf = box(b"dinf", full(b"dref", 0, 0, struct.pack(">I", 1) + full(b"url ", 0, 1, b"")))
+        minf = box(b"minf", full(b"vmhd", 0, 1, bytes(8)) + dinf + box(b"stbl", stbl))
+        mdia = box(b"mdia", full(b"mdhd", 0, 0, struct.pack(">IIIIHH", 0, 0, timescale, v_media, 0x55C4, 0)) +
+                   full(b"hdlr", 0, 0, struct.pack(">I4s12x", 0, b"vide") + b"FixtureVideo\x00") + minf)
+        edts = box(b"edts", full(b"elst", 0, 0, struct.pack(">IIiI", 1, v_movie, video_media_time, 0x10000)))
+        tkhd = full(b"tkhd", 0, 3, struct.pack(">IIIII", 0, 0, 1, 0, v_movie) + bytes(8) +
+                    struct.pack(">hhhH", 0, 0, 0, 0) + MATRIX + struct.pack(">II", width << 16, height << 16))
+        traks = box(b"trak", tkhd + edts + mdia)
+        movie_dur = v_movie
+        if n_a:
+            a_movie = n_a * movie_timescale // audio_rate
+            sowt = struct.pack(">6xH", 1) + struct.pack(">HHIHHHHI", 0, 0, 0, audio_channels, 16, 0, 0,
+                                                        audio_rate << 16)
+            stbl = full(b"stsd", 0, 0, struct.pack(">I", 1) + box(b"sowt", sowt))
+            stbl += full(b"stts", 0, 0, struct.pack(">III", 1, n_a, 1))
+            r = _runs([b - a for a, b in a_chunks])
+            ent, first = b"", 1
+            for c, v in r:
+                ent += struct.pack(">III", first, v, 1)
+                first += c
+            stbl += full(b"stsc", 0, 0, struct.pack(">I", len(r)) + ent)
+            stbl += full(b"stsz", 0, 0, struct.pack(">II", bpf, n_a))
+            if co64:
+                stbl += full(b"co64", 0, 0, struct.pack(">I", len(a_off)) + struct.pack(">%dQ" % len(a_off), *a_off))
+            else:
+                stbl += full(b"stco", 0, 0, struct.pack(">I", len(a_off)) + struct.pack(">%dI" % len(a_off), *a_off))
+            minf = box(b"minf", full(b"smhd", 0, 0, bytes(4)) + dinf + box(b"stbl", stbl))
+            mdia = box(b"mdia", full(b"mdhd", 0, 0, struct.pack(">IIIIHH", 0, 0, audio_rate, n_a, 0x55C4, 0)) +
+                       full(b"hdlr", 0, 0, struct.pack(">I4s12x", 0, b"soun") + b"FixtureAudio\x00") + minf)
+            ent = b""
+            n_e = 1
+            if audio_empty_edit:
+                ent += struct.pack(">IiI", audio_empty_edit, -1, 0x10000)
+                n_e = 2
+            ent += struct.pack(">IiI", a_movie, 0, 0x10000)
+            edts = box(b"edts", full(b"elst", 0, 0, struct.pack(">I", n_e) + ent))
+            tkhd = full(b"tkhd", 0, 3, struct.pack(">IIIII", 0, 0, 2, 0, a_movie + audio_empty_edit) + bytes(8) +
+                        struct.pack(">hhhH", 0, 1, 0x0100, 0) + MATRIX + struct.pack(">II", 0, 0))
+            traks += box(b"trak", tkhd + edts + mdia)
+            movie_dur = max(movie_dur, a_movie + audio_empty_edit)
+        mvhd = full(b"mvhd", 0, 0, struct.pack(">IIIIIH", 0, 0, movie_timescale, movie_dur, 0x10000, 0x0100) +
+                    bytes(10) + MATRIX + bytes(24) + struct.pack(">I", 3))
+        return box(b"moov", mvhd + traks + box(b"udta", box(b"name", b"fixture")))
+
+    ftyp = box(b"ftyp", b"isom" + struct.pack(">I", 0x200) + b"isomiso2avc1mp41")
+    free = box(b"free", b"")
+    mdat_payload = b""
+    for _t, trk, ci in order:
+        if trk == 0:
+            mdat_payload += b"".join(vs[v_chunks[ci][0]:v_chunks[ci][1]])
+        else:
+            mdat_payload += a_bytes[a_chunks[ci][0] * bpf:a_chunks[ci][1] * bpf]
+    if moov_first:
+        m = moov(0)
+        base = len(ftyp) + len(m) + len(free) + 8
+        data = ftyp + moov(base) + free + box(b"mdat", mdat_payload)
+    else:
+        base = len(ftyp) + len(free) + 8
+        data = ftyp + free + box(b"mdat", mdat_payload) + moov(base)
+    with open(path, "wb") as f:
+        f.write(data)
+    return {"video_samples": vs, "audio_bytes": a_bytes, "audio_frames": n_a, "bytes_per_audio_frame": bpf}
+
+
+def write_fragmented_mp4(path, *, n_frag=4, per_frag=25, timescale=12800, delta=512, with_mehd=False):
+    """A minimal fragmented (moof) file with dummy 16-byte samples: only its timing is meaningful."""
+    total = n_frag * per_frag * delta
+    mp4v = struct.pack(">6xH", 1) + bytes(16) + struct.pack(">HH", 64, 48) + \
+        struct.pack(">IIIH", 0x00480000, 0x00480000, 0, 1) + bytes(32) + struct.pack(">Hh", 0x18, -1)
+    stbl = full(b"stsd", 0, 0, struct.pack(">I", 1) + box(b"mp4v", mp4v)) + full(b"stts", 0, 0, struct.pack(">I", 0)) + \
+        full(b"stsc", 0, 0, struct.pack(">I", 0)) + full(b"stsz", 0, 0, struct.pack(">II", 0, 0)) + \
+        full(b"stco", 0, 0, struct.pack(">I", 0))
+    dinf = box(b"dinf", full(b"dref", 0, 0, struct.pack(">I", 1) + full(b"url ", 0, 1, b"")))
+    minf = box(b"minf", full(b"vmhd", 0, 1, bytes(8)) + dinf + box(b"stbl", stbl))
+    mdia = box(b"mdia", full(b"mdhd", 0, 0, struct.pack(">IIIIHH", 0, 0, timescale, 0, 0x55C4, 0)) +
+               full(b"hdlr", 0, 0, struct.pack(">I4s12x", 0, b"vide") + b"V\x00") + minf)
+    tkhd = full(b"tkhd", 0, 3, struct.pack(">IIIII", 0, 0, 1, 0, 0) + bytes(8) + struct.pack(">hhhH", 0, 0, 0, 0) +
+                MATRIX + struct.pack(">II", 64 << 16, 48 << 16))
+    mvex = full(b"trex", 0, 0, struct.pack(">IIIII", 1, 1, delta, 16, 0))
+    if with_mehd:
+        mvex = full(b"mehd", 0, 0, struct.pack(">I", total * 1000 // timescale)) + mvex
+    mvhd = full(b"mvhd", 0, 0, struct.pack(">IIIIIH", 0, 0, 1000, 0, 0x10000, 0x0100) + bytes(10) + MATRIX +
+                bytes(24) + struct.pack(">I", 2))
+    data = box(b"ftyp", b"iso5" + struct.pack(">I", 0x200) + b"iso5iso6mp41") + \
+        box(b"moov", mvhd + box(b"trak", tkhd + mdia) + box(b"mvex", mvex))
+    for k in range(n_frag):
+        tfhd = full(b"tfhd", 0, 0x020000, struct.pack(">I", 1))
+        tfdt = full(b"tfdt", 0, 0, struct.pack(">I", k * per_frag * delta))
+        trun = full(b"trun", 0, 0x000001, struct.pack(">Ii", per_frag, 0))          # durations from trex
+        if k == n_frag - 1:                                                          # explicit durations in the last
+            trun = full(b"trun", 0, 0x000101, struct.pack(">Ii", per_frag, 0) + struct.pack(">I", delta) * per_frag)
+        moof = box(b"moof", full(b"mfhd", 0, 0, struct.pack(">I", k + 1)) + box(b"traf", tfhd + tfdt + trun))
+        data += moof + box(b"mdat", bytes(16 * per_frag))
+    with open(path, "wb") as f:
+        f.write(data)
+    return total / timescale

@@ -1,7 +1,7 @@
 // Micro-benchmark: issue rates of the integer instructions the scaler is made of, per SM (B200, sm_100a).
 // Each variant runs ILP independent dependency chains per thread for `iters` iterations; the result is
 // warp-instructions per cycle per SM at full occupancy (2048 threads/SM) and at the scaler's occupancy.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/ubench_pipes tools/ubench_pipes.cu
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared -o /tmp/ubench_pipes tools/ubench_pipes.cu
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>

@@ -1,6 +1,6 @@
 // Micro-benchmark: how fast can per-warp TMA rings pull strided strips of a batch of pitch-linear luma planes
 // into shared memory?  (Design input for vt_scale_pair.cu: box width/height, stages, warps per SM.)
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/ubench_tma tools/ubench_tma.cu -lcuda
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared -o /tmp/ubench_tma tools/ubench_tma.cu -lcuda   (build outside the tree; -cudart shared keeps the static runtime out)
 #include <cstdio>
 #include <cstdint>
 #include <cstdlib>

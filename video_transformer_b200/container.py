@@ -17,6 +17,8 @@ from pathlib import Path
 
 import numpy as np
 
+from . import isobmff
+
 
 @dataclass
 class StreamIndex:
@@ -107,29 +109,6 @@ def write_mp4(path: str | Path, *, sps: bytes, pps: bytes, samples, width: int, 
             f.write(s)
 
 
-def _iter_boxes(buf, start: int, end: int):
-    pos = start
-    while pos + 8 <= end:
-        size, kind = struct.unpack_from(">I4s", buf, pos)
-        head = 8
-        if size == 1:
-            size = struct.unpack_from(">Q", buf, pos + 8)[0]
-            head = 16
-        elif size == 0:
-            size = end - pos
-        if size < head or pos + size > end:
-            return
-        yield kind, pos + head, pos + size
-        pos += size
-
-
-def _find(buf, start, end, kind):
-    for k, s, e in _iter_boxes(buf, start, end):
-        if k == kind:
-            return s, e
-    return None
-
-
 def _sps_size(sps: bytes) -> tuple[int, int]:
     """Display size from an SPS NAL via the library's parser (vt_h264_scan on a tiny Annex-B blob)."""
     from . import _lib
@@ -139,126 +118,171 @@ def _sps_size(sps: bytes) -> tuple[int, int]:
     return info.width, info.height
 
 
-def probe_mp4(path: Path) -> StreamIndex | None:
-    data = np.memmap(path, dtype=np.uint8, mode="r")
-    n_bytes = data.size
-    moov = None
-    pos = 0
-    # walk top-level boxes reading only their headers (mdat can be many GB)
-    while pos + 8 <= n_bytes:
-        size, kind = struct.unpack(">I4s", bytes(data[pos:pos + 8]))
-        head = 8
-        if size == 1:
-            size = struct.unpack(">Q", bytes(data[pos + 8:pos + 16]))[0]
-            head = 16
-        elif size == 0:
-            size = n_bytes - pos
-        if size < head:
+def _parse_avcc(stsd: bytes, lo: int, hi: int):
+    """(nal_length_size, first SPS, first PPS) from the avcC box of an avc1/avc3 sample entry, or None."""
+    # VisualSampleEntry: 8 bytes SampleEntry + 70 bytes visual fields, then child boxes
+    at = isobmff.find_box(stsd, lo + 78, hi, b"avcC")
+    if at is None:
+        return None
+    a, e = at
+    if e - a < 7:
+        return None
+    nls = (stsd[a + 4] & 3) + 1
+    n_sps = stsd[a + 5] & 31
+    p = a + 6
+    sps = pps = b""
+    for _ in range(n_sps):
+        if p + 2 > e:
             return None
-        if kind == b"moov":
-            moov = bytes(data[pos + head:pos + size])
+        ln = struct.unpack_from(">H", stsd, p)[0]
+        sps = sps or stsd[p + 2:p + 2 + ln]
+        p += 2 + ln
+    if p >= e:
+        return nls, sps, pps
+    n_pps = stsd[p]
+    p += 1
+    for _ in range(n_pps):
+        if p + 2 > e:
             break
-        pos += size
-    if moov is None:
+        ln = struct.unpack_from(">H", stsd, p)[0]
+        pps = pps or stsd[p + 2:p + 2 + ln]
+        p += 2 + ln
+    return nls, sps, pps
+
+
+def _walk_avc_samples(data: np.ndarray, offsets: np.ndarray, sizes: np.ndarray, nls: int, max_nals: int = 64):
+    """Walk the length-prefixed NAL units of every sample at once (one numpy pass per NAL position).
+
+    Returns (first_vcl_offset uint64 [n], first_vcl_size uint32 [n], vcl_count int32 [n], ok bool [n]);
+    first_vcl_offset points at the NAL header byte of the sample's first slice NAL (types 1..5).  ok is False for
+    samples whose framing runs past the sample or that hold more than max_nals units."""
+    n = offsets.size
+    pos = offsets.astype(np.int64).copy()
+    end = pos + sizes.astype(np.int64)
+    limit = int(data.size)
+    first_off = np.zeros(n, np.uint64)
+    first_size = np.zeros(n, np.uint32)
+    count = np.zeros(n, np.int32)
+    ok = np.ones(n, bool)
+    active = np.nonzero(pos + nls < end)[0]
+    ok[(sizes.astype(np.int64) <= nls)] = False
+    for _ in range(max_nals):
+        if active.size == 0:
+            break
+        p = pos[active]
+        bad = p + nls + 1 > limit
+        if bad.any():
+            ok[active[bad]] = False
+            active, p = active[~bad], p[~bad]
+            if active.size == 0:
+                break
+        ln = np.zeros(active.size, np.int64)
+        for b in range(nls):
+            ln = (ln << 8) | data[p + b].astype(np.int64)
+        hdr = data[p + nls]
+        typ = hdr & 31
+        nal_end = p + nls + ln
+        broken = (ln <= 0) | (nal_end > end[active])
+        ok[active[broken]] = False
+        vcl = (~broken) & (typ >= 1) & (typ <= 5)
+        fresh = vcl & (count[active] == 0)
+        first_off[active[fresh]] = (p[fresh] + nls).astype(np.uint64)
+        first_size[active[fresh]] = ln[fresh].astype(np.uint32)
+        count[active[vcl]] += 1
+        pos[active] = nal_end
+        go = (~broken) & (nal_end + nls < end[active])
+        active = active[go]
+    if active.size:
+        ok[active] = False
+    return first_off, first_size, count, ok
+
+
+def index_from_movie(movie: "isobmff.Movie") -> StreamIndex | None:
+    """StreamIndex of the first video track of a parsed ISO-BMFF movie (any codec).
+
+    For H.264 (`avc1`/`avc3`) the samples' NAL framing is walked so that `nal_offsets` points at each picture's first
+    slice NAL; other codecs get whole-sample offsets and `extra["decodable"] = False` (the pixel pass cannot run, the
+    stream copy can)."""
+    t = movie.video_track()
+    if t is None:
         return None
-    mvhd = _find(moov, 0, len(moov), b"mvhd")
-    if mvhd is None:
-        return None
-    ver = moov[mvhd[0]]
-    if ver == 1:
-        ts, dur = struct.unpack_from(">IQ", moov, mvhd[0] + 20)
+    n = t.n
+    mts = movie.timescale or 1000
+    vals, counts = np.unique(t.deltas, return_counts=True)
+    delta = int(vals[np.argmax(counts)]) if vals.size else 0
+    if delta <= 0 or t.timescale <= 0:
+        delta, fps_n = 1, 0
     else:
-        ts, dur = struct.unpack_from(">II", moov, mvhd[0] + 12)
-    movie_duration = dur / ts if ts else 0.0
-    for kind, s, e in _iter_boxes(moov, 0, len(moov)):
-        if kind != b"trak":
-            continue
-        mdia = _find(moov, s, e, b"mdia")
-        if mdia is None:
-            continue
-        hdlr = _find(moov, mdia[0], mdia[1], b"hdlr")
-        if hdlr is None or moov[hdlr[0] + 8:hdlr[0] + 12] != b"vide":
-            continue
-        mdhd = _find(moov, mdia[0], mdia[1], b"mdhd")
-        mver = moov[mdhd[0]]
-        m_ts = struct.unpack_from(">I", moov, mdhd[0] + (20 if mver == 1 else 12))[0]
-        minf = _find(moov, mdia[0], mdia[1], b"minf")
-        stbl = _find(moov, minf[0], minf[1], b"stbl")
-        stsd = _find(moov, stbl[0], stbl[1], b"stsd")
-        entry = stsd[0] + 8
-        esize, ekind = struct.unpack_from(">I4s", moov, entry)
-        if ekind != b"avc1":
-            return None
-        width, height = struct.unpack_from(">HH", moov, entry + 8 + 24)
-        avcc = _find(moov, entry + 8 + 78, entry + esize, b"avcC")
-        a = avcc[0]
-        nal_len_size = (moov[a + 4] & 3) + 1
-        n_sps = moov[a + 5] & 31
-        p = a + 6
-        sps = b""
-        for _ in range(n_sps):
-            ln = struct.unpack_from(">H", moov, p)[0]
-            sps = sps or moov[p + 2:p + 2 + ln]
-            p += 2 + ln
-        n_pps = moov[p]
-        p += 1
-        pps = b""
-        for _ in range(n_pps):
-            ln = struct.unpack_from(">H", moov, p)[0]
-            pps = pps or moov[p + 2:p + 2 + ln]
-            p += 2 + ln
-        stts = _find(moov, stbl[0], stbl[1], b"stts")
-        n_tt = struct.unpack_from(">I", moov, stts[0] + 4)[0]
-        tt = np.frombuffer(moov, ">u4", 2 * n_tt, stts[0] + 8).reshape(-1, 2)
-        stsz = _find(moov, stbl[0], stbl[1], b"stsz")
-        fixed, n = struct.unpack_from(">II", moov, stsz[0] + 4)
-        sizes = np.full(n, fixed, np.uint64) if fixed else np.frombuffer(moov, ">u4", n, stsz[0] + 12).astype(np.uint64)
-        stsc = _find(moov, stbl[0], stbl[1], b"stsc")
-        n_sc = struct.unpack_from(">I", moov, stsc[0] + 4)[0]
-        sc = np.frombuffer(moov, ">u4", 3 * n_sc, stsc[0] + 8).reshape(-1, 3)
-        co = _find(moov, stbl[0], stbl[1], b"co64")
-        if co is not None:
-            n_co = struct.unpack_from(">I", moov, co[0] + 4)[0]
-            chunk_off = np.frombuffer(moov, ">u8", n_co, co[0] + 8).astype(np.uint64)
-        else:
-            co = _find(moov, stbl[0], stbl[1], b"stco")
-            n_co = struct.unpack_from(">I", moov, co[0] + 4)[0]
-            chunk_off = np.frombuffer(moov, ">u4", n_co, co[0] + 8).astype(np.uint64)
-        # samples per chunk -> sample offsets
-        per_chunk = np.zeros(n_co, np.int64)
-        for i in range(n_sc):
-            first = int(sc[i, 0]) - 1
-            last = int(sc[i + 1, 0]) - 1 if i + 1 < n_sc else n_co
-            per_chunk[first:last] = int(sc[i, 1])
-        offs = np.zeros(n, np.uint64)
-        k = 0
-        for c in range(n_co):
-            o = int(chunk_off[c])
-            for _ in range(int(per_chunk[c])):
-                if k >= n:
-                    break
-                offs[k] = o
-                o += int(sizes[k])
-                k += 1
-        stss = _find(moov, stbl[0], stbl[1], b"stss")
-        key = np.zeros(n, bool)
-        if stss is None:
-            key[:] = True
-        else:
-            n_ss = struct.unpack_from(">I", moov, stss[0] + 4)[0]
-            key[np.frombuffer(moov, ">u4", n_ss, stss[0] + 8).astype(np.int64) - 1] = True
-        if n_tt == 0 or n == 0:
-            return None
-        delta = int(tt[0, 1])
-        g = gcd(int(m_ts), delta) or 1
+        fps_n = t.timescale
+    g = gcd(fps_n, delta) or 1
+    empty_s, media_time = t.edit_shift(mts)
+    first_cts = int(t.cts_off[0]) if t.cts_off is not None else 0
+    cfr = bool(vals.size == 1 and (t.cts_off is None or (t.cts_off == first_cts).all())
+               and empty_s == 0.0 and media_time == first_cts)
+    extra = {"cfr": cfr, "codec": t.codec.decode("latin-1"), "movie": movie, "track_id": t.track_id,
+             "decodable": False, "times": None if cfr else t.pres_times(mts),
+             "tracks": [(x.handler.decode("latin-1"), x.codec.decode("latin-1")) for x in movie.tracks]}
+    sps = pps = b""
+    nal_off, nal_size = t.offsets.astype(np.uint64), np.minimum(t.sizes, 0xFFFFFFFF).astype(np.uint32)
+    width, height = t.width, t.height
+    if t.codec in (b"avc1", b"avc3"):
+        cfg = _parse_avcc(t.stsd, *t.entry_payload)
+        if cfg is not None:
+            nls, sps, pps = cfg
+            extra["nal_length_size"] = nls
+            try:
+                data = np.memmap(movie.path, dtype=np.uint8, mode="r")
+                f_off, f_size, vcl, ok = _walk_avc_samples(data, t.offsets, t.sizes, nls)
+                extra["single_slice"] = bool(ok.all() and (vcl == 1).all())
+                if extra["single_slice"] and sps and pps:
+                    nal_off, nal_size = f_off, f_size
+                    extra["decodable"] = True        # framing is what the PCM-intra decoder indexes; slices are
+                                                     # classified later (classify_pcm), which may still refuse
+            except (OSError, ValueError):
+                extra["single_slice"] = False
+            if sps:
+                try:
+                    width, height = _sps_size(sps)
+                except Exception:  # noqa: BLE001 - no library / odd SPS: keep the sample entry's size
+                    pass
+    return StreamIndex("mp4", Path(movie.path), int(width), int(height), fps_n // g, delta // g, n,
+                       movie.duration_seconds(), nal_off, nal_size, t.sync.copy(), bytes(sps), bytes(pps), extra)
+
+
+def probe_mp4(path: Path) -> StreamIndex | None:
+    try:
+        movie = isobmff.read_movie(path)
+    except (isobmff.BmffError, struct.error, OSError, IndexError):
+        return None
+    return index_from_movie(movie)
+
+
+def classify_pcm(idx: StreamIndex) -> bool:
+    """True when every picture of `idx` is one the PCM-intra decoder (vt_h264_pcm_decode) handles: the result is cached
+    in idx.extra["pcm_intra_only"].  Unknown or unparsable streams are False (fail closed)."""
+    cached = idx.extra.get("pcm_intra_only")
+    if cached is not None:
+        return bool(cached)
+    ok = False
+    if idx.kind == "mp4" and idx.extra.get("decodable") and idx.n_frames:
+        from . import _lib
         try:
-            dw, dh = _sps_size(sps)
-        except Exception:  # noqa: BLE001
-            dw, dh = width, height
-        return StreamIndex("mp4", Path(path), dw, dh, int(m_ts) // g, delta // g, n, movie_duration,
-                           offs + np.uint64(nal_len_size), (sizes - nal_len_size).astype(np.uint32), key, sps, pps,
-                           {"cfr": bool(n_tt == 1), "nal_length_size": nal_len_size})
-    return None
+            host = np.memmap(idx.path, dtype=np.uint8, mode="r")
+            pay = np.zeros(idx.n_frames, np.uint64)
+            sps = np.frombuffer(idx.sps, np.uint8)
+            pps = np.frombuffer(idx.pps, np.uint8)
+            offs = np.ascontiguousarray(idx.nal_offsets, dtype=np.uint64)
+            sizes = np.ascontiguousarray(idx.nal_sizes, dtype=np.uint32)
+            rc = _lib.lib().vt_h264_pcm_layout_ps(host.ctypes.data, host.size, sps.ctypes.data, sps.size,
+                                                  pps.ctypes.data, pps.size, offs.ctypes.data, sizes.ctypes.data,
+                                                  idx.n_frames, pay.ctypes.data)
+            ok = rc == 0
+            if ok:
+                idx.extra["payload"] = pay
+        except (OSError, ValueError):
+            ok = False
+    idx.extra["pcm_intra_only"] = ok
+    return ok
 
 
 def probe_h264(path: Path) -> StreamIndex | None:
@@ -282,17 +306,66 @@ def probe_h264(path: Path) -> StreamIndex | None:
 
 
 def probe(path: Path) -> StreamIndex | None:
-    """Index a media file.  Returns None when the file is not a container this layer reads."""
+    """Index a media file.  Returns None when the file is not a container this layer can cut (ISO-BMFF with a video
+    track, or a raw Annex-B H.264 stream); `container_duration` still knows Matroska/WebM and AVI."""
     path = Path(path)
     if not path.is_file() or path.stat().st_size < 16:
         return None
     with open(path, "rb") as f:
         head = f.read(12)
-    if head[4:8] in (b"ftyp", b"moov", b"free", b"mdat", b"styp"):
+    if head[4:8] in (b"ftyp", b"moov", b"free", b"mdat", b"styp", b"wide", b"skip", b"pnot"):
         return probe_mp4(path)
     if head[:4] == b"\x00\x00\x00\x01" or head[:3] == b"\x00\x00\x01":
         return probe_h264(path)
     return None
+
+
+def container_duration(path: Path) -> float:
+    """Seconds that `ffprobe -show_entries format=duration` prints for the file (0.0 when unknown).
+
+    ISO-BMFF: the movie header (any codec, audio-only files included); Matroska/WebM: Segment Info Duration x
+    TimestampScale; AVI: the longest stream header; raw Annex-B H.264: picture count over the VUI frame rate."""
+    path = Path(path)
+    if not path.is_file() or path.stat().st_size < 12:
+        return 0.0
+    with open(path, "rb") as f:
+        head = f.read(12)
+    if head[:4] == b"\x1a\x45\xdf\xa3":
+        from . import matroska
+        return matroska.duration_seconds(path)
+    if head[:4] == b"RIFF" and head[8:12] == b"AVI ":
+        return _avi_duration(path)
+    if head[4:8] in (b"ftyp", b"moov", b"free", b"mdat", b"styp", b"wide", b"skip", b"pnot"):
+        try:
+            return isobmff.read_movie(path).duration_seconds()
+        except (isobmff.BmffError, struct.error, OSError, IndexError):
+            return 0.0
+    idx = probe(path)
+    return float(idx.duration) if idx is not None else 0.0
+
+
+def _avi_duration(path: Path) -> float:
+    """Longest stream of an AVI file: strh dwLength * dwScale / dwRate (what libavformat's avi demuxer derives),
+    falling back to avih dwTotalFrames * dwMicroSecPerFrame."""
+    with open(path, "rb") as f:
+        buf = f.read(1 << 16)
+    best = 0.0
+    pos = buf.find(b"avih")
+    fallback = 0.0
+    if pos >= 0 and pos + 8 + 20 <= len(buf):
+        us_per_frame, = struct.unpack_from("<I", buf, pos + 8)
+        total, = struct.unpack_from("<I", buf, pos + 8 + 16)
+        fallback = us_per_frame * total / 1e6
+    pos = 0
+    while True:
+        pos = buf.find(b"strh", pos)
+        if pos < 0 or pos + 8 + 36 > len(buf):
+            break
+        scale, rate, _start, length = struct.unpack_from("<IIII", buf, pos + 8 + 20)
+        if rate:
+            best = max(best, length * scale / rate)
+        pos += 4
+    return best if best > 0 else fallback
 
 
 def annexb_to_mp4(src_h264: str | Path, dst_mp4: str | Path) -> StreamIndex:

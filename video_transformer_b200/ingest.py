@@ -77,21 +77,6 @@ class PinnedRing:
             self.callback(chunk, first_picture)
 
 
-class FileSink:
-    """Appends raw planar YUV420P frames to a file (the `segment_XXXX.frames` artefact)."""
-
-    def __init__(self, path):
-        self.f = open(path, "wb")
-        self.frames = 0
-
-    def __call__(self, chunk: torch.Tensor, first_picture: int) -> None:
-        self.f.write(chunk.numpy().tobytes())
-        self.frames += chunk.shape[0]
-
-    def close(self) -> None:
-        self.f.close()
-
-
 class SegmentIngestor:
     """Decode/score/scale engine for one indexed file on one GPU."""
 
@@ -105,7 +90,13 @@ class SegmentIngestor:
         self.payload = np.zeros(n, np.uint64)
         offs = np.ascontiguousarray(index.nal_offsets, dtype=np.uint64)
         sizes = np.ascontiguousarray(index.nal_sizes, dtype=np.uint32)
-        if index.kind == "mp4":
+        if index.kind == "mp4" and not index.extra.get("decodable", True):
+            raise _lib.VtError(_lib.VT_ERR_UNSUPPORTED, "video track (%s) is not H.264 with one slice per sample; "
+                               "the decode front end of this build handles PCM-intra H.264 only"
+                               % index.extra.get("codec"))
+        if index.extra.get("payload") is not None:       # container.classify_pcm already ran the slice classifier
+            self.payload = index.extra["payload"]
+        elif index.kind == "mp4":
             sps = np.frombuffer(index.sps, np.uint8)
             pps = np.frombuffer(index.pps, np.uint8)
             check(L.vt_h264_pcm_layout_ps(self.host.ctypes.data, self.host.size, sps.ctypes.data, sps.size,
@@ -122,6 +113,8 @@ class SegmentIngestor:
         self.surface_bytes = self.rows * self.pitch
         th = self.opts.target_height
         self.rgb_plan = None
+        if self.dev.type == "cuda":
+            torch.cuda.set_device(self.dev)               # plans, tables and per-device kernel attributes live on this device
         if self.opts.output not in ("yuv420p", "rgb24") or self.opts.sample_every < 1:
             raise ValueError("output must be 'yuv420p' or 'rgb24', sample_every >= 1")
         if self.opts.output == "rgb24":
@@ -167,7 +160,7 @@ class SegmentIngestor:
                 "sad_host": torch.empty(B, dtype=torch.int64, pin_memory=True),
                 "hist_host": torch.empty((B, 256), dtype=torch.int32, pin_memory=True),
                 "ev_in": torch.cuda.Event(), "ev_cmp": torch.cuda.Event(), "ev_out": torch.cuda.Event(),
-                "used": False, "pending": None, "kept": None,
+                "used": False, "pending": None, "kept": None, "land": None, "wfut": None,
             })
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
         self.h2d_bytes = 0
@@ -208,8 +201,20 @@ class SegmentIngestor:
         pay[first_idr - b0:] = self.payload[first_idr:b1] - np.uint64(lo)
         return pay, nbytes
 
-    def run(self, first: int, last: int, sink=None, device_sink=None) -> IngestResult:
+    def kept_pictures(self, first: int, last: int) -> int:
+        """How many output frames run(first, last) delivers."""
+        if not self.opts.keep_frames:
+            return 0
+        se = self.opts.sample_every
+        return last - first if se == 1 else len(range(-(-first // se) * se, last, se))
+
+    def run(self, first: int, last: int, sink=None, device_sink=None, landing=None) -> IngestResult:
         """Process pictures [first, last).  Output frames go to sink(chunk_host_tensor, first_picture).
+
+        landing (landing.Landing), if given, is the `.frames` file of the segment: with a registered mapping the copy
+        engine writes every batch's frames straight into the file at their final position (no pinned staging, no
+        host copy, nothing on the drain path); otherwise batches go through the pinned ring to the landing's writer
+        thread.
 
         device_sink(chunk_device_tensor, first_picture), if given, receives every batch's frames ON THE DEVICE instead:
         it is called with the compute stream current, right after the kernels that produce the chunk were enqueued,
@@ -217,6 +222,10 @@ class SegmentIngestor:
         frames are then not copied to the host at all (scores still are).  This is the hand-off for a consumer that
         lives on the GPU (the model's own input pipeline): the D2H copy is what bounds the host-buffer path."""
         n_total = self.idx.n_frames
+        with torch.cuda.device(self.dev):
+            return self._run(first, last, sink, device_sink, landing, n_total)
+
+    def _run(self, first, last, sink, device_sink, landing, n_total) -> IngestResult:
         if not (0 <= first < last <= n_total):
             raise ValueError("picture range [%d,%d) outside the stream (%d pictures)" % (first, last, n_total))
         L = lib()
@@ -238,8 +247,16 @@ class SegmentIngestor:
             s.wait_stream(cur)
         prev_surface = None
         batches = [(b, min(b + B, last)) for b in range(d0, last, B)]
+        fb = self.frame_bytes
+        direct = landing is not None and landing.direct and device_sink is None
+        staged = landing is not None and not direct and device_sink is None
+        landed = 0                           # frames already given a place in the landing file
 
         def drain(slot):
+            w = slot.get("wfut")
+            if w is not None:                # the writer thread still reads this slot's pinned frames
+                w.result()
+                slot["wfut"] = None
             p = slot["pending"]
             if p is None:
                 return
@@ -250,6 +267,10 @@ class SegmentIngestor:
                 k0 = lo - b0
                 sad_all[lo - r0:hi - r0] = slot["sad_host"].numpy()[k0:k0 + hi - lo].view(np.uint64)
                 hist_all[lo - r0:hi - r0] = slot["hist_host"].numpy()[k0:k0 + hi - lo].view(np.uint32)
+            if staged and slot["land"] is not None:
+                at, cnt, row0 = slot["land"]
+                slot["wfut"] = landing.write_chunk(slot["out_host"][row0:row0 + cnt], at * fb)
+                slot["land"] = None
             if sink is not None and self.opts.keep_frames and device_sink is None:
                 keep = slot["kept"]
                 if keep is None:                              # every picture from max(b0, first) on, in place
@@ -344,16 +365,23 @@ class SegmentIngestor:
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(slot["ev_cmp"])
                 lo = max(b0, first)
-                if device_sink is not None:
-                    pass                                  # frames were handed over on the device
-                elif self.opts.keep_frames and kept is not None:
-                    if len(kept):
-                        slot["out_host"][:len(kept)].copy_(slot["out"][:len(kept)], non_blocking=True)
-                        self.d2h_bytes += len(kept) * self.frame_bytes
-                elif self.opts.keep_frames and b1 > lo:
-                    k0 = lo - b0
-                    slot["out_host"][k0:nb].copy_(slot["out"][k0:nb], non_blocking=True)
-                    self.d2h_bytes += (nb - k0) * self.frame_bytes
+                slot["land"] = None
+                cnt = row0 = 0
+                if device_sink is None and self.opts.keep_frames:     # else: scores only / handed over on the device
+                    if kept is not None:
+                        cnt = len(kept)                                # sampled pictures, packed from row 0
+                    elif b1 > lo:
+                        cnt, row0 = b1 - lo, lo - b0
+                if cnt:
+                    if direct:                            # straight into the file's registered mapping
+                        landing.tensor[landed * fb:(landed + cnt) * fb].view(cnt, fb).copy_(
+                            slot["out"][row0:row0 + cnt], non_blocking=True)
+                    else:
+                        slot["out_host"][row0:row0 + cnt].copy_(slot["out"][row0:row0 + cnt], non_blocking=True)
+                        if staged:
+                            slot["land"] = (landed, cnt, row0)
+                    landed += cnt
+                    self.d2h_bytes += cnt * fb
                 slot["sad_host"][:nb].copy_(slot["sad"][:nb], non_blocking=True)
                 slot["hist_host"][:nb].copy_(slot["hist"][:nb], non_blocking=True)
                 self.d2h_bytes += nb * (8 + 1024)
@@ -361,8 +389,12 @@ class SegmentIngestor:
             # drain() synchronises this slot's ev_out before the host issues batch i+2 into the same buffers,
             # which orders every device-side reuse (bitstream, surfaces, output) after the copies that read them
             slot["pending"] = (b0, b1)
+            if staged and i >= 1:
+                drain(self.slots[(i - 1) % self.n_slots])    # hand batch i-1 to the writer while batch i runs
         for slot in sorted(self.slots, key=lambda sl: sl["pending"][0] if sl["pending"] else -1):
             drain(slot)                      # oldest batch first: the sink sees pictures in order
+        for slot in self.slots:
+            drain(slot)                      # writer futures of the last batches
         cur.wait_stream(self.s_cmp)
         cur.wait_stream(self.s_out)
         if r0 == 0:
@@ -373,4 +405,5 @@ class SegmentIngestor:
         cuts = scene.select_cuts(scores, self.opts.scene_threshold, first)
         return IngestResult(first, last, self.out_w, self.out_h, self.frame_bytes, sad_all, hist_all, scores, cuts,
                             {"decoded_from": d0, "batches": len(batches), "h2d_bytes": self.h2d_bytes,
-                             "d2h_bytes": self.d2h_bytes})
+                             "d2h_bytes": self.d2h_bytes, "landed_frames": landed,
+                             "landing": ("direct" if direct else "staged" if staged else None)})

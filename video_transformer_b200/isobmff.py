@@ -1,0 +1,724 @@
+"""Codec-agnostic ISO-BMFF (MP4 / MOV / 3GP / M4A) reader and all-track stream-copy cutter.  Host-side byte I/O.
+
+What it replaces in the reference (both run inside ffmpeg/ffprobe child processes there):
+  * ffprobe `format=duration`                          /root/reference/src/utils/video_utils.py:7-38
+  * `ffmpeg -ss S -i IN -t D -movflags +faststart -c copy OUT`
+                                                       /root/reference/src/utils/video_segmenter.py:118-137
+A stream copy never looks inside a sample: every track is carried with its sample description (`stsd`) copied
+verbatim, its sample tables re-cut to the selected range and its sample bytes copied as they are, so the cut works
+for any codec (H.264 with several NALs per sample, HEVC, MPEG-4 part 2, VP9, AV1, AAC, PCM ...), with B-frame
+reordering (`ctts`), edit lists (`edts/elst`), 32- and 64-bit chunk offsets and any chunking.
+
+Selection rule (derived from the command line above): s = round(start, 3),
+d = round(end - start, 3); the reference track (first video track) keeps the samples whose presentation time is in
+[s, s + d), extended back to the last sync sample at or before the first of them; every other track keeps the
+samples that overlap the reference track's kept time span.  The movie box is written before the media data
+(`+faststart`).  Fragmented files (`moof`) are probed for their duration but not cut.
+"""
+from __future__ import annotations
+
+import os
+import struct
+from dataclasses import dataclass, field
+from pathlib import Path
+
+import numpy as np
+
+CONTAINER_BOXES = (b"moov", b"trak", b"edts", b"mdia", b"minf", b"dinf", b"stbl", b"mvex", b"moof", b"traf")
+
+
+class BmffError(ValueError):
+    pass
+
+
+# ---- box walking ------------------------------------------------------------------------------------------------
+def iter_boxes(buf, start: int, end: int):
+    """Yield (type, payload_start, box_end) for the boxes of buf[start:end]; stops at the first malformed header."""
+    pos = start
+    while pos + 8 <= end:
+        size, kind = struct.unpack_from(">I4s", buf, pos)
+        head = 8
+        if size == 1:
+            if pos + 16 > end:
+                return
+            size = struct.unpack_from(">Q", buf, pos + 8)[0]
+            head = 16
+        elif size == 0:
+            size = end - pos
+        if size < head or pos + size > end:
+            return
+        yield kind, pos + head, pos + size
+        pos += size
+
+
+def find_box(buf, start: int, end: int, kind: bytes):
+    for k, s, e in iter_boxes(buf, start, end):
+        if k == kind:
+            return s, e
+    return None
+
+
+def box(kind: bytes, payload: bytes) -> bytes:
+    n = 8 + len(payload)
+    if n >= 1 << 32:
+        return struct.pack(">I4sQ", 1, kind, n + 8) + payload
+    return struct.pack(">I4s", n, kind) + payload
+
+
+def full_box(kind: bytes, version: int, flags: int, payload: bytes) -> bytes:
+    return box(kind, struct.pack(">I", (version << 24) | flags) + payload)
+
+
+def top_level(path: Path):
+    """[(type, box_start, payload_start, box_end)] of a file's top-level boxes, reading headers only."""
+    out = []
+    size_file = os.path.getsize(path)
+    with open(path, "rb") as f:
+        pos = 0
+        while pos + 8 <= size_file:
+            f.seek(pos)
+            hdr = f.read(16)
+            if len(hdr) < 8:
+                break
+            size, kind = struct.unpack_from(">I4s", hdr, 0)
+            head = 8
+            if size == 1:
+                if len(hdr) < 16:
+                    break
+                size = struct.unpack_from(">Q", hdr, 8)[0]
+                head = 16
+            elif size == 0:
+                size = size_file - pos
+            if size < head:
+                break
+            end = min(pos + size, size_file)      # a truncated last box (e.g. mdat of an interrupted download)
+            out.append((kind, pos, pos + head, end))
+            pos += size
+    return out
+
+
+# ---- data model -------------------------------------------------------------------------------------------------
+@dataclass
+class Track:
+    track_id: int
+    handler: bytes                  # b"vide", b"soun", b"text", ...
+    codec: bytes                    # fourcc of the first sample entry (b"avc1", b"hev1", b"mp4v", b"vp09", b"mp4a", ...)
+    timescale: int
+    media_duration: int             # mdhd duration (media timescale)
+    width: int                      # video: from the sample entry; else 0
+    height: int
+    tkhd: bytes                     # whole box payload incl. version/flags (copied, duration patched on write)
+    mdhd: bytes
+    hdlr: bytes
+    minf_other: bytes               # the boxes of minf except stbl (vmhd/smhd/nmhd, dinf), as whole boxes
+    stsd: bytes                     # whole stsd box, copied verbatim
+    sizes: np.ndarray               # uint64 [n]
+    offsets: np.ndarray             # uint64 [n] file offsets of the samples
+    dts: np.ndarray                 # int64 [n] decode times (media timescale), dts[0] = 0
+    deltas: np.ndarray              # int64 [n] sample durations
+    cts_off: np.ndarray | None      # int64 [n] composition offsets (None without ctts)
+    sync: np.ndarray                # bool [n]
+    has_stss: bool
+    edits: list                     # [(segment_duration (movie ts), media_time, rate_16_16)]
+    entry_payload: tuple = (0, 0)   # (start, end) of the first sample entry's payload inside `stsd`
+
+    @property
+    def n(self) -> int:
+        return int(self.sizes.size)
+
+    def edit_shift(self, movie_timescale: int):
+        """(empty duration in seconds, media_time of the first normal edit)."""
+        empty = 0
+        media_time = 0
+        for seg_dur, mt, _rate in self.edits:
+            if mt < 0:
+                empty += seg_dur
+            else:
+                media_time = mt
+                break
+        return (empty / movie_timescale if movie_timescale else 0.0), media_time
+
+    def pres_times(self, movie_timescale: int) -> np.ndarray:
+        """Presentation time (seconds, float64) of every sample, decode order."""
+        empty_s, mt = self.edit_shift(movie_timescale)
+        cts = self.dts if self.cts_off is None else self.dts + self.cts_off
+        return (cts - mt).astype(np.float64) / float(self.timescale) + empty_s
+
+
+@dataclass
+class Movie:
+    path: Path
+    timescale: int
+    duration: int                   # mvhd duration (movie timescale); 0 when unknown
+    tracks: list = field(default_factory=list)
+    ftyp: bytes = b""               # whole ftyp box (copied)
+    fragmented: bool = False
+    fragment_duration_s: float = 0.0
+
+    def duration_seconds(self) -> float:
+        """What `ffprobe -show_entries format=duration` prints: libavformat keeps the movie header's duration
+        (rescaled to microseconds); a fragmented file without it gets the longest track."""
+        if self.duration and self.timescale:
+            return _us(self.duration, self.timescale)
+        if self.fragment_duration_s > 0:
+            return self.fragment_duration_s
+        best = 0.0
+        for t in self.tracks:
+            if t.timescale and t.n:
+                best = max(best, _us(int(t.dts[-1] + t.deltas[-1]), t.timescale))
+        return best
+
+    def video_track(self):
+        for t in self.tracks:
+            if t.handler == b"vide" and t.n:
+                return t
+        return None
+
+
+def _us(value: int, timescale: int) -> float:
+    """value/timescale rounded to microseconds the way av_rescale does (nearest, half away from zero)."""
+    return ((value * 1000000 + timescale // 2) // timescale) / 1e6
+
+
+# ---- reading ----------------------------------------------------------------------------------------------------
+def _be(buf, dtype, count, offset):
+    if offset + count * np.dtype(dtype).itemsize > len(buf):
+        raise BmffError("table runs past its box")
+    return np.frombuffer(buf, dtype, count, offset)
+
+
+def _parse_track(moov: bytes, s: int, e: int) -> Track | None:
+    tkhd = find_box(moov, s, e, b"tkhd")
+    mdia = find_box(moov, s, e, b"mdia")
+    if tkhd is None or mdia is None:
+        return None
+    tk = moov[tkhd[0]:tkhd[1]]
+    v = tk[0]
+    track_id = struct.unpack_from(">I", tk, 20 if v == 1 else 12)[0]
+    edits = []
+    edts = find_box(moov, s, e, b"edts")
+    if edts:
+        elst = find_box(moov, edts[0], edts[1], b"elst")
+        if elst:
+            ev = moov[elst[0]]
+            n = struct.unpack_from(">I", moov, elst[0] + 4)[0]
+            p = elst[0] + 8
+            for _ in range(n):
+                if ev == 1:
+                    if p + 20 > elst[1]:
+                        break
+                    sd, mt, rate = struct.unpack_from(">Qqi", moov, p)
+                    p += 20
+                else:
+                    if p + 12 > elst[1]:
+                        break
+                    sd, mt, rate = struct.unpack_from(">Iii", moov, p)
+                    p += 12
+                edits.append((int(sd), int(mt), int(rate)))
+    mdhd = find_box(moov, mdia[0], mdia[1], b"mdhd")
+    hdlr = find_box(moov, mdia[0], mdia[1], b"hdlr")
+    minf = find_box(moov, mdia[0], mdia[1], b"minf")
+    if mdhd is None or hdlr is None or minf is None:
+        return None
+    md = moov[mdhd[0]:mdhd[1]]
+    if md[0] == 1:
+        timescale, mdur = struct.unpack_from(">IQ", md, 20)
+    else:
+        timescale, mdur = struct.unpack_from(">II", md, 12)
+    handler = moov[hdlr[0] + 8:hdlr[0] + 12]
+    stbl = find_box(moov, minf[0], minf[1], b"stbl")
+    if stbl is None:
+        return None
+    minf_other = b""
+    for k, bs, be in iter_boxes(moov, minf[0], minf[1]):
+        if k != b"stbl":
+            hdr = 16 if struct.unpack_from(">I", moov, bs - 8)[0] != be - (bs - 8) else 8
+            minf_other += moov[bs - hdr:be]
+    tabs = {k: (bs, be) for k, bs, be in iter_boxes(moov, stbl[0], stbl[1])}
+    if b"stsd" not in tabs:
+        return None
+    sd_s, sd_e = tabs[b"stsd"]
+    stsd_box = box(b"stsd", moov[sd_s:sd_e])
+    codec, width, height = b"", 0, 0
+    entry_payload = (0, 0)
+    if struct.unpack_from(">I", moov, sd_s + 4)[0] >= 1 and sd_s + 16 <= sd_e:
+        esize, codec = struct.unpack_from(">I4s", moov, sd_s + 8)
+        entry_payload = (24, min(16 + esize, len(stsd_box)))
+        if handler == b"vide" and sd_s + 8 + 36 <= sd_e:
+            width, height = struct.unpack_from(">HH", moov, sd_s + 8 + 8 + 24)
+    # sample sizes
+    if b"stsz" in tabs:
+        zs = tabs[b"stsz"][0]
+        fixed, n = struct.unpack_from(">II", moov, zs + 4)
+        sizes = np.full(n, fixed, np.uint64) if fixed else _be(moov, ">u4", n, zs + 12).astype(np.uint64)
+    elif b"stz2" in tabs:
+        zs = tabs[b"stz2"][0]
+        fsize = moov[zs + 7]
+        n = struct.unpack_from(">I", moov, zs + 8)[0]
+        if fsize == 16:
+            sizes = _be(moov, ">u2", n, zs + 12).astype(np.uint64)
+        elif fsize == 8:
+            sizes = _be(moov, np.uint8, n, zs + 12).astype(np.uint64)
+        elif fsize == 4:
+            raw = _be(moov, np.uint8, (n + 1) // 2, zs + 12)
+            sizes = np.stack([raw >> 4, raw & 15], 1).reshape(-1)[:n].astype(np.uint64)
+        else:
+            raise BmffError("stz2 field size %d" % fsize)
+    else:
+        sizes = np.zeros(0, np.uint64)
+    n = int(sizes.size)
+    # chunk offsets
+    if b"co64" in tabs:
+        cs = tabs[b"co64"][0]
+        n_co = struct.unpack_from(">I", moov, cs + 4)[0]
+        chunk_off = _be(moov, ">u8", n_co, cs + 8).astype(np.uint64)
+    elif b"stco" in tabs:
+        cs = tabs[b"stco"][0]
+        n_co = struct.unpack_from(">I", moov, cs + 4)[0]
+        chunk_off = _be(moov, ">u4", n_co, cs + 8).astype(np.uint64)
+    else:
+        chunk_off = np.zeros(0, np.uint64)
+    n_co = int(chunk_off.size)
+    offsets = np.zeros(n, np.uint64)
+    if n and n_co and b"stsc" in tabs:
+        ss = tabs[b"stsc"][0]
+        n_sc = struct.unpack_from(">I", moov, ss + 4)[0]
+        sc = _be(moov, ">u4", 3 * n_sc, ss + 8).reshape(-1, 3).astype(np.int64)
+        if n_sc == 0:
+            raise BmffError("empty stsc")
+        first = np.clip(sc[:, 0] - 1, 0, n_co)
+        nxt = np.append(first[1:], n_co)
+        per_chunk = np.repeat(sc[:, 1], np.maximum(nxt - first, 0))
+        if per_chunk.size < n_co:
+            per_chunk = np.append(per_chunk, np.zeros(n_co - per_chunk.size, np.int64))
+        per_chunk = per_chunk[:n_co]
+        first_sample = np.concatenate(([0], np.cumsum(per_chunk)[:-1]))
+        chunk_of = np.repeat(np.arange(n_co), per_chunk)
+        if chunk_of.size < n:
+            raise BmffError("stsc/stco describe %d samples, stsz has %d" % (chunk_of.size, n))
+        chunk_of = chunk_of[:n]
+        excl = np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(np.uint64)
+        offsets = chunk_off[chunk_of] + excl - excl[first_sample[chunk_of]]
+    elif n:
+        raise BmffError("samples without chunk tables")
+    # decode times
+    deltas = np.zeros(n, np.int64)
+    if b"stts" in tabs and n:
+        ts_ = tabs[b"stts"][0]
+        n_tt = struct.unpack_from(">I", moov, ts_ + 4)[0]
+        tt = _be(moov, ">u4", 2 * n_tt, ts_ + 8).reshape(-1, 2).astype(np.int64)
+        d = np.repeat(tt[:, 1], tt[:, 0])
+        if d.size < n:
+            d = np.append(d, np.full(n - d.size, d[-1] if d.size else 0, np.int64))
+        deltas = d[:n].copy()
+    dts = np.concatenate(([0], np.cumsum(deltas)[:-1])).astype(np.int64) if n else np.zeros(0, np.int64)
+    cts_off = None
+    if b"ctts" in tabs and n:
+        cs = tabs[b"ctts"][0]
+        cv = moov[cs]
+        n_ct = struct.unpack_from(">I", moov, cs + 4)[0]
+        raw = _be(moov, ">u4", 2 * n_ct, cs + 8).reshape(-1, 2)
+        cnt = raw[:, 0].astype(np.int64)
+        # version 1 is signed by definition; writers also put negative values into version 0 (QuickTime), and
+        # libavformat reads the field as signed in both cases
+        off = raw[:, 1].astype(np.uint32).view(np.int32).astype(np.int64)
+        _ = cv
+        c = np.repeat(off, cnt)
+        if c.size < n:
+            c = np.append(c, np.zeros(n - c.size, np.int64))
+        cts_off = c[:n].copy()
+    sync = np.ones(n, bool)
+    has_stss = b"stss" in tabs
+    if has_stss and n:
+        s0 = tabs[b"stss"][0]
+        n_ss = struct.unpack_from(">I", moov, s0 + 4)[0]
+        k = _be(moov, ">u4", n_ss, s0 + 8).astype(np.int64) - 1
+        sync[:] = False
+        sync[k[(k >= 0) & (k < n)]] = True
+    return Track(track_id, handler, codec, int(timescale), int(mdur), int(width), int(height), tk, md,
+                 moov[hdlr[0]:hdlr[1]], minf_other, stsd_box, sizes, offsets, dts, deltas, cts_off, sync, has_stss,
+                 edits, entry_payload)
+
+
+def _fragments_duration(path: Path, tops, moov: bytes, movie: Movie) -> float:
+    """Longest track of a fragmented file: mehd when present, else the sum of the fragments' sample durations."""
+    mvex = find_box(moov, 0, len(moov), b"mvex")
+    defaults = {}
+    if mvex:
+        mehd = find_box(moov, mvex[0], mvex[1], b"mehd")
+        if mehd and movie.timescale:
+            v = moov[mehd[0]]
+            dur = struct.unpack_from(">Q" if v == 1 else ">I", moov, mehd[0] + 4)[0]
+            if dur:
+                return _us(dur, movie.timescale)
+        for k, s, e in iter_boxes(moov, mvex[0], mvex[1]):
+            if k == b"trex":
+                tid, _desc, ddur = struct.unpack_from(">III", moov, s + 4)
+                defaults[tid] = ddur
+    scales = {t.track_id: t.timescale for t in movie.tracks}
+    total = {}
+    with open(path, "rb") as f:
+        for kind, b0, p0, b1 in tops:
+            if kind != b"moof":
+                continue
+            f.seek(p0)
+            moof = f.read(b1 - p0)
+            for k, s, e in iter_boxes(moof, 0, len(moof)):
+                if k != b"traf":
+                    continue
+                tfhd = find_box(moof, s, e, b"tfhd")
+                if not tfhd:
+                    continue
+                fl = struct.unpack_from(">I", moof, tfhd[0])[0] & 0xFFFFFF
+                tid = struct.unpack_from(">I", moof, tfhd[0] + 4)[0]
+                p = tfhd[0] + 8 + (8 if fl & 1 else 0) + (4 if fl & 2 else 0)
+                ddur = defaults.get(tid, 0)
+                if fl & 8:
+                    ddur = struct.unpack_from(">I", moof, p)[0]
+                for k2, s2, e2 in iter_boxes(moof, s, e):
+                    if k2 != b"trun":
+                        continue
+                    tf = struct.unpack_from(">I", moof, s2)[0] & 0xFFFFFF
+                    cnt = struct.unpack_from(">I", moof, s2 + 4)[0]
+                    q = s2 + 8 + (4 if tf & 1 else 0) + (4 if tf & 4 else 0)
+                    stride = 4 * (bool(tf & 0x100) + bool(tf & 0x200) + bool(tf & 0x400) + bool(tf & 0x800))
+                    if tf & 0x100:
+                        d = int(_be(moof, ">u4", cnt * stride // 4, q).reshape(cnt, -1)[:, 0].astype(np.int64).sum())
+                    else:
+                        d = cnt * ddur
+                    total[tid] = total.get(tid, 0) + d
+    best = 0.0
+    for tid, d in total.items():
+        if scales.get(tid):
+            best = max(best, _us(d, scales[tid]))
+    return best
+
+
+def read_movie(path: str | Path) -> Movie:
+    """Parse the movie box of an ISO-BMFF file.  Raises BmffError when there is none."""
+    path = Path(path)
+    tops = top_level(path)
+    moov_at = next(((p0, b1) for kind, b0, p0, b1 in tops if kind == b"moov"), None)
+    if moov_at is None:
+        raise BmffError("no moov box")
+    ftyp = b""
+    with open(path, "rb") as f:
+        for kind, b0, p0, b1 in tops:
+            if kind == b"ftyp" and b1 - b0 <= 4096:
+                f.seek(b0)
+                ftyp = f.read(b1 - b0)
+                break
+        f.seek(moov_at[0])
+        moov = f.read(moov_at[1] - moov_at[0])
+    mvhd = find_box(moov, 0, len(moov), b"mvhd")
+    if mvhd is None:
+        raise BmffError("no mvhd box")
+    if moov[mvhd[0]] == 1:
+        ts, dur = struct.unpack_from(">IQ", moov, mvhd[0] + 20)
+    else:
+        ts, dur = struct.unpack_from(">II", moov, mvhd[0] + 12)
+        if dur == 0xFFFFFFFF:
+            dur = 0
+    movie = Movie(path, int(ts), int(dur), ftyp=ftyp)
+    for kind, s, e in iter_boxes(moov, 0, len(moov)):
+        if kind == b"trak":
+            t = _parse_track(moov, s, e)
+            if t is not None:
+                movie.tracks.append(t)
+    movie.fragmented = any(kind == b"moof" for kind, *_ in tops)
+    if movie.fragmented and not movie.duration:
+        movie.fragment_duration_s = _fragments_duration(path, tops, moov, movie)
+    return movie
+
+
+# ---- cutting ----------------------------------------------------------------------------------------------------
+@dataclass
+class CutResult:
+    first: int                      # reference-track sample range [first, last) that was copied (decode order)
+    last: int
+    first_accurate: int             # first sample whose presentation time is >= the requested start
+    tracks: int                     # tracks written
+    bytes_copied: int
+    presentation_start: float       # seconds, on the source timeline, where the output's presentation begins
+
+
+def select_reference_range(pres: np.ndarray, sync: np.ndarray, start: float, end: float, stream_copy: bool):
+    """(first, last, first_accurate) over decode-order samples, or None when the window holds no sample."""
+    s = float("%.3f" % start)
+    d = float("%.3f" % (end - start))
+    if d <= 0 or pres.size == 0:
+        return None
+    keep = np.nonzero((pres >= s) & (pres < s + d))[0]
+    if keep.size == 0:
+        return None
+    first_acc, last = int(keep[0]), int(keep[-1]) + 1
+    first = first_acc
+    if stream_copy:
+        k = np.nonzero(sync[:first_acc + 1])[0]
+        if k.size:
+            first = int(k[-1])
+    return first, last, first_acc
+
+
+def _runs(values: np.ndarray):
+    """Run-length encode an int64 array -> (counts, values)."""
+    if values.size == 0:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    brk = np.nonzero(np.diff(values))[0] + 1
+    starts = np.concatenate(([0], brk))
+    counts = np.diff(np.concatenate((starts, [values.size])))
+    return counts.astype(np.int64), values[starts].astype(np.int64)
+
+
+def _patch_duration(payload: bytes, at_v0: int, at_v1: int, value: int) -> bytes:
+    """Return a header payload (tkhd/mdhd/mvhd, incl. version+flags) with its duration field replaced."""
+    b = bytearray(payload)
+    if b[0] == 1:
+        struct.pack_into(">Q", b, at_v1, value)
+    else:
+        struct.pack_into(">I", b, at_v0, min(value, 0xFFFFFFFF))
+    return bytes(b)
+
+
+def cut_movie(movie: Movie, start: float, end: float, dst: str | Path, *, stream_copy: bool = True,
+              accurate_presentation: bool = False, selection: tuple | None = None,
+              first_sample: bytes | None = None, chunk_seconds: float = 0.5,
+              chunk_bytes: int = 4 << 20) -> CutResult | None:
+    """Write the samples of [start, end) of every track of `movie` into a new faststart MP4 at `dst`.
+
+    stream_copy            : extend the reference track back to its last sync sample (what `-c copy` does).
+    accurate_presentation  : keep the keyframe lead-in in the file but start the PRESENTATION at the first sample
+                             at or after `start` through the edit list (frame-accurate for any player that honours
+                             edit lists, without re-encoding).
+    selection              : (first, last, first_accurate) of the reference track when the caller already chose the
+                             range (select_reference_range on its own time table).
+    first_sample           : replacement bytes for the first copied sample of the reference track, which is then
+                             marked as a sync sample (the PCM-intra frame-accurate path: a picture that repeats its
+                             IDR is re-expressed by that IDR's sample).
+    Returns None when the window selects nothing; raises BmffError/OSError on malformed input.
+    """
+    if movie.fragmented and not any(t.n for t in movie.tracks):
+        raise BmffError("fragmented MP4 (moof): stream copy not supported")
+    ref = movie.video_track() or next((t for t in movie.tracks if t.n), None)
+    if ref is None:
+        return None
+    mts = movie.timescale or 1000
+    pres = ref.pres_times(mts)
+    if selection is not None:
+        first, last, first_acc = (int(v) for v in selection)
+        if not (0 <= first <= first_acc < last <= ref.n):
+            raise BmffError("selection outside the reference track")
+    else:
+        sel = select_reference_range(pres, ref.sync, start, end, stream_copy)
+        if sel is None:
+            return None
+        first, last, first_acc = sel
+    span = pres[first:last]
+    t_lo = float(span.min())
+    dur_ref = ref.deltas[first:last].astype(np.float64) / ref.timescale
+    t_hi = float((span + dur_ref).max())
+    t_present = float(pres[first_acc]) if accurate_presentation else t_lo
+
+    plans = []
+    for t in movie.tracks:
+        if not t.n:
+            continue
+        if t is ref:
+            a, b = first, last
+        else:
+            p = t.pres_times(mts)
+            e = p + t.deltas.astype(np.float64) / t.timescale
+            idx = np.nonzero((e > t_lo) & (p < t_hi))[0]
+            if idx.size == 0:
+                continue
+            a, b = int(idx[0]), int(idx[-1]) + 1
+            if t.has_stss:                      # non-reference tracks with sync tables also start on a sync sample
+                k = np.nonzero(t.sync[:a + 1])[0]
+                if k.size:
+                    a = int(k[-1])
+        sizes = t.sizes[a:b].copy()
+        override = None
+        if t is ref and first_sample is not None:
+            override = first_sample
+            sizes[0] = len(override)
+        deltas = t.deltas[a:b]
+        cts_off = None if t.cts_off is None else t.cts_off[a:b]
+        sync = t.sync[a:b].copy()
+        if override is not None:
+            sync[0] = True
+        # edit list of the cut: presentation begins at t_present on the source timeline
+        _empty_s, mt_src = t.edit_shift(mts)
+        tp = t.pres_times(mts)[a:b]
+        cts_rel = (t.dts[a:b] - t.dts[a]) + (cts_off if cts_off is not None else 0)   # media time, new origin
+        first_pres = float(tp.min())
+        min_cts = int(np.min(cts_rel))
+        if first_pres >= t_present:
+            empty_ticks = int(round((first_pres - t_present) * mts))
+            media_time = min_cts
+        else:                                    # this track starts before the presentation start: skip into it
+            empty_ticks = 0
+            media_time = min_cts + int(round((t_present - first_pres) * t.timescale))
+        media_dur = int(deltas.sum())
+        pres_ticks = max(0, (media_dur - (media_time - min_cts)) * mts + t.timescale - 1) // t.timescale
+        # chunking: consecutive samples up to chunk_seconds / chunk_bytes
+        rel = (t.dts[a:b] - t.dts[a]).astype(np.float64) / t.timescale
+        n = b - a
+        bucket_t = np.floor(rel / chunk_seconds).astype(np.int64)
+        csum = np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(np.int64)
+        bucket_b = csum // chunk_bytes
+        key = bucket_t * (1 << 20) + (bucket_b - bucket_b[np.searchsorted(bucket_t, bucket_t, side="left")])
+        brk = np.nonzero(np.diff(key))[0] + 1
+        chunk_first = np.concatenate(([0], brk)).astype(np.int64)
+        chunk_count = np.diff(np.concatenate((chunk_first, [n]))).astype(np.int64)
+        chunk_bytes_ = np.add.reduceat(sizes.astype(np.int64), chunk_first)
+        chunk_time = tp[chunk_first] if cts_off is None else (t.dts[a:b][chunk_first] - mt_src) / t.timescale
+        plans.append({"t": t, "a": a, "b": b, "sizes": sizes, "deltas": deltas, "cts_off": cts_off, "sync": sync,
+                      "override": override, "empty_ticks": empty_ticks, "media_time": media_time,
+                      "media_dur": media_dur, "pres_ticks": pres_ticks + empty_ticks, "chunk_first": chunk_first,
+                      "chunk_count": chunk_count, "chunk_bytes": chunk_bytes_,
+                      "chunk_time": np.asarray(chunk_time, np.float64)})
+    if not plans:
+        return None
+
+    # interleave: chunks of all tracks ordered by time (stable by track order)
+    order = []
+    for ti, p in enumerate(plans):
+        for ci in range(p["chunk_first"].size):
+            order.append((float(p["chunk_time"][ci]), ti, ci))
+    order.sort()
+    total_bytes = int(sum(int(p["chunk_bytes"].sum()) for p in plans))
+
+    def build_moov(base: int, wide: bool) -> bytes:
+        pos = base
+        offs = [np.zeros(p["chunk_first"].size, np.uint64) for p in plans]
+        for _t, ti, ci in order:
+            offs[ti][ci] = pos
+            pos += int(plans[ti]["chunk_bytes"][ci])
+        traks = b""
+        movie_dur = 0
+        for ti, p in enumerate(plans):
+            t = p["t"]
+            n = p["b"] - p["a"]
+            c, v = _runs(p["deltas"])
+            stts = full_box(b"stts", 0, 0, struct.pack(">I", c.size) +
+                            np.stack([c, v], 1).astype(">u4").tobytes())
+            ctts = b""
+            if p["cts_off"] is not None:
+                c, v = _runs(p["cts_off"])
+                ver = 1 if (v < 0).any() else 0
+                ctts = full_box(b"ctts", ver, 0, struct.pack(">I", c.size) +
+                                np.stack([c, v & 0xFFFFFFFF], 1).astype(">u4").tobytes())
+            stss = b""
+            if t.has_stss or not p["sync"].all():
+                k = np.nonzero(p["sync"])[0] + 1
+                stss = full_box(b"stss", 0, 0, struct.pack(">I", k.size) + k.astype(">u4").tobytes())
+            c, v = _runs(p["chunk_count"])
+            firsts = np.concatenate(([0], np.cumsum(c)[:-1])) + 1
+            stsc = full_box(b"stsc", 0, 0, struct.pack(">I", c.size) +
+                            np.stack([firsts, v, np.ones_like(v)], 1).astype(">u4").tobytes())
+            sz = p["sizes"]
+            if n and (sz == sz[0]).all():
+                stsz = full_box(b"stsz", 0, 0, struct.pack(">II", int(sz[0]), n))
+            else:
+                stsz = full_box(b"stsz", 0, 0, struct.pack(">II", 0, n) + sz.astype(">u4").tobytes())
+            if wide:
+                stco = full_box(b"co64", 0, 0, struct.pack(">I", offs[ti].size) + offs[ti].astype(">u8").tobytes())
+            else:
+                stco = full_box(b"stco", 0, 0, struct.pack(">I", offs[ti].size) + offs[ti].astype(">u4").tobytes())
+            stbl = box(b"stbl", t.stsd + stts + ctts + stss + stsc + stsz + stco)
+            minf = box(b"minf", t.minf_other + stbl)
+            mdhd = box(b"mdhd", _patch_duration(t.mdhd, 16, 24, p["media_dur"]))
+            mdia = box(b"mdia", mdhd + box(b"hdlr", t.hdlr) + minf)
+            entries = b""
+            n_e = 0
+            shown = p["pres_ticks"] - p["empty_ticks"]
+            if p["empty_ticks"] > 0:
+                entries += struct.pack(">Qqi", p["empty_ticks"], -1, 0x10000)
+                n_e += 1
+            entries += struct.pack(">Qqi", shown, p["media_time"], 0x10000)
+            n_e += 1
+            edts = box(b"edts", full_box(b"elst", 1, 0, struct.pack(">I", n_e) + entries))
+            tkhd = box(b"tkhd", _patch_duration(t.tkhd, 20, 28, p["pres_ticks"]))
+            traks += box(b"trak", tkhd + edts + mdia)
+            movie_dur = max(movie_dur, p["pres_ticks"])
+        next_id = max(p["t"].track_id for p in plans) + 1
+        mvhd = full_box(b"mvhd", 0, 0, struct.pack(">IIIIIH", 0, 0, mts, min(movie_dur, 0xFFFFFFFF), 0x10000, 0x0100) +
+                        bytes(10) + struct.pack(">9I", 0x10000, 0, 0, 0, 0x10000, 0, 0, 0, 0x40000000) + bytes(24) +
+                        struct.pack(">I", next_id))
+        return box(b"moov", mvhd + traks)
+
+    ftyp = movie.ftyp or box(b"ftyp", b"isom" + struct.pack(">I", 0x200) + b"isomiso2mp41")
+    wide = False
+    moov = build_moov(0, wide)
+    base = len(ftyp) + len(moov) + 16
+    if base + total_bytes >= (1 << 32) - 1:
+        wide = True
+        moov = build_moov(0, wide)
+        base = len(ftyp) + len(moov) + 16
+    moov = build_moov(base, wide)
+
+    # source byte ranges in output order, adjacent ranges merged
+    src_lo, src_len, over_at = [], [], {}
+    for _t, ti, ci in order:
+        p = plans[ti]
+        t = p["t"]
+        f0 = p["a"] + int(p["chunk_first"][ci])
+        cnt = int(p["chunk_count"][ci])
+        o = t.offsets[f0:f0 + cnt].astype(np.int64)
+        z = t.sizes[f0:f0 + cnt].astype(np.int64)
+        if p["override"] is not None and ci == 0:
+            over_at[len(src_lo)] = p["override"]
+            src_lo.append(-1)
+            src_len.append(len(p["override"]))
+            o, z = o[1:], z[1:]
+            if o.size == 0:
+                continue
+        brk = np.nonzero(o[1:] != o[:-1] + z[:-1])[0] + 1
+        st = np.concatenate(([0], brk))
+        en = np.concatenate((brk, [o.size]))
+        zc = np.concatenate(([0], np.cumsum(z)))
+        for s_, e_ in zip(st, en):
+            lo, ln = int(o[s_]), int(zc[e_] - zc[s_])
+            if src_lo and src_lo[-1] >= 0 and src_lo[-1] + src_len[-1] == lo:
+                src_len[-1] += ln
+            else:
+                src_lo.append(lo)
+                src_len.append(ln)
+    dst = Path(dst)
+    src_size = os.path.getsize(movie.path)
+    with open(movie.path, "rb") as fin, open(dst, "wb") as fout:
+        fout.write(ftyp)
+        fout.write(moov)
+        fout.write(struct.pack(">I4sQ", 1, b"mdat", 16 + total_bytes))
+        fout.flush()
+        in_fd, out_fd = fin.fileno(), fout.fileno()
+        for i, (lo, ln) in enumerate(zip(src_lo, src_len)):
+            if lo < 0:
+                os.write(out_fd, over_at[i])
+                continue
+            if lo + ln > src_size:
+                raise BmffError("sample data past the end of the file (truncated source)")
+            _copy_range(in_fd, out_fd, lo, ln)
+    return CutResult(first, last, first_acc, len(plans), total_bytes, t_present)
+
+
+def _copy_range(in_fd: int, out_fd: int, offset: int, length: int) -> None:
+    """Copy bytes between files inside the kernel (sendfile), falling back to pread/write."""
+    done = 0
+    use_sendfile = True
+    while done < length:
+        if use_sendfile:
+            try:
+                k = os.sendfile(out_fd, in_fd, offset + done, min(length - done, 1 << 30))
+            except OSError:
+                use_sendfile = False
+                continue
+            if k == 0:
+                raise BmffError("unexpected end of source while copying samples")
+        else:
+            buf = os.pread(in_fd, min(length - done, 8 << 20), offset + done)
+            if not buf:
+                raise BmffError("unexpected end of source while copying samples")
+            os.write(out_fd, buf)
+            k = len(buf)
+        done += k

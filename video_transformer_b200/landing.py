@@ -1,0 +1,217 @@
+"""K5: where a segment's frame buffers land -- directly in the `.frames` file, with no host copy.
+
+The artefact of extract_segment (/root/reference/src/utils/video_segmenter.py:86-154 leaves ONE file per call) gets a
+sibling `<segment>.frames`.  Instead of copying device frames into a pinned staging buffer and then `write()`-ing
+them (two passes over host memory, the second one in the file system), the file itself is the copy target:
+
+    create the file at its final size -> mmap(MAP_SHARED) -> cudaHostRegister(mapping) -> cudaMemcpyAsync D2H into it
+
+Registering is the expensive part (measured on the B200 box, tmpfs: allocate 13.6 GB/s, register 4.3 GB/s, D2H into
+the registered mapping 50-56 GB/s = the PCIe ceiling; tools/landing_probe.py), so registered files are RECYCLED:
+each lives under a hidden arena directory beside the outputs and the `.frames` name is a hard link to it.  When the
+consumer deletes (or this module replaces) the `.frames` name, the arena file's link count drops back to 1 and the
+next segment of the same size lands in the already-registered pages.  File systems whose mappings cannot be
+registered (anything but tmpfs here) get the classic path: pinned ring -> a writer thread -> pwrite.
+"""
+from __future__ import annotations
+
+import atexit
+import ctypes
+import mmap
+import os
+import threading
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ARENA_DIR = ".vt_landing"
+_libc = ctypes.CDLL("libc.so.6", use_errno=True)
+_libc.posix_fallocate.argtypes = [ctypes.c_int, ctypes.c_long, ctypes.c_long]
+_lock = threading.Lock()
+_slots: list["_Slot"] = []
+_seq = 0
+
+
+class _Slot:
+    """One registered file mapping."""
+
+    def __init__(self, path: Path, nbytes: int):
+        self.path, self.nbytes = path, nbytes
+        self.fd = os.open(path, os.O_RDWR | os.O_CREAT | os.O_EXCL, 0o644)
+        try:
+            rc = _libc.posix_fallocate(self.fd, 0, nbytes)
+            if rc != 0:
+                raise OSError(rc, "posix_fallocate(%d bytes) failed" % nbytes)
+            self.mm = mmap.mmap(self.fd, nbytes, flags=mmap.MAP_SHARED, prot=mmap.PROT_READ | mmap.PROT_WRITE)
+        except Exception:
+            os.close(self.fd)
+            os.unlink(path)
+            raise
+        self.array = np.frombuffer(self.mm, dtype=np.uint8)
+        self.base = self.array.ctypes.data
+        self.registered = int(torch.cuda.cudart().cudaHostRegister(self.base, nbytes, 0)) == 0
+        self.tensor = torch.from_numpy(self.array)
+        self.stamp = 0
+
+    def free(self) -> bool:
+        try:
+            return os.fstat(self.fd).st_nlink <= 1 and os.path.exists(self.path)
+        except OSError:
+            return False
+
+    def destroy(self) -> None:
+        if self.registered:
+            try:
+                torch.cuda.cudart().cudaHostUnregister(self.base)
+            except Exception:  # noqa: BLE001 - interpreter shutdown
+                pass
+            self.registered = False
+        self.tensor = None
+        self.array = None
+        try:
+            self.mm.close()
+        except (BufferError, ValueError):
+            pass
+        try:
+            os.close(self.fd)
+        except OSError:
+            pass
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+
+
+class Landing:
+    """A `.frames` file being filled.  `tensor` (uint8, [nbytes]) is host memory the copy engine writes into when
+    `direct` is True; otherwise frames arrive through write_chunk() from a pinned staging buffer."""
+
+    def __init__(self, path: Path, nbytes: int, slot: _Slot | None, recycled: bool):
+        self.path, self.nbytes = path, nbytes
+        self.slot = slot
+        self.direct = slot is not None
+        self.recycled = recycled
+        self.tensor = slot.tensor[:nbytes] if slot is not None else None
+        self._fd = None
+        self._writer = None
+        if slot is None:
+            self._fd = os.open(path, os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o644)
+            from concurrent.futures import ThreadPoolExecutor
+            self._writer = ThreadPoolExecutor(max_workers=1)
+            self._pending = []
+
+    # -- staged path -----------------------------------------------------------------------------------------
+    def write_chunk(self, chunk: torch.Tensor, byte_offset: int):
+        """Queue `chunk` (pinned host memory, contiguous) for pwrite at byte_offset; returns a future the caller waits on
+        before reusing the staging buffer."""
+        mv = memoryview(chunk.numpy()).cast("B")
+        fut = self._writer.submit(_pwrite_all, self._fd, mv, byte_offset)
+        self._pending.append(fut)
+        return fut
+
+    def finish(self, nbytes_used: int | None = None) -> None:
+        """All copies into the landing have completed (the caller synchronised its stream)."""
+        if self._writer is not None:
+            for f in self._pending:
+                f.result()
+            self._writer.shutdown()
+            if nbytes_used is not None:
+                os.ftruncate(self._fd, nbytes_used)
+            os.close(self._fd)
+            self._fd = None
+
+    def abort(self) -> None:
+        if self._writer is not None:
+            self._writer.shutdown(wait=True)
+            if self._fd is not None:
+                os.close(self._fd)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+
+
+def _pwrite_all(fd: int, mv: memoryview, offset: int) -> None:
+    done = 0
+    while done < len(mv):
+        done += os.pwrite(fd, mv[done:], offset + done)
+
+
+def _arena_cap() -> int:
+    return int(float(os.environ.get("VT_LANDING_CAP_GB", "64")) * (1 << 30))
+
+
+def acquire(path: str | Path, nbytes: int, direct: bool | None = None) -> Landing:
+    """Prepare `path` (a `.frames` file of exactly nbytes) as a D2H copy target.
+
+    direct=None: try the registered-mapping path and fall back to the staged writer when the file system's mappings
+    cannot be registered; True: registered mapping or OSError; False: staged writer."""
+    global _seq
+    path = Path(path)
+    path.parent.mkdir(parents=True, exist_ok=True)
+    if nbytes <= 0:
+        raise ValueError("landing size must be positive")
+    if direct is None:
+        direct = os.environ.get("VT_LANDING", "direct") != "staged"
+    with _lock:
+        if path.exists() or path.is_symlink():
+            path.unlink()                       # a replaced artefact frees its arena file for the search below
+        if direct:
+            arena = path.parent / ARENA_DIR
+            slot = None
+            for s in _slots:
+                if s.nbytes == nbytes and s.path.parent == arena and s.free():
+                    slot = s
+                    break
+            recycled = slot is not None
+            if slot is None:
+                # drop free files of other sizes when the arena is over its cap
+                used = sum(s.nbytes for s in _slots)
+                for s in sorted([s for s in _slots if s.free()], key=lambda s: s.stamp):
+                    if used + nbytes <= _arena_cap():
+                        break
+                    s.destroy()
+                    _slots.remove(s)
+                    used -= s.nbytes
+                try:
+                    arena.mkdir(exist_ok=True)
+                    _seq += 1
+                    slot = _Slot(arena / ("landing_%d_%d.bin" % (os.getpid(), _seq)), nbytes)
+                    if not slot.registered:
+                        slot.destroy()
+                        slot = None
+                except OSError:
+                    slot = None
+            if slot is not None:
+                try:
+                    os.link(slot.path, path)
+                except OSError:
+                    slot.destroy()
+                    slot = None
+                else:
+                    _seq += 1
+                    slot.stamp = _seq
+                    if not recycled:
+                        _slots.append(slot)
+                    return Landing(path, nbytes, slot, recycled)
+            if direct is True and os.environ.get("VT_LANDING") == "direct-only":
+                raise OSError("cannot register a mapping of %s" % path)
+        return Landing(path, nbytes, None, False)
+
+
+def stats() -> dict:
+    with _lock:
+        return {"files": len(_slots), "bytes": sum(s.nbytes for s in _slots),
+                "free": sum(1 for s in _slots if s.free())}
+
+
+def release_all() -> None:
+    """Unregister and remove every arena file (the `.frames` hard links stay)."""
+    with _lock:
+        for s in _slots:
+            s.destroy()
+        _slots.clear()
+
+
+atexit.register(release_all)

@@ -114,16 +114,30 @@ def snap_to_keyframe(video_path: str | Path, timestamp: float) -> float:
 
 
 def keyframe_at_or_before(video_path: str | Path, timestamp: float) -> float:
-    """Presentation time of the last keyframe at or before `timestamp` (what `-ss T -i IN -c copy` starts at)."""
-    from . import container
+    """Presentation time of the last keyframe at or before `timestamp` (what `-ss T -i IN -c copy` starts at).
+    This is the GOP-aligned answer for the reference's stub hook (src/utils/video_segmenter.py:157-159)."""
     t = max(0.0, float(timestamp))
-    idx = container.probe(Path(video_path))
+    idx = _probe_cached(Path(video_path))
     if idx is None or not idx.n_frames:
         return t
-    k = np.nonzero(idx.keyframe)[0]
-    times = k.astype(np.float64) * float(idx.fps_den) / float(idx.fps_num)
-    ok = times[times <= t]
-    return float(ok[-1]) if ok.size else 0.0
+    times = _picture_times(idx)
+    k = _keyframe_index_at_or_before(idx, times, t)
+    return float(times[k]) if k is not None else 0.0
+
+
+def _picture_times(idx) -> np.ndarray:
+    """Presentation time of every picture (decode order): k*den/num for plain constant-rate streams (the K4
+    definition, one multiply then one divide), the container's own table otherwise."""
+    from . import scene
+    tt = idx.extra.get("times")
+    if tt is not None:
+        return np.asarray(tt, np.float64)
+    return scene.pts(np.arange(idx.n_frames), idx.fps_num, idx.fps_den)
+
+
+def _keyframe_index_at_or_before(idx, times: np.ndarray, t: float):
+    ok = np.nonzero(idx.keyframe & (times <= t))[0]
+    return int(ok[-1]) if ok.size else None
 
 
 # ---- cutting ------------------------------------------------------------------------------------------------
@@ -155,64 +169,180 @@ def _sidecar_path(mp4: Path) -> Path:
     return mp4.with_suffix(".json")
 
 
+_INDEX_CACHE: dict = {}
+_ENGINE_CACHE: dict = {}
+
+
+def _file_key(path: Path):
+    st = path.stat()
+    return (str(path.resolve()), st.st_mtime_ns, st.st_size)
+
+
+def _probe_cached(path: Path):
+    """container.probe with a one-entry-per-file cache: the segments of one long video are cut by successive calls
+    (src/analyzer/content_analyzer.py:745-758), and indexing a two-hour file once is enough."""
+    from . import container
+    try:
+        key = _file_key(path)
+    except OSError:
+        return None
+    hit = _INDEX_CACHE.get(key[0])
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    idx = container.probe(path)
+    if len(_INDEX_CACHE) > 8:
+        _INDEX_CACHE.clear()
+    _INDEX_CACHE[key[0]] = (key, idx)
+    return idx
+
+
 def _cut(src: Path, start: float, end: float, dst: Path, stream_copy: bool) -> bool:
-    from . import container, scene
-    idx = container.probe(src)
-    if idx is None or idx.n_frames == 0 or idx.fps_num <= 0:
+    from . import container, isobmff, scene
+    idx = _probe_cached(src)
+    if idx is None or idx.n_frames == 0:
         return False
-    keyframes = np.nonzero(idx.keyframe)[0]
-    first, last = scene.frames_for_window(start, end, idx.n_frames, idx.fps_num, idx.fps_den, keyframes, stream_copy)
-    if last <= first:
-        return False
-    data = np.memmap(src, dtype=np.uint8, mode="r")
+    times = _picture_times(idx)
     if idx.kind == "h264":
-        sps, pps = container.find_parameter_sets(data)
-    else:
-        sps, pps = idx.sps, idx.pps
-    samples = [bytes(data[int(o):int(o) + int(s)]) for o, s in
-               zip(idx.nal_offsets[first:last], idx.nal_sizes[first:last])]
-    keys = [bool(k) for k in idx.keyframe[first:last]]
-    if not keys[0]:
-        # frame-accurate cut that starts inside a GOP (the reference re-encodes here).  The PCM-intra subset
-        # lets us re-express the first picture exactly: it repeats its reference IDR, so that IDR's samples
-        # become the first sample.  Anything else would need an encoder.
-        ref = keyframes[keyframes <= first]
-        if idx.extra.get("pcm_intra_only") is False or ref.size == 0:
+        # raw Annex-B elementary stream (the synthetic clips): one slice NAL per picture, wrapped into a new MP4
+        if idx.fps_num <= 0:
             return False
-        k = int(ref[-1])
-        samples[0] = bytes(data[int(idx.nal_offsets[k]):int(idx.nal_offsets[k]) + int(idx.nal_sizes[k])])
-        keys[0] = True
-    container.write_mp4(dst, sps=sps, pps=pps, samples=samples, width=idx.width, height=idx.height,
-                        fps_num=idx.fps_num, fps_den=idx.fps_den, keyframes=keys)
-    if _OPTIONS["frame_buffers"]:
-        _ingest_to_files(idx, data, first, last, dst)
-    return True
+        keyframes = np.nonzero(idx.keyframe)[0]
+        first, last = scene.frames_for_window(start, end, idx.n_frames, idx.fps_num, idx.fps_den, keyframes,
+                                              stream_copy)
+        if last <= first:
+            return False
+        data = np.memmap(src, dtype=np.uint8, mode="r")
+        sps, pps = container.find_parameter_sets(data)
+        samples = [data[int(o):int(o) + int(z)] for o, z in zip(idx.nal_offsets[first:last], idx.nal_sizes[first:last])]
+        keys = [bool(k) for k in idx.keyframe[first:last]]
+        if not keys[0]:
+            k = _keyframe_index_at_or_before(idx, times, float(times[first]))
+            if k is None or not idx.extra.get("pcm_intra_only"):
+                return False                 # a mid-GOP start needs an encoder unless pictures merely repeat the IDR
+            samples[0] = data[int(idx.nal_offsets[k]):int(idx.nal_offsets[k]) + int(idx.nal_sizes[k])]
+            keys[0] = True
+        container.write_mp4(dst, sps=sps, pps=pps, samples=samples, width=idx.width, height=idx.height,
+                            fps_num=idx.fps_num, fps_den=idx.fps_den, keyframes=keys)
+        copier = None
+    else:
+        movie = idx.extra["movie"]
+        track = movie.video_track()
+        sel = isobmff.select_reference_range(times, idx.keyframe, start, end, stream_copy)
+        if sel is None:
+            return False
+        first, last, first_acc = sel
+        kwargs = {"stream_copy": stream_copy, "selection": sel}
+        if not stream_copy and not idx.keyframe[first]:
+            # frame-accurate cut that starts inside a GOP (the reference re-encodes with libx264 here,
+            # src/utils/video_segmenter.py:138-154; this image has no encoder).  PCM-intra streams let the first
+            # picture be re-expressed exactly: it repeats its reference IDR, whose sample becomes the first sample.
+            # Every other stream keeps the keyframe lead-in in the file and starts the PRESENTATION at the exact
+            # picture through the edit list.
+            k = _keyframe_index_at_or_before(idx, times, float(times[first]))
+            if k is not None and container.classify_pcm(idx):
+                with open(src, "rb") as f:
+                    f.seek(int(track.offsets[k]))
+                    sample = f.read(int(track.sizes[k]))
+                kwargs["first_sample"] = sample
+            else:
+                first = k if k is not None else first
+                kwargs = {"stream_copy": True, "accurate_presentation": True, "selection": (first, last, first_acc)}
+        # the stream copy (file -> file, inside the kernel) runs beside the GPU pass
+        copier = _Background(isobmff.cut_movie, movie, start, end, dst, **kwargs)
+    try:
+        if _OPTIONS["frame_buffers"]:
+            reason = None
+            if idx.kind == "mp4" and not idx.extra.get("decodable"):
+                reason = ("video track %r is not single-slice H.264: the decode front end of this build (K0) handles "
+                          "PCM-intra H.264 only and NVDEC is not available on this host" % idx.extra.get("codec"))
+            elif idx.kind == "mp4" and not container.classify_pcm(idx):
+                reason = ("H.264 stream uses coding tools outside the PCM-intra subset K0 decodes; NVDEC is not "
+                          "available on this host")
+            if reason is None:
+                _ingest_to_files(idx, first, last, dst)
+            else:                               # the stream copy needs no decode: the cut stands, the pixel pass is skipped
+                _write_sidecar(dst, idx, first, last, None, reason)
+                log.info("event=segment_pixel_pass_skipped reason=%s", reason)
+    finally:
+        res = copier.result() if copier is not None else True
+    return res is not None and res is not False
 
 
-def _ingest_to_files(idx, data, first: int, last: int, dst: Path) -> None:
-    """GPU pass for pictures [first,last): writes <dst>.frames and <dst>.json.  Raises on any failure."""
+class _Background:
+    """Runs one call on a helper thread; result() re-raises its exception."""
+
+    def __init__(self, fn, *args, **kwargs):
+        import threading
+        self._out = None
+        self._exc = None
+
+        def body():
+            try:
+                self._out = fn(*args, **kwargs)
+            except BaseException as e:  # noqa: BLE001
+                self._exc = e
+
+        self._t = threading.Thread(target=body, daemon=True)
+        self._t.start()
+
+    def result(self):
+        self._t.join()
+        if self._exc is not None:
+            raise self._exc
+        return self._out
+
+
+def _engine_for(idx):
+    """SegmentIngestor for (file, options), kept across calls: the segments of one video share plans, pinned staging
+    and device buffers."""
     from . import ingest
+    key = (_file_key(idx.path), tuple(sorted((k, str(v)) for k, v in _OPTIONS.items())))
+    eng = _ENGINE_CACHE.get("engine")
+    if eng is not None and eng[0] == key:
+        return eng[1]
+    _ENGINE_CACHE.clear()
     opts = ingest.IngestOptions(target_height=_OPTIONS["target_height"], sws_flags=_OPTIONS["sws_flags"],
                                 batch_frames=_OPTIONS["batch_frames"], scene_threshold=_OPTIONS["scene_threshold"],
                                 output=_OPTIONS["output"], rgb_size=_OPTIONS["rgb_size"],
                                 sample_every=_OPTIONS["sample_every"], device=_OPTIONS["device"])
-    eng = ingest.SegmentIngestor(idx, opts, host_bytes=data)
-    sink = ingest.FileSink(_frames_path(dst))
+    engine = ingest.SegmentIngestor(idx, opts)
+    _ENGINE_CACHE["engine"] = (key, engine)
+    return engine
+
+
+def _ingest_to_files(idx, first: int, last: int, dst: Path) -> None:
+    """GPU pass for pictures [first,last): writes <dst>.frames and <dst>.json.  Raises on any failure."""
+    from . import landing
+    eng = _engine_for(idx)
+    n_out = eng.kept_pictures(first, last)
+    land = landing.acquire(_frames_path(dst), max(n_out, 1) * eng.frame_bytes)
     try:
-        res = eng.run(first, last, sink)
-    finally:
-        sink.close()
-    side = {
-        "source": str(idx.path), "first_picture": first, "last_picture": last, "fps": [idx.fps_num, idx.fps_den],
-        "source_size": [idx.width, idx.height], "frame_size": [res.out_width, res.out_height],
-        "pixel_format": opts.output, "sample_every": opts.sample_every, "frame_bytes": res.frame_bytes,
-        "frames": sink.frames,
-        "scene_threshold": opts.scene_threshold, "cuts": [int(c) for c in res.cuts],
-        "sad": [int(s) for s in res.sad], "score": [float(s) for s in res.scores],
-    }
+        res = eng.run(first, last, landing=land)
+        land.finish(res.stats["landed_frames"] * eng.frame_bytes)
+    except BaseException:
+        land.abort()
+        raise
+    _write_sidecar(dst, idx, first, last, res, None, eng.opts, land)
+    log.info("event=segment_ingest frames=%d size=%dx%d cuts=%d landing=%s", res.stats["landed_frames"],
+             res.out_width, res.out_height, len(res.cuts), res.stats["landing"])
+
+
+def _write_sidecar(dst: Path, idx, first: int, last: int, res, reason, opts=None, land=None) -> None:
+    side = {"source": str(idx.path), "first_picture": first, "last_picture": last,
+            "fps": [idx.fps_num, idx.fps_den], "source_size": [idx.width, idx.height],
+            "codec": idx.extra.get("codec", "h264")}
+    if res is None:
+        side.update({"frames": None, "reason": reason})
+    else:
+        side.update({
+            "frame_size": [res.out_width, res.out_height], "pixel_format": opts.output,
+            "sample_every": opts.sample_every, "frame_bytes": res.frame_bytes,
+            "frames": res.stats["landed_frames"],
+            "landing": res.stats["landing"], "landing_recycled": bool(land is not None and land.recycled),
+            "scene_threshold": opts.scene_threshold, "cuts": res.cuts.tolist(),
+            "sad": res.sad.tolist(), "score": res.scores.tolist(),
+        })
     _sidecar_path(dst).write_text(json.dumps(side), encoding="utf-8")
-    log.info("event=segment_ingest frames=%d size=%dx%d cuts=%d", sink.frames, res.out_width, res.out_height,
-             len(res.cuts))
 
 
 # ---- manifest lifecycle -------------------------------------------------------------------------------------
