@@ -107,6 +107,13 @@ int vt_sad_hist_u8(const uint8_t *luma_dev, int pitch, size_t frame_stride, int 
 int vt_gather_frames(const uint8_t *src_dev, size_t src_frame_stride, size_t frame_bytes, const int32_t *index_dev,
                      int count, uint8_t *dst_dev, void *stream);
 
+/* Landing of K5: frames go from the device straight into a page-locked mapping of the segment's `.frames` file.
+ * vt_host_register pins an existing host range (VT_ERR_CUDA when the range cannot be pinned; the CUDA error state is
+ * cleared), vt_copy_to_host_async is the D2H copy on `stream`. */
+int vt_host_register(void *ptr, size_t n_bytes);
+int vt_host_unregister(void *ptr);
+int vt_copy_to_host_async(void *dst_host, const void *src_dev, size_t n_bytes, void *stream);
+
 /* ---- K0: decode front end --------------------------------------------------------------------------------
  * Replaces: libavcodec inside the ffmpeg child process (src/utils/video_segmenter.py:141-154,
  * src/analyzer/content_analyzer.py:193-211) and ffprobe (src/utils/video_utils.py:7-38). */

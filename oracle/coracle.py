@@ -33,6 +33,8 @@ def lib():
                                           ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.vto_sad_hist.argtypes = [u8p, ctypes.c_int, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, u8p, u8p]
         L.vto_sad_hist.restype = None
+        L.vto_sad_hist_fast.argtypes = L.vto_sad_hist.argtypes
+        L.vto_sad_hist_fast.restype = None
         L.vto_nv12_to_yuv420p.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, u8p, u8p, u8p]
         L.vto_nv12_to_yuv420p.restype = None
         L.vto_pcm_picture_to_yuv420p.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, u8p, u8p, u8p]
@@ -71,15 +73,16 @@ def scale_yuv420p(y, u, v, dw, dh, flags=BICUBIC):
     return scale_plane(y, dw, dh, flags), scale_plane(u, cw, ch, flags), scale_plane(v, cw, ch, flags)
 
 
-def sad_hist(cur: np.ndarray, prev: np.ndarray | None):
+def sad_hist(cur: np.ndarray, prev: np.ndarray | None, fast: bool = False):
     cur = np.ascontiguousarray(cur)
     h, w = cur.shape
     sad = np.zeros(1, np.uint64)
     hist = np.zeros(256, np.uint32)
     if prev is not None:
         prev = np.ascontiguousarray(prev)
-    lib().vto_sad_hist(cur.ctypes.data, cur.strides[0], prev.ctypes.data if prev is not None else None,
-                       prev.strides[0] if prev is not None else 0, w, h, sad.ctypes.data, hist.ctypes.data)
+    fn = lib().vto_sad_hist_fast if fast else lib().vto_sad_hist
+    fn(cur.ctypes.data, cur.strides[0], prev.ctypes.data if prev is not None else None,
+       prev.strides[0] if prev is not None else 0, w, h, sad.ctypes.data, hist.ctypes.data)
     return int(sad[0]), hist
 
 

@@ -14,13 +14,13 @@
  *                         file restates its published algorithm (libswscale/utils.c initFilter,
  *                         swscale.c hScale8To15_c, output.c yuv2planeX_8_c) for the version the image
  *                         carries: libswscale 9.1.100 (FFmpeg 8.0.1, OpenCV wheel).  Parity is PINNED:
- *                         tests/test_oracle_sws.py checks it bit-for-bit against that library run
+ *                         tests/test_oracle.py checks it bit-for-bit against that library run
  *                         with SWS_ACCURATE_RND|SWS_BITEXACT (the CPU-independent C path), and
  *                         tests/golden/sws_*.npz hold outputs generated from the library.
  *  - vto_sad_hist, vto_nv12_* , vto_rgb24_*   no reference code exists; the
  *                         definitions in SURVEY.md section 8a K1/K3 are the authority and this file is
  *                         their first statement ("parity unpinned by the reference", pinned against
- *                         numpy in tests/test_oracle_kernels.py and, for RGB, against libswscale).
+ *                         numpy and, for RGB, against libswscale in tests/test_oracle.py).
  *
  * Plain C99, no dependencies.  Build: make -C oracle  (-> oracle/libvtoracle.so)
  */
@@ -307,6 +307,39 @@ void vto_sad_hist(const uint8_t *cur, int cur_pitch, const uint8_t *prev, int pr
             if (p) s += (uint64_t)(c[x] > p[x] ? c[x] - p[x] : p[x] - c[x]);
         }
     }
+    *sad = s;
+}
+
+/* The same K3, written the way a tuned host implementation would be (bench.py's CPU arm takes whichever of this
+ * and OpenCV's norm/calcHist is faster, i.e. the STRONGER baseline): SAD in its own loop so the compiler turns it into
+ * psadbw, four interleaved sub-histograms so consecutive equal pixels do not serialise on one counter.  Results are
+ * identical to vto_sad_hist (tests/test_oracle.py). */
+#if defined(__GNUC__) && defined(__x86_64__)
+__attribute__((target_clones("avx2", "default")))
+#endif
+void vto_sad_hist_fast(const uint8_t *cur, int cur_pitch, const uint8_t *prev, int prev_pitch, int w, int h,
+                       uint64_t *sad, uint32_t *hist) {
+    uint64_t s = 0;
+    uint32_t sub[4][256];
+    memset(sub, 0, sizeof(sub));
+    for (int y = 0; y < h; y++) {
+        const uint8_t *c = cur + (size_t)y * cur_pitch;
+        int x = 0;
+        for (; x + 4 <= w; x += 4) {
+            sub[0][c[x]]++;
+            sub[1][c[x + 1]]++;
+            sub[2][c[x + 2]]++;
+            sub[3][c[x + 3]]++;
+        }
+        for (; x < w; x++) sub[0][c[x]]++;
+        if (prev) {
+            const uint8_t *p = prev + (size_t)y * prev_pitch;
+            uint32_t row = 0;
+            for (int i = 0; i < w; i++) row += (uint32_t)(c[i] > p[i] ? c[i] - p[i] : p[i] - c[i]);
+            s += row;
+        }
+    }
+    for (int i = 0; i < 256; i++) hist[i] = sub[0][i] + sub[1][i] + sub[2][i] + sub[3][i];
     *sad = s;
 }
 

@@ -200,3 +200,54 @@ def test_device_sink_hands_over_the_same_frames_without_a_host_copy(cuda, tmp_pa
     assert np.array_equal(dev.cpu().numpy(), np.concatenate([c for _, c in host]))
     assert np.array_equal(res.sad, ref.sad) and res.cuts.tolist() == ref.cuts.tolist()
     assert eng.d2h_bytes == 50 * 0 + sum(min(8, 47 - b) for b in range(0, 47, 8)) * (8 + 1024)   # scores only
+
+
+@pytest.mark.parametrize("where", ["shm", "disk"])
+@pytest.mark.parametrize("sample_every", [1, 7])
+def test_frames_land_directly_in_the_file_and_landing_files_are_recycled(cuda, tmp_path, where, sample_every):
+    """K5: on tmpfs the copy engine writes into a registered mapping of the `.frames` file (no host copy); elsewhere a
+    writer thread drains the pinned ring.  Either way the file equals the frames the engine API delivers, and a
+    replaced artefact lands in the same registered pages (landing_recycled)."""
+    import os
+    import shutil
+    import tempfile
+    from video_transformer_b200 import ingest, landing
+    src, meta = _clip(tmp_path, 640, 480, 90, 10, cuts=[23, 61])
+    idx = container.probe(src)
+    opts = ingest.IngestOptions(target_height=240, batch_frames=16, scene_threshold=0.05, sample_every=sample_every)
+    first, last = 10, 90
+    ref = []
+    ingest.SegmentIngestor(idx, opts).run(first, last, lambda chunk, k0: ref.append(chunk.numpy().copy()))
+    ref = np.concatenate(ref)
+    if where == "shm":
+        if not os.path.isdir("/dev/shm"):
+            pytest.skip("no /dev/shm")
+        out_dir = tempfile.mkdtemp(prefix="vt_landing_test_", dir="/dev/shm")
+    else:
+        out_dir = str(tmp_path / "out")
+    try:
+        video_segmenter.configure(target_height=240, batch_frames=16, scene_threshold=0.05, sample_every=sample_every)
+        out = os.path.join(out_dir, "segment_0000.mp4")
+        sides = []
+        for rep in range(3):
+            assert video_segmenter.extract_segment(src, first / 30.0, last / 30.0, out) is True
+            side = json.loads(open(out[:-4] + ".json").read())
+            sides.append(side)
+            frames = np.fromfile(out[:-4] + ".frames", np.uint8).reshape(-1, side["frame_bytes"])
+            assert side["frames"] == ref.shape[0] == frames.shape[0]
+            assert np.array_equal(frames, ref), (where, rep)
+        if where == "shm" and sides[0]["landing"] == "direct":
+            assert [s["landing_recycled"] for s in sides] == [False, True, True]
+            assert landing.stats()["files"] >= 1
+            # the consumer deletes the artefact: its landing file becomes free, the next segment reuses it
+            os.unlink(out[:-4] + ".frames")
+            out2 = os.path.join(out_dir, "segment_0001.mp4")
+            assert video_segmenter.extract_segment(src, first / 30.0, last / 30.0, out2) is True
+            assert json.loads(open(out2[:-4] + ".json").read())["landing_recycled"] is True
+            assert np.array_equal(np.fromfile(out2[:-4] + ".frames", np.uint8).reshape(ref.shape), ref)
+        else:
+            assert sides[0]["landing"] in ("staged", "direct")
+    finally:
+        video_segmenter.configure(target_height=720, batch_frames=32, scene_threshold=0.10, sample_every=1)
+        landing.release_all()
+        shutil.rmtree(out_dir, ignore_errors=True)

@@ -45,6 +45,9 @@ SIGNATURES = {
     "vt_scale_nv12_to_rgb24": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_size_t, c_int, c_void_p]),
     "vt_sad_hist_u8": (c_int, [c_void_p, c_int, c_size_t, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "vt_gather_frames": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_int, c_void_p, c_void_p]),
+    "vt_host_register": (c_int, [c_void_p, c_size_t]),
+    "vt_host_unregister": (c_int, [c_void_p]),
+    "vt_copy_to_host_async": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "vt_h264_scan": (c_int, [c_void_p, c_size_t, POINTER(StreamInfo), c_void_p, c_void_p, c_void_p, c_int]),
     "vt_h264_pcm_layout": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_void_p]),
     "vt_h264_pcm_layout_ps": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p,

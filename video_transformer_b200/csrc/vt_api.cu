@@ -15,15 +15,21 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= VT_MAX_DEVICES) dev = 0;
+    return dev;
+}
+
 int sm_count() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;  // B200
+    static int n[VT_MAX_DEVICES] = {0};
+    const int dev = current_device();
+    if (!n[dev]) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;  // B200
+        n[dev] = v;
     }
-    return n;
+    return n[dev];
 }
 
 int launch_score(const uint8_t *, int, size_t, int, int, const uint8_t *, int, uint64_t *, uint32_t *, cudaStream_t);
@@ -38,6 +44,42 @@ extern "C" {
 int vt_version(void) { return 100; }
 const char *vt_last_error(void) { return vt::g_err; }
 uint64_t vt_launch_count(void) { return vt::g_launches.load(); }
+
+/* K5: page-lock an existing host range (a MAP_SHARED mapping of the `.frames` file) so the copy engine can write device
+ * frames straight into the file.  On failure the runtime's last-error state is cleared, so the refusal (file systems whose
+ * mappings cannot be pinned) does not surface at the next kernel launch. */
+int vt_host_register(void *ptr, size_t n_bytes) {
+    if (!ptr || !n_bytes) {
+        vt::set_error("vt_host_register: bad arguments");
+        return VT_ERR_INVALID;
+    }
+    cudaError_t e = cudaHostRegister(ptr, n_bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return vt::cuda_fail(e, "cudaHostRegister");
+    }
+    return VT_OK;
+}
+
+int vt_host_unregister(void *ptr) {
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return vt::cuda_fail(e, "cudaHostUnregister");
+    }
+    return VT_OK;
+}
+
+/* Asynchronous device -> host copy on `stream` (the landing copy of K5; the host range must be page-locked for the copy
+ * to overlap with kernels). */
+int vt_copy_to_host_async(void *dst_host, const void *src_dev, size_t n_bytes, void *stream) {
+    if (!dst_host || !src_dev) {
+        vt::set_error("vt_copy_to_host_async: bad arguments");
+        return VT_ERR_INVALID;
+    }
+    VT_CUDA(cudaMemcpyAsync(dst_host, src_dev, n_bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return VT_OK;
+}
 
 int vt_sad_hist_u8(const uint8_t *luma, int pitch, size_t frame_stride, int w, int h, const uint8_t *prev0,
                    int n_frames, uint64_t *sad, uint32_t *hist, void *stream) {

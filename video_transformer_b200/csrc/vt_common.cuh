@@ -33,6 +33,8 @@ inline int cuda_fail(cudaError_t e, const char *what) {
         if (e__ != cudaSuccess) return vt::cuda_fail(e__, name); \
     } while (0)
 
+#define VT_MAX_DEVICES 64
+int current_device();   // ordinal of the calling thread's device (per-device caches index by it)
 int sm_count();
 
 // ---- device-side helpers ------------------------------------------------------------------------------

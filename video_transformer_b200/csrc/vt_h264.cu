@@ -314,8 +314,8 @@ int layout_core(const uint8_t *bs, size_t n, const Sps &sps, const Pps &pps, con
                 const uint32_t *frame_sizes, int n_frames, uint64_t *payload_off) {
     uint64_t last_idr = UINT64_MAX;
     for (int f = 0; f < n_frames; f++) {
-        if (frame_offsets[f] + frame_sizes[f] > n) {
-            vt::set_error("vt_h264_pcm_layout: frame %d outside the buffer", f);
+        if (frame_sizes[f] < 2 || frame_offsets[f] > n || frame_sizes[f] > n - frame_offsets[f]) {
+            vt::set_error("vt_h264_pcm_layout: frame %d is empty or outside the buffer", f);
             return VT_ERR_BITSTREAM;
         }
         SliceInfo si = parse_slice(bs + frame_offsets[f], frame_sizes[f], sps, pps);
@@ -480,7 +480,8 @@ extern "C" int vt_h264_pcm_decode(const uint8_t *bs_dev, const uint64_t *payload
         }
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)mb_w * 386 + 64;
-    static size_t smem_set = 0;
+    static size_t smem_set_dev[VT_MAX_DEVICES] = {0};   // function attributes are per device
+    size_t &smem_set = smem_set_dev[vt::current_device()];
     if (smem > 48 * 1024 && smem > smem_set) {
         VT_CUDA(cudaFuncSetAttribute(vt::h264_pcm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;

@@ -608,10 +608,11 @@ int upload(const void *h, size_t n, void **d) {
 template <int HP, int TV, bool UV, int MASK, int Q, int HS = 0>
 int launch_t(const vt_scale_plan::Pair &s, const CUtensorMap &tm, PairArgs a, int rows_total, cudaStream_t st) {
     auto k = scale_pair_kernel<HP, TV, UV, MASK, Q, HS>;
-    static int smem_set = 0, blocks_per_sm = 0;
+    static int smem_set_dev[VT_MAX_DEVICES] = {0}, blocks_per_sm_dev[VT_MAX_DEVICES] = {0};   // per device ordinal
     const int smem = s.warp_smem * 4;
     static std::mutex mu;
     std::lock_guard<std::mutex> lock(mu);
+    int &smem_set = smem_set_dev[current_device()], &blocks_per_sm = blocks_per_sm_dev[current_device()];
     if (smem > smem_set || !blocks_per_sm) {
         VT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         VT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k, 128, smem));

@@ -493,7 +493,8 @@ int launch_score(const uint8_t *luma, int pitch, size_t frame_stride, int w, int
         static const kern_t table[2][5] = {
             {score_kernel<0, false>, score_kernel<1, false>, score_kernel<2, false>, score_kernel<3, false>, score_kernel<4, false>},
             {score_kernel<0, false>, score_kernel<1, true>, score_kernel<2, true>, score_kernel<3, true>, score_kernel<4, true>}};
-        static bool attr_done = false;
+        static bool attr_done_dev[VT_MAX_DEVICES] = {false};   // function attributes are per device
+        bool &attr_done = attr_done_dev[current_device()];
         if (!attr_done) {
             for (int r = 0; r < 2; r++)
                 for (int i = 0; i < 5; i++)

@@ -84,6 +84,8 @@ class SegmentIngestor:
         self.idx = index
         self.opts = opts or IngestOptions()
         self.dev = torch.device(self.opts.device)
+        if self.dev.type == "cuda" and self.dev.index is None:
+            self.dev = torch.device("cuda", torch.cuda.current_device())
         self.host = host_bytes if host_bytes is not None else np.memmap(index.path, dtype=np.uint8, mode="r")
         n = index.n_frames
         L = lib()
@@ -249,7 +251,7 @@ class SegmentIngestor:
         batches = [(b, min(b + B, last)) for b in range(d0, last, B)]
         fb = self.frame_bytes
         direct = landing is not None and landing.direct and device_sink is None
-        staged = landing is not None and not direct and device_sink is None
+        land_staged = landing is not None and not direct and device_sink is None
         landed = 0                           # frames already given a place in the landing file
 
         def drain(slot):
@@ -267,7 +269,7 @@ class SegmentIngestor:
                 k0 = lo - b0
                 sad_all[lo - r0:hi - r0] = slot["sad_host"].numpy()[k0:k0 + hi - lo].view(np.uint64)
                 hist_all[lo - r0:hi - r0] = slot["hist_host"].numpy()[k0:k0 + hi - lo].view(np.uint32)
-            if staged and slot["land"] is not None:
+            if land_staged and slot["land"] is not None:
                 at, cnt, row0 = slot["land"]
                 slot["wfut"] = landing.write_chunk(slot["out_host"][row0:row0 + cnt], at * fb)
                 slot["land"] = None
@@ -378,7 +380,7 @@ class SegmentIngestor:
                             slot["out"][row0:row0 + cnt], non_blocking=True)
                     else:
                         slot["out_host"][row0:row0 + cnt].copy_(slot["out"][row0:row0 + cnt], non_blocking=True)
-                        if staged:
+                        if land_staged:
                             slot["land"] = (landed, cnt, row0)
                     landed += cnt
                     self.d2h_bytes += cnt * fb
@@ -389,7 +391,7 @@ class SegmentIngestor:
             # drain() synchronises this slot's ev_out before the host issues batch i+2 into the same buffers,
             # which orders every device-side reuse (bitstream, surfaces, output) after the copies that read them
             slot["pending"] = (b0, b1)
-            if staged and i >= 1:
+            if land_staged and i >= 1:
                 drain(self.slots[(i - 1) % self.n_slots])    # hand batch i-1 to the writer while batch i runs
         for slot in sorted(self.slots, key=lambda sl: sl["pending"][0] if sl["pending"] else -1):
             drain(slot)                      # oldest batch first: the sink sees pictures in order
@@ -406,4 +408,4 @@ class SegmentIngestor:
         return IngestResult(first, last, self.out_w, self.out_h, self.frame_bytes, sad_all, hist_all, scores, cuts,
                             {"decoded_from": d0, "batches": len(batches), "h2d_bytes": self.h2d_bytes,
                              "d2h_bytes": self.d2h_bytes, "landed_frames": landed,
-                             "landing": ("direct" if direct else "staged" if staged else None)})
+                             "landing": ("direct" if direct else "staged" if land_staged else None)})

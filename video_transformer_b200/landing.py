@@ -25,6 +25,8 @@ from pathlib import Path
 import numpy as np
 import torch
 
+from ._lib import lib
+
 ARENA_DIR = ".vt_landing"
 _libc = ctypes.CDLL("libc.so.6", use_errno=True)
 _libc.posix_fallocate.argtypes = [ctypes.c_int, ctypes.c_long, ctypes.c_long]
@@ -50,7 +52,7 @@ class _Slot:
             raise
         self.array = np.frombuffer(self.mm, dtype=np.uint8)
         self.base = self.array.ctypes.data
-        self.registered = int(torch.cuda.cudart().cudaHostRegister(self.base, nbytes, 0)) == 0
+        self.registered = lib().vt_host_register(ctypes.c_void_p(self.base), nbytes) == 0
         self.tensor = torch.from_numpy(self.array)
         self.stamp = 0
 
@@ -63,7 +65,7 @@ class _Slot:
     def destroy(self) -> None:
         if self.registered:
             try:
-                torch.cuda.cudart().cudaHostUnregister(self.base)
+                lib().vt_host_unregister(ctypes.c_void_p(self.base))
             except Exception:  # noqa: BLE001 - interpreter shutdown
                 pass
             self.registered = False

@@ -233,7 +233,12 @@ class H264PcmWriter:
         body[:, 2:] = mbs
         self.idr_count += 1
         self.frame_num = 1
-        out = (self._sps + self._pps if with_params else b"") + _START + head + body.reshape(-1)[2:].tobytes() + b"\x80"
+        prefix = (self._sps + self._pps if with_params else b"") + _START
+        # offset, inside the returned bytes, of macroblock 0's first sample (what vt_h264_pcm_layout reports as the
+        # picture's payload): the generator knows it without parsing anything
+        self.last_payload_offset = len(prefix) + len(head)
+        self.last_nal_offset = len(prefix)
+        out = prefix + head + body.reshape(-1)[2:].tobytes() + b"\x80"
         return out
 
     def skip(self) -> bytes:
