@@ -1,23 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- 720p output frames/s of the long-video ingest path (BASELINE.json metric) on N B200s.
 
-Workload (N=1): BASELINE.json configs[1], "2-hour synthetic 1080p30 H.264 -> 720p downscale + segment", run as a
-bounded stream of GOP-aligned steps: one step = 256 pictures of a synthetic 1920x1080@30 testsrc clip (I_PCM IDR
-every 30 pictures + all-skip P pictures, see video_transformer_b200/synth.py; entropy decoding cost is NOT
-representative of real CABAC content) through decode -> SAD/histogram -> swscale-exact bicubic 1280x720 YUV420P.
-`value`  : kernels only, bitstream already resident in HBM (decode + score + scale per step, CUDA events).
-`e2e`    : SegmentIngestor.run() from host bytes to pinned host frame buffers, H2D/D2H inside the timed region.
-N > 1    : one process per GPU (torchrun), every rank ingests its own GOP-aligned shard, no data-path
-           collective (weak scaling); torch.distributed is used for the barrier and the max-over-ranks only.
-`--impl reference`: the same work on the host cores (libswscale bicubic + OpenCV SAD/histogram + C oracle
-           PCM re-layout, all cores), because the literal reference path (ffmpeg child processes) cannot run
-           here: the image has no ffmpeg binary.
+Workload: BASELINE.json configs[1], "2-hour synthetic 1080p30 H.264 -> 720p downscale + segment", run as a bounded
+stream of GOP-aligned pieces of ONE synthetic 1920x1080@30 testsrc clip (I_PCM IDR every 30 pictures + all-skip P
+pictures, video_transformer_b200/synth.py; entropy decoding cost is NOT representative of real CABAC content) through
+decode -> SAD/histogram -> swscale-exact bicubic 1280x720 YUV420P.
+
+`value`      kernels only, bitstream already resident in HBM: one step = R passes of 256 pictures (decode + score +
+             scale), R chosen once so that the K timed steps last >= 1 s; CUDA events on the launching stream.
+`e2e`        the reference-facing plugin call: video_segmenter.extract_segment(clip.mp4, start, end, segment.mp4) on
+             /dev/shm, wall clock.  Every call reads host bytes, stream-copies its samples into a faststart MP4, runs
+             the GPU pass and lands the frames in `<segment>.frames` (D2H straight into the registered mapping of the
+             file) plus the JSON sidecar.  One step = UNITS_PER_STEP such calls per GPU, each UNIT_PICTURES long.
+N > 1        ONE clip, sharded dynamically: ranks pull unit indices from a shared counter (torch's TCPStore -- control
+             plane only; no collective touches pixels), so a rank whose D2H path is slower takes fewer units.  The
+             record carries per-rank units / D2H GB/s, the concurrent D2H ceiling measured in the same run, and
+             `cuts_equal_single_gpu` (cuts merged from all ranks' shards == a single-GPU pass over the whole clip).
+`--impl reference`  the same work on the host cores (libswscale bicubic, the faster of OpenCV / tuned C for SAD+hist,
+             C PCM re-layout; one process per core), because the literal reference path (ffmpeg child processes)
+             cannot run here: the image has no ffmpeg binary.  It never loads libvtseg.so.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import shutil
 import statistics
 import subprocess
 import sys
@@ -32,22 +40,28 @@ sys.path.insert(0, ROOT)
 
 SRC_W, SRC_H, FPS, GOP = 1920, 1080, 30, 30
 OUT_H = 720
-STEP_FRAMES = 256
+PASS_FRAMES = 256                      # pictures per kernel launch of the device-resident arm
+UNIT_PICTURES = 1920                   # pictures per extract_segment call of the e2e arm (64 GOPs = 64 s of video)
+UNITS_PER_STEP = 2                     # e2e units per GPU and step
+CLIP_FRAMES = 3840                     # the bench clip: 128 s
 METRIC = "720p_output_frames_per_sec"
 UNIT = "frames/s"
 # algorithmic bytes per picture (SURVEY.md section 8d / BASELINE.md section 3)
 BYTES_SCALE = 3110400 + 1382400          # 1080p NV12 in, 720p YUV420P out
 BYTES_SCORE = 2 * SRC_W * SRC_H          # cur + prev luma
 BYTES_DECODE = 2 * 3110400               # samples in, NV12 surface out
+BYTES_FUSED_C2 = 3110400 + 2073600 + 1382400   # scale + score on the source luma in one pass (SURVEY.md 8d "Fused C2")
 
 
 def load_traffic():
-    """DRAM bytes per picture per kernel from the committed ncu capture (profiles/r01_traffic.json), or None."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """DRAM bytes per picture per kernel from the newest committed ncu capture (profiles/r*_traffic.json), or None."""
+    pdir = os.path.join(ROOT, "profiles")
     try:
-        return json.load(open(p))["per_picture_bytes"]
+        names = sorted(n for n in os.listdir(pdir) if n.endswith("_traffic.json"))
+        d = json.load(open(os.path.join(pdir, names[-1])))
+        return d["per_picture_bytes"], "profiles/" + names[-1]
     except Exception:  # noqa: BLE001
-        return None
+        return None, None
 
 
 def load_peaks():
@@ -90,83 +104,138 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
                 sm.append(float(f[1])); mx.append(float(f[2]))
+                pw.append(float(f[3]))
             except ValueError:
                 continue
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- the clip -------------------------------------------------------------------------------------------------
+def make_clip(n_frames: int, path: str):
+    """Write the synthetic Annex-B clip.  Returns (payload offsets u64[n], keyframe flags, cut list): the generator knows
+    where every picture's samples are, so the host-core arm needs no bitstream parser (and no libvtseg.so)."""
+    from video_transformer_b200 import synth
+    wr = synth.H264PcmWriter(SRC_W, SRC_H, FPS, 1)
+    cuts = set(synth.scene_cut_frames(n_frames, FPS, seed=42))
+    payload = np.zeros(n_frames, np.uint64)
+    key = np.zeros(n_frames, bool)
+    scene = 0
+    pos = 0
+    last = 0
+    with open(path, "wb") as f:
+        for k in range(n_frames):
+            if k in cuts:
+                scene += 1
+            if k % GOP == 0 or k in cuts:
+                b = wr.idr(*synth.testsrc_frame(SRC_W, SRC_H, k, scene))
+                last = pos + wr.last_payload_offset
+                key[k] = True
+            else:
+                b = wr.skip()
+            payload[k] = last
+            f.write(b)
+            pos += len(b)
+    return payload, key, sorted(cuts)
 
 
 # ---- host-core arm -----------------------------------------------------------------------------------------------
 _W = {}
 
 
-def _cpu_worker_init(path, payload, keyframe, w, h, dw, dh):
-    import cv2  # noqa: F401
+def _cpu_worker_init(path, payload, w, h, dw, dh):
+    import cv2
     from oracle import coracle, ffsws
-    _W.update(buf=np.memmap(path, dtype=np.uint8, mode="r"), payload=payload, key=keyframe, w=w, h=h, dw=dw, dh=dh,
-              coracle=coracle, ffsws=ffsws, sws=ffsws.available())
     try:
         cv2.setNumThreads(1)
     except Exception:  # noqa: BLE001
         pass
+    _W.update(buf=np.memmap(path, dtype=np.uint8, mode="r"), payload=payload, w=w, h=h, dw=dw, dh=dh,
+              coracle=coracle, ffsws=ffsws, sws=ffsws.available(), cv2=cv2)
+    # SAD + histogram: take the faster of OpenCV (norm L1 + calcHist) and the tuned C loop -- the stronger baseline
+    y = np.frombuffer(np.random.default_rng(0).bytes(w * h), np.uint8).reshape(h, w)
+    p = np.roll(y, 1, 1).copy()
+
+    def t(fn):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            fn()
+        return (time.perf_counter() - t0) / 3
+
+    t_cv = t(lambda: (cv2.norm(y, p, cv2.NORM_L1), cv2.calcHist([y], [0], None, [256], [0, 256])))
+    t_c = t(lambda: coracle.sad_hist(y, p, True))
+    _W["score_c"] = t_c < t_cv
 
 
 def _cpu_worker(rng):
-    """Decode + score + downscale pictures [a,b) on one host core.  Returns (frames, checksum)."""
-    import cv2
+    """Decode + score + downscale pictures [a,b) on one host core.  Returns (frames, checksum, seconds per stage)."""
     a, b = rng
     W = _W
-    co, ff = W["coracle"], W["ffsws"]
+    co, ff, cv2 = W["coracle"], W["ffsws"], W["cv2"]
     w, h, dw, dh = W["w"], W["h"], W["dw"], W["dh"]
     out = np.empty((dw * dh * 3 // 2,), np.uint8)     # the segment frame buffer slot being filled
     prev_y = None
     cur = None
     last_payload = None
     acc = 0
+    t_dec = t_score = t_scale = 0.0
     if a > 0:                                          # predecessor of the task's first picture, for its SAD
         last_payload = int(W["payload"][a - 1])
         cur = co.pcm_picture_to_yuv420p(W["buf"], last_payload, w, h)
         prev_y = cur[0]
     for k in range(a, b):
+        t0 = time.perf_counter()
         p = int(W["payload"][k])
         if p != last_payload:                          # IDR: re-layout the PCM samples; skip pictures repeat
             cur = co.pcm_picture_to_yuv420p(W["buf"], p, w, h)
             last_payload = p
         y, u, v = cur
-        if prev_y is not None:
-            acc += int(cv2.norm(y, prev_y, cv2.NORM_L1))
-        hist = cv2.calcHist([y], [0], None, [256], [0, 256])
-        acc += int(hist[16, 0])
+        t1 = time.perf_counter()
+        if W["score_c"]:
+            s, hist = co.sad_hist(y, prev_y, True)
+            acc += s + int(hist[16])
+        else:
+            if prev_y is not None:
+                acc += int(cv2.norm(y, prev_y, cv2.NORM_L1))
+            hist = cv2.calcHist([y], [0], None, [256], [0, 256])
+            acc += int(hist[16, 0])
+        t2 = time.perf_counter()
         if W["sws"]:
             sy, su, sv = ff.scale_yuv420p(y, u, v, dw, dh, ff.SWS_BICUBIC)
         else:
             sy, su, sv = co.scale_yuv420p(y, u, v, dw, dh, co.BICUBIC)
         n = dw * dh
         out[:n] = sy.reshape(-1); out[n:n + n // 4] = su.reshape(-1); out[n + n // 4:] = sv.reshape(-1)
+        t3 = time.perf_counter()
+        t_dec += t1 - t0; t_score += t2 - t1; t_scale += t3 - t2
         prev_y = y
-    return b - a, acc
+    return b - a, acc, (t_dec, t_score, t_scale), (W["sws"], W["score_c"])
 
 
 class CpuArm:
     """All host cores over pictures of the clip, split into small contiguous ranges per worker task.  The worker pool
     lives across calls (start-up and library warm-up are outside every timed region)."""
 
-    def __init__(self, path, payload, keyframe, w, h, dw, dh, n_clip, cores):
+    def __init__(self, path, payload, w, h, dw, dh, n_clip, cores):
         import multiprocessing as mp
         self.cores, self.n_clip = cores, n_clip
         self.pool = mp.get_context("fork").Pool(cores, initializer=_cpu_worker_init,
-                                                initargs=(path, payload, keyframe, w, h, dw, dh))
+                                                initargs=(path, payload, w, h, dw, dh))
         self.pool.map(_cpu_worker, [(a, min(a + 4, n_clip)) for a in range(0, min(n_clip, 4 * cores), 4)])   # warm
+        self.stage_s = [0.0, 0.0, 0.0]
+        self.stage_frames = 0
+        self.kind = (None, None)
 
     def run(self, count):
         """Process `count` pictures (wrapping around the clip).  Returns (pictures/s, seconds, pictures)."""
@@ -182,30 +251,90 @@ class CpuArm:
         res = self.pool.map(_cpu_worker, tasks, chunksize=4)
         dt = time.perf_counter() - t0
         frames = sum(r[0] for r in res)
+        for r in res:
+            for i in range(3):
+                self.stage_s[i] += r[2][i]
+        self.stage_frames += frames
+        self.kind = res[0][3]
         return frames / dt, dt, frames
+
+    def describe(self):
+        n = max(self.stage_frames, 1)
+        sws, score_c = self.kind
+        return {"decode_ms_per_picture": 1e3 * self.stage_s[0] / n, "score_ms_per_picture": 1e3 * self.stage_s[1] / n,
+                "scale_ms_per_picture": 1e3 * self.stage_s[2] / n,
+                "sws": "live libswscale 9.1 (SIMD, bicubic)" if sws else "c-oracle (scalar restatement; libswscale absent)",
+                "score": "tuned C (psadbw SAD + 4-way histogram)" if score_c else "OpenCV norm(L1) + calcHist"}
 
     def close(self):
         self.pool.close()
         self.pool.join()
 
 
-# ---- workload ---------------------------------------------------------------------------------------------------
-def make_clip(n_frames: int, tmpdir: str):
-    from video_transformer_b200 import container, synth
-    wr = synth.H264PcmWriter(SRC_W, SRC_H, FPS, 1)
-    cuts = set(synth.scene_cut_frames(n_frames, FPS, seed=42))
-    path = os.path.join(tmpdir, "bench_1080p.h264")
-    scene = 0
-    with open(path, "wb") as f:
-        for k in range(n_frames):
-            if k in cuts:
-                scene += 1
-            if k % GOP == 0 or k in cuts:
-                f.write(wr.idr(*synth.testsrc_frame(SRC_W, SRC_H, k, scene)))
-            else:
-                f.write(wr.skip())
-    idx = container.probe(path)
-    return path, idx, sorted(cuts)
+def one_core_rate(path, payload, dw, dh, n_clip, frames=96):
+    """The same worker on ONE core, in this process (for the per-core figure)."""
+    _cpu_worker_init(path, payload, SRC_W, SRC_H, dw, dh)
+    _cpu_worker((0, 8))
+    t0 = time.perf_counter()
+    n, _, _, _ = _cpu_worker((8, 8 + min(frames, n_clip - 8)))
+    return n / (time.perf_counter() - t0)
+
+
+def _out_width():
+    # `-2:720` semantics of ffmpeg's scale filter: width from the aspect ratio, rounded to an even number
+    return int(round(SRC_W * OUT_H / SRC_H / 2.0)) * 2
+
+
+def run_reference(args, K, Wm, cores):
+    tmpdir = tempfile.mkdtemp(prefix="vtbench_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        n_clip = 4 * PASS_FRAMES
+        path = os.path.join(tmpdir, "bench_1080p.h264")
+        payload, _key, _ = make_clip(n_clip, path)
+        dw = _out_width()
+        arm = CpuArm(path, payload, SRC_W, SRC_H, dw, OUT_H, n_clip, cores)
+        ref_step = args.cpu_step_frames               # pictures per reference step (a bounded sample of the workload)
+        times = []
+        for s in range(Wm + K):
+            fps, dt, frames = arm.run(ref_step)
+            if s >= Wm:
+                times.append(dt)
+        desc = arm.describe()
+        arm.close()
+        one = one_core_rate(path, payload, dw, OUT_H, n_clip)
+        total = sum(times)
+        value = ref_step * K / total
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+                "warmup": Wm, "ms_per_step": 1000 * total / K, "step_pictures": ref_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": _config(dw, 1),
+                "cpu_baseline": dict({"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                                      "one_core_value": one,
+                                      "sample": "%d pictures per step, %d steps; one process per core; frames written "
+                                                "into an in-memory segment buffer (no file); ffmpeg binary absent, so "
+                                                "this is the restated reference work, not the ffmpeg child process"
+                                                % (ref_step, K)}, **desc),
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "native_so": "oracle/libvtoracle.so + libswscale (ctypes) + OpenCV; libvtseg.so is not loaded"}
+        print(json.dumps(line))
+    finally:
+        shutil.rmtree(tmpdir, ignore_errors=True)
+    return 0
+
+
+# ---- shared unit counter (control plane of the N-GPU arms) --------------------------------------------------------
+class UnitCounter:
+    """next() hands out 0, 1, 2, ... across all ranks: TCPStore.add on the process group's store (one small TCP round
+    trip to rank 0 per unit; no tensor, no collective)."""
+
+    def __init__(self, store, key: str):
+        self.store, self.key, self.local = store, key, 0
+
+    def next(self) -> int:
+        if self.store is None:
+            self.local += 1
+            return self.local - 1
+        return int(self.store.add(self.key, 1)) - 1
 
 
 def main():
@@ -216,72 +345,87 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample-frames", type=int, default=32768,
                     help="pictures the host-core baseline processes at N=1 (about 10 s of CPU work)")
-    ap.add_argument("--batch-frames", type=int, default=int(os.environ.get("VT_BENCH_BATCH", "32")),
-                    help="pictures per pipeline batch of the end-to-end arm")
+    ap.add_argument("--batch-frames", type=int, default=int(os.environ.get("VT_BENCH_BATCH", "64")),
+                    help="pictures per pipeline batch of the end-to-end arms")
     ap.add_argument("--cpu-step-frames", type=int, default=2048, help="pictures per step of --impl reference")
+    ap.add_argument("--min-timed-s", type=float, default=1.0, help="the device-resident timed region lasts at least this long")
     args = ap.parse_args()
     K, Wm = args.steps, max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     cores = len(os.sched_getaffinity(0))
-    tmpdir = tempfile.mkdtemp(prefix="vtbench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        from video_transformer_b200 import ops
-        from video_transformer_b200.ingest import SegmentIngestor  # noqa: F401  (index/payload helper only)
-        n_clip = 4 * STEP_FRAMES
-        path, idx, _ = make_clip(n_clip, tmpdir)
-        payload = _payload_for(idx, path)
-        dw = ops.scale_width_for_height(SRC_W, SRC_H, OUT_H)
-        arm = CpuArm(path, payload, idx.keyframe, SRC_W, SRC_H, dw, OUT_H, n_clip, cores)
-        ref_step = args.cpu_step_frames               # pictures per reference step (a bounded sample of the workload)
-        times = []
-        for s in range(Wm + K):
-            fps, dt, frames = arm.run(ref_step)
-            if s >= Wm:
-                times.append(dt)
-        arm.close()
-        total = sum(times)
-        value = ref_step * K / total
-        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
-                "warmup": Wm, "ms_per_step": 1000 * total / K, "step_pictures": ref_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": _config(dw, world),
-                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                                 "sample": "%d pictures per step, %d steps; libswscale bicubic + OpenCV SAD/hist + "
-                                           "C PCM re-layout, one process per core (ffmpeg binary absent)"
-                                           % (ref_step, K)},
-                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return 0
+        return run_reference(args, K, Wm, cores)
 
     import torch
     import torch.distributed as dist
     from ctypes import c_void_p
 
-    from video_transformer_b200 import _lib, ingest, ops
+    from video_transformer_b200 import _lib, container, ingest, landing, shard, video_segmenter
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    store = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        store = dist.distributed_c10d._get_default_store()
     L = _lib.lib()
 
-    n_clip = (Wm + K) * STEP_FRAMES
-    n_clip = min(n_clip, 16 * STEP_FRAMES)              # bounded clip; steps cycle through its chunks
-    path, idx, cuts = make_clip(n_clip, tmpdir)
-    n_chunks = n_clip // STEP_FRAMES
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- the clip: written once by rank 0 into /dev/shm, opened by every rank ---------------------------------------
+    box = [None]
+    if rank == 0:
+        box[0] = tempfile.mkdtemp(prefix="vtbench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)
+    workdir = box[0]
+    raw_path = os.path.join(workdir, "bench_1080p.h264")
+    mp4_path = os.path.join(workdir, "bench_1080p.mp4")
+    n_clip = CLIP_FRAMES
+    if rank == 0:
+        payload_gen, key_gen, cuts_truth = make_clip(n_clip, raw_path)
+        container.annexb_to_mp4(raw_path, mp4_path)
+        np.save(os.path.join(workdir, "cuts.npy"), np.asarray(cuts_truth, np.int64))
+    barrier()
+    cuts_truth = np.load(os.path.join(workdir, "cuts.npy")).tolist()
+    try:
+        return _run_ours(args, K, Wm, rank, world, local, cores, dev, store, L, barrier, workdir, raw_path, mp4_path,
+                         n_clip, cuts_truth, torch, dist, c_void_p, _lib, container, ingest, landing, shard,
+                         video_segmenter)
+    finally:
+        landing.release_all()
+        if world > 1:
+            try:
+                dist.barrier()
+            except Exception:  # noqa: BLE001
+                pass
+        if rank == 0:
+            shutil.rmtree(workdir, ignore_errors=True)
+        if world > 1:
+            dist.destroy_process_group()
+
+
+def _run_ours(args, K, Wm, rank, world, local, cores, dev, store, L, barrier, workdir, raw_path, mp4_path, n_clip,
+              cuts_truth, torch, dist, c_void_p, _lib, container, ingest, landing, shard, video_segmenter):
+    idx = container.probe(raw_path)
     opts = ingest.IngestOptions(target_height=OUT_H, batch_frames=args.batch_frames, device=str(dev))
     eng = ingest.SegmentIngestor(idx, opts)
     dw, dh, fb = eng.out_w, eng.out_h, eng.frame_bytes
+    n_chunks = n_clip // PASS_FRAMES
 
-    # ---- device-resident arm: whole bitstream in HBM, one step = decode + score + scale of 256 pictures ----------
-    host = np.memmap(path, dtype=np.uint8, mode="r")
+    # ---- device-resident arm: whole bitstream in HBM, one pass = decode + score + scale of 256 pictures -------------
+    host = np.memmap(raw_path, dtype=np.uint8, mode="r")
     bs_dev = torch.zeros(host.size + 64, dtype=torch.uint8, device=dev)
     bs_dev[:host.size].copy_(torch.from_numpy(np.array(host)))
-    F = STEP_FRAMES
+    F = PASS_FRAMES
     surf = torch.empty((F, eng.rows, eng.pitch), dtype=torch.uint8, device=dev)
     out = torch.empty((F, fb), dtype=torch.uint8, device=dev)
     sad = torch.empty(F, dtype=torch.int64, device=dev)
@@ -291,7 +435,7 @@ def main():
     names = ("decode", "score", "scale")
     ev = {n: [] for n in names}
 
-    def step(chunk: int, timed: bool):
+    def one_pass(chunk: int, timed: bool):
         b0 = chunk * F
         pay = eng.payload[b0:b0 + F].copy()              # absolute offsets: the whole stream is resident
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timed else None
@@ -312,14 +456,20 @@ def main():
             for i, n in enumerate(names):
                 ev[n].append((marks[i], marks[i + 1]))
 
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
     for s in range(max(Wm, 3)):
-        step(s % n_chunks, False)
+        one_pass(s % n_chunks, False)
+    torch.cuda.synchronize(dev)
+    # calibrate R (passes per step) so that K steps last >= min_timed_s; identical on every rank (max over ranks)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record(st)
+    for s in range(4):
+        one_pass(s % n_chunks, False)
+    c1.record(st)
+    torch.cuda.synchronize(dev)
+    pass_ms = torch.tensor([c0.elapsed_time(c1) / 4.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(pass_ms, op=dist.ReduceOp.MIN)
+    R = int(max(1, min(4096, np.ceil(args.min_timed_s * 1e3 / max(K, 1) / float(pass_ms[0])))))
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -327,115 +477,226 @@ def main():
     launches0 = L.vt_launch_count()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record(st)
+    q = 0
     for s in range(K):
-        step((Wm + s) % n_chunks, True)
+        for r in range(R):
+            one_pass(q % n_chunks, r == 0 or R <= 8)     # per-kernel events on the first pass of each step
+            q += 1
     t_end.record(st)
     barrier()
     launches = L.vt_launch_count() - launches0
     dev_ms = t_start.elapsed_time(t_end)
-    kern_ms = {n: sum(a.elapsed_time(b) for a, b in ev[n]) / K for n in names}
+    kern_ms = {n: sum(a.elapsed_time(b) for a, b in ev[n]) / len(ev[n]) for n in names}   # per 256-picture launch
+    clocks_dev = sampler.stop() if rank == 0 else None
+    del bs_dev, surf, out
 
-    # ---- end-to-end arm: host bytes -> pinned host frame buffers through SegmentIngestor.run ----------------------
-    sink = ingest.PinnedRing()
-    n_e2e = min(K, n_chunks) * F
-    reps = (K * F + n_e2e - 1) // n_e2e
-    eng.run(0, min(max(Wm, 1) * F, n_clip), sink)       # warm-up pass
-    barrier()
-    eng.h2d_bytes = eng.d2h_bytes = 0
+    # ---- end-to-end arm: the plugin call, units pulled from a shared counter ---------------------------------------
+    video_segmenter.configure(target_height=OUT_H, batch_frames=args.batch_frames, device=str(dev), frame_buffers=True)
+    unit_s = UNIT_PICTURES / FPS
+    n_windows = n_clip // UNIT_PICTURES
+    my_dir = os.path.join(workdir, "segments", "rank%d" % rank)
+    os.makedirs(my_dir, exist_ok=True)
+
+    def run_unit(u: int, slot: int):
+        j = u % n_windows
+        out_mp4 = os.path.join(my_dir, "segment_%04d.mp4" % slot)
+        ok = video_segmenter.extract_segment(input_path=mp4_path, start=j * unit_s, end=(j + 1) * unit_s,
+                                             output_path=out_mp4, stream_copy=True)
+        if not ok:
+            raise RuntimeError("extract_segment failed on unit %d" % u)
+        return out_mp4
+
     t0 = time.perf_counter()
-    done = 0
-    for r in range(reps):
-        cnt = min(n_e2e, K * F - done)
-        eng.run(0, cnt, sink)
-        done += cnt
+    first_out = run_unit(rank, 0)
+    cold_s = time.perf_counter() - t0
+    side = json.loads(open(first_out[:-4] + ".json").read())
+    assert side["frames"] == UNIT_PICTURES and side["frame_size"] == [dw, dh], side
+    landing_mode = side["landing"]
+    for wu in range(1, max(2, min(Wm, 4))):
+        run_unit(rank + wu, wu % 2)
+    barrier()
+    sampler2 = ClockSampler(local)
+    if rank == 0:
+        sampler2.start()
+    counter = UnitCounter(store, "vtbench_units_timed")
+    total_units = K * UNITS_PER_STEP * world
+    eng_plugin = video_segmenter._ENGINE_CACHE["engine"][1]
+    eng_plugin.h2d_bytes = eng_plugin.d2h_bytes = 0
+    barrier()
+    t0 = time.perf_counter()
+    my_units = 0
+    busy = 0.0
+    while True:
+        u = counter.next()
+        if u >= total_units:
+            break
+        tu = time.perf_counter()
+        run_unit(u, my_units % 2)
+        busy += time.perf_counter() - tu
+        my_units += 1
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
-    e2e_h2d, e2e_d2h = eng.h2d_bytes, eng.d2h_bytes
-    clocks = sampler.stop() if rank == 0 else None
-    barrier()
-    # the same pass with the frames handed over on the device (no D2H of frames): what a GPU-resident consumer sees
-    t0 = time.perf_counter()
-    done = 0
-    for r in range(reps):
-        cnt = min(n_e2e, K * F - done)
-        eng.run(0, cnt, None, device_sink=lambda chunk, k0: None)
-        done += cnt
-    torch.cuda.synchronize(dev)
-    dsink_s = time.perf_counter() - t0
+    timings = dict(video_segmenter.LAST_TIMINGS)
+    e2e_h2d, e2e_d2h = eng_plugin.h2d_bytes, eng_plugin.d2h_bytes
+    clocks_e2e = sampler2.stop() if rank == 0 else None
     barrier()
 
-    t = torch.tensor([dev_ms, e2e_s * 1000.0, dsink_s * 1000.0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max, dsink_ms_max = float(t[0]), float(t[1]), float(t[2])
-    if rank != 0:
+    # ---- concurrent D2H ceiling, measured in the same run: every rank copies 44 MB chunks into pinned memory at once --
+    chunk = 44 << 20
+    d_src = torch.empty(chunk, dtype=torch.uint8, device=dev)
+    h_dst = [torch.empty(chunk, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    s_copy = torch.cuda.Stream(dev)
+    with torch.cuda.stream(s_copy):
+        for i in range(4):
+            h_dst[i % 2].copy_(d_src, non_blocking=True)
+        s_copy.synchronize()
         if world > 1:
-            dist.destroy_process_group()
+            dist.barrier()
+        tc = time.perf_counter()
+        reps = 24
+        for i in range(reps):
+            h_dst[i % 2].copy_(d_src, non_blocking=True)
+        s_copy.synchronize()
+        ceil_gbs = reps * chunk / (time.perf_counter() - tc) / 1e9
+    del d_src, h_dst
+    barrier()
+
+    # ---- boundaries: shards pulled dynamically by all ranks, merged on rank 0, vs ONE single-GPU pass ---------------
+    piece = 240                                          # 8 GOPs per shard: 16 shards over the clip
+    pieces = [(a, min(a + piece, n_clip)) for a in range(0, n_clip, piece)]
+    counter2 = UnitCounter(store, "vtbench_units_cuts")
+    eng_sc = ingest.SegmentIngestor(idx, ingest.IngestOptions(target_height=OUT_H, batch_frames=args.batch_frames,
+                                                              keep_frames=False, device=str(dev)))
+    mine = []
+    while True:
+        u = counter2.next()
+        if u >= len(pieces):
+            break
+        a, b = pieces[u]
+        res = eng_sc.run(a, b, None)
+        mine.append((a, res.sad))
+    gathered = [None] * world
+    if world > 1:
+        dist.all_gather_object(gathered, mine)
+    else:
+        gathered = [mine]
+    cuts_equal = None
+    n_cuts = None
+    if rank == 0:
+        parts = [p for g in gathered for p in g]
+        _sad, _scores, cuts_n = shard.merge_and_score(parts, SRC_W, SRC_H, opts.scene_threshold)
+        single = eng_sc.run(0, n_clip, None)
+        cuts_equal = bool(np.array_equal(cuts_n, single.cuts) and set(cuts_truth) <= set(single.cuts.tolist()))
+        n_cuts = int(len(single.cuts))
+
+    # ---- engine API arm (N=1): SegmentIngestor.run into a pinned ring, no file ------------------------------------
+    eng_ms = None
+    if world == 1:
+        sink = ingest.PinnedRing()
+        eng.run(0, min(2 * PASS_FRAMES, n_clip), sink)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        n_eng = 0
+        for r in range(max(1, min(K, 4))):
+            eng.run(0, n_clip, sink)
+            n_eng += n_clip
+        torch.cuda.synchronize(dev)
+        eng_ms = (time.perf_counter() - t0) * 1e3
+
+    stats = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    per_rank = torch.tensor([float(my_units), busy, ceil_gbs, float(e2e_d2h), float(e2e_h2d)], dtype=torch.float64,
+                            device=dev)
+    all_rank = [torch.zeros_like(per_rank) for _ in range(world)]
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_gather(all_rank, per_rank)
+    else:
+        all_rank = [per_rank]
+    dev_ms_max, e2e_ms_max = float(stats[0]), float(stats[1])
+    if rank != 0:
         return 0
 
     peak, peak_kind = load_peaks()
     dominant = max(names, key=lambda n: kern_ms[n])
     alg = {"decode": BYTES_DECODE, "score": BYTES_SCORE, "scale": BYTES_SCALE}
     ach = {n: alg[n] * F / (kern_ms[n] * 1e-3) / 1e9 for n in names}
-    traffic = load_traffic()
-    value = world * K * F / (dev_ms_max * 1e-3)
-    e2e_value = world * K * F / (e2e_ms_max * 1e-3)
+    traffic, traffic_src = load_traffic()
+    dram = {n: (traffic[n] * F / (kern_ms[n] * 1e-3) / 1e9 if traffic and n in traffic else None) for n in names}
+    step_pictures = R * F
+    value = world * K * step_pictures / (dev_ms_max * 1e-3)
+    e2e_pictures = total_units * UNIT_PICTURES
+    e2e_value = e2e_pictures / (e2e_ms_max * 1e-3)
     segs_per_s = value / (720.0 * FPS)                   # shipped plan for 7200 s: 10 segments of 720 s
+    ranks = [{"rank": r, "units": int(t[0]), "busy_s": float(t[1]),
+              "d2h_gbs": float(t[3]) / float(t[1]) / 1e9 if float(t[1]) > 0 else 0.0,
+              "d2h_ceiling_gbs": float(t[2])} for r, t in enumerate(all_rank)]
+    ceiling_fps = sum(r["d2h_ceiling_gbs"] for r in ranks) * 1e9 / (fb + 1032)
+    fused_ms = kern_ms["score"] + kern_ms["scale"]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8", "data": "synthetic", "config": _config(dw, world),
+        "dtype": "u8", "data": "synthetic", "config": _config(dw, world, step_pictures, R),
+        "timed_region_s": dev_ms_max * 1e-3,
         "segments_per_sec": segs_per_s,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_h2d // max(K, 1),
-                "d2h_bytes_per_step": e2e_d2h // max(K, 1)},
-        "e2e_device_sink": {"value": world * K * F / (dsink_ms_max * 1e-3), "unit": UNIT,
-                            "note": "host bitstream in, frames consumed on the device (SegmentIngestor.run(device_sink=...)), "
-                                    "scores to host; not the contract's e2e"},
+        "e2e": {"value": e2e_value, "unit": UNIT,
+                "h2d_bytes_per_step": int(sum(float(t[4]) for t in all_rank) // max(K, 1)),
+                "d2h_bytes_per_step": int(sum(float(t[3]) for t in all_rank) // max(K, 1)),
+                "through": "video_segmenter.extract_segment (host MP4 in, faststart MP4 + .frames + .json on /dev/shm out)",
+                "pictures": e2e_pictures, "seconds": e2e_ms_max * 1e-3, "unit_pictures": UNIT_PICTURES,
+                "landing": landing_mode,
+                "last_call_ms": {k: round(v * 1e3, 2) for k, v in timings.items()}},
+        "e2e_cold": {"value": UNIT_PICTURES / cold_s, "unit": UNIT,
+                     "note": "first call of the process: index, plans, pinned staging, and a new landing file "
+                             "(allocate + cudaHostRegister, ~4 GB/s on this box) -- later calls recycle it"},
+        "e2e_ceiling": {"d2h_gbs_per_rank_concurrent": [r["d2h_ceiling_gbs"] for r in ranks],
+                        "frames_per_s": ceiling_fps, "e2e_of_ceiling": e2e_value / ceiling_fps if ceiling_fps else None,
+                        "note": "all ranks copy 44 MB chunks device -> pinned host at once, right after the timed arm; "
+                                "a picture costs frame_bytes + 1032 B of D2H"},
+        "per_rank": ranks,
+        "cuts_equal_single_gpu": cuts_equal, "cuts": n_cuts,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": ach[dominant], "peak": peak, "unit": "GB/s",
                      "frac": ach[dominant] / peak,
+                     "frac_dram": (dram[dominant] / peak if dram[dominant] else None),
                      "traffic": (traffic[dominant] * F if traffic and dominant in traffic else None),
-                     "traffic_source": "profiles/r01_traffic.json (ncu dram__bytes_read+write per launch of %d pictures)" % F,
+                     "traffic_source": "%s (ncu dram__bytes_read+write per launch of %d pictures)" % (traffic_src, F),
                      "algorithmic_bytes": alg[dominant] * F, "peak_source": peak_kind,
                      "frac_of_nominal_8000": ach[dominant] / 8000.0},
-        "kernels": {n: {"ms_per_step": kern_ms[n], "achieved_gbs": ach[n], "frac": ach[n] / peak,
-                        "alg_bytes_per_picture": alg[n]} for n in names},
-        "clocks": clocks,
+        "kernels": {n: {"ms_per_launch": kern_ms[n], "achieved_gbs": ach[n], "frac": ach[n] / peak,
+                        "frac_dram": (dram[n] / peak if dram[n] else None),
+                        "alg_bytes_per_picture": alg[n],
+                        "dram_bytes_per_picture": (traffic[n] if traffic and n in traffic else None)} for n in names},
+        "fused_c2": {"ms_per_launch": fused_ms, "alg_bytes_per_picture": BYTES_FUSED_C2,
+                     "frac": BYTES_FUSED_C2 * F / (fused_ms * 1e-3) / 1e9 / peak,
+                     "note": "score + scale against the fused-pass roofline (source luma counted once)"},
+        "clocks": clocks_dev, "clocks_e2e": clocks_e2e,
     }
+    if eng_ms is not None:
+        line["e2e_engine"] = {"value": n_eng / (eng_ms * 1e-3), "unit": UNIT,
+                              "note": "SegmentIngestor.run: host bitstream in, frames into a 3-slot pinned ring that is "
+                                      "overwritten (round 1's e2e); no file, no MP4"}
     if world == 1 and args.cpu_sample_frames > 0:
+        from oracle import coracle  # noqa: F401  (the CPU baseline leg: the one place bench.py may execute oracle/)
         payload = eng.payload
-        arm = CpuArm(path, payload, idx.keyframe, SRC_W, SRC_H, dw, dh, n_clip, cores)
+        arm = CpuArm(raw_path, payload, SRC_W, SRC_H, dw, dh, n_clip, cores)
         cfps, cdt, cframes = arm.run(args.cpu_sample_frames)
+        desc = arm.describe()
         arm.close()
-        line["cpu_baseline"] = {"value": cfps, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "%d pictures (the bench clip, wrapped) in %.1f s; libswscale bicubic + "
-                                          "OpenCV SAD/hist + C PCM re-layout, one process per core" % (cframes, cdt)}
+        line["cpu_baseline"] = dict({"value": cfps, "unit": UNIT, "cores": cores, "kind": "port",
+                                     "sample": "%d pictures (the bench clip, wrapped) in %.1f s; one process per core; "
+                                               "frames into an in-memory segment buffer (no file)" % (cframes, cdt)},
+                                    **desc)
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
     return 0
 
 
-def _payload_for(idx, path):
-    """Payload offsets of every picture (host-side index; no GPU needed)."""
-    import ctypes as C
-    from video_transformer_b200 import _lib
-    L = _lib.lib()
-    host = np.memmap(path, dtype=np.uint8, mode="r")
-    n = idx.n_frames
-    pay = np.zeros(n, np.uint64)
-    offs = np.ascontiguousarray(idx.nal_offsets, dtype=np.uint64)
-    sizes = np.ascontiguousarray(idx.nal_sizes, dtype=np.uint32)
-    _lib.check(L.vt_h264_pcm_layout(host.ctypes.data, host.size, offs.ctypes.data, sizes.ctypes.data, n,
-                                    pay.ctypes.data))
-    return pay
-
-
-def _config(dw, world):
+def _config(dw, world, step_pictures=None, passes=None):
     return {"workload": "configs[1]: synthetic 1920x1080@30 H.264 (I_PCM IDR / GOP 30 + P_Skip) -> %dx%d yuv420p "
                         "bicubic + SAD/hist + segment plan" % (dw, OUT_H),
-            "step_pictures": STEP_FRAMES, "l2": "inputs larger than L2 (step surfaces = 852 MB)",
-            "sharding": "1 process/GPU, GOP-aligned shards, no collective" if world > 1 else "single GPU",
+            "step_pictures": step_pictures, "passes_per_step": passes, "pass_pictures": PASS_FRAMES,
+            "l2": "inputs larger than L2 (surfaces of one pass = 852 MB; passes cycle through the clip)",
+            "sharding": ("one clip; 1 process/GPU pulls GOP-aligned units from a shared counter, no collective on the "
+                         "data path") if world > 1 else "single GPU",
             "bitstream": "I_PCM/P_Skip synthetic; entropy decode cost not representative of CABAC content",
             "nvdec": "unavailable on this pool (driver refuses video decode); decode = CUDA PCM-intra kernel"}
 

@@ -38,3 +38,30 @@ def frames_for_window(start, end, n_frames, fps_num, fps_den, keyframes=None, st
         if earlier:
             first = max(earlier)
     return (first, last)
+
+
+def boundary_frame(t, n_frames, fps_num, fps_den):
+    """First picture whose presentation time is >= t (n_frames when t lies past the last picture)."""
+    for k in range(n_frames):
+        if (k * float(fps_den)) / float(fps_num) >= t:
+            return k
+    return n_frames
+
+
+def snap_boundaries(boundaries_s, cuts, n_frames, fps_num, fps_den, tolerance_s):
+    """Boundary selection (the hook the reference leaves as a stub, src/utils/video_segmenter.py:157-159): every
+    planned boundary moves to the detected cut nearest in time within +-tolerance_s; on a tie the earlier cut wins;
+    without a cut in range the boundary keeps its time-plan picture."""
+    out = []
+    for t in boundaries_s:
+        t = float(t)
+        planned = boundary_frame(t, n_frames, fps_num, fps_den)
+        best, best_d, snapped = planned, None, False
+        for c in cuts:
+            ct = (int(c) * float(fps_den)) / float(fps_num)
+            d = abs(ct - t)
+            if d <= tolerance_s and (best_d is None or d < best_d):
+                best, best_d, snapped = int(c), d, True
+        out.append({"planned_time": t, "planned_frame": planned, "frame": best,
+                    "time": (best * float(fps_den)) / float(fps_num), "snapped": snapped})
+    return out

@@ -93,7 +93,13 @@ def ingest_video(video_path, temp_dir, config: dict | None = None, current_api_c
                 raise RuntimeError("extract_segment failed for %s segment %d" % (video_path, entry["id"]))
         side = seg.with_suffix(".json")
         if side.exists():
-            pictures += int(json.loads(side.read_text(encoding="utf-8")).get("frames", 0))
+            info = json.loads(side.read_text(encoding="utf-8"))
+            pictures += int(info.get("frames") or 0)
+            b = info.get("boundaries")
+            if b and (b.get("start_snapped") or b.get("end_snapped")):
+                # boundary selection moved this segment onto detected scene cuts (opt-in, ingest option
+                # snap_tolerance_s): recorded as extra keys, the reference's own keys keep their planned values
+                entry["snapped_start"], entry["snapped_end"] = b["start"], b["end"]
         done += 1
     # statuses stay "pending": the analyzer owns the status machine (processing/completed) when it runs later
     video_segmenter.save_manifest(mpath, manifest)

@@ -152,7 +152,7 @@ class SegmentIngestor:
                 "bs_dev": torch.empty(self.bs_cap + 64, dtype=torch.uint8, device=self.dev),
                 "surf": torch.empty((B, self.rows, self.pitch), dtype=torch.uint8, device=self.dev),
                 "out": torch.empty((B, self.frame_bytes), dtype=torch.uint8, device=self.dev),
-                "out_host": torch.empty((B, self.frame_bytes), dtype=torch.uint8, pin_memory=True),
+                "out_host": None,        # pinned frames, allocated on first use: the direct landing never needs it
                 "sel_surf": (torch.empty((B, self.rows, self.pitch), dtype=torch.uint8, device=self.dev)
                              if self.opts.sample_every > 1 else None),
                 "sel_idx": torch.empty(B, dtype=torch.int32, device=self.dev),
@@ -379,6 +379,8 @@ class SegmentIngestor:
                         landing.tensor[landed * fb:(landed + cnt) * fb].view(cnt, fb).copy_(
                             slot["out"][row0:row0 + cnt], non_blocking=True)
                     else:
+                        if slot["out_host"] is None:
+                            slot["out_host"] = torch.empty((B, fb), dtype=torch.uint8, pin_memory=True)
                         slot["out_host"][row0:row0 + cnt].copy_(slot["out"][row0:row0 + cnt], non_blocking=True)
                         if land_staged:
                             slot["land"] = (landed, cnt, row0)

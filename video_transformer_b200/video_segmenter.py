@@ -71,6 +71,10 @@ _OPTIONS = {
     "rgb_size": None,          # (width, height) of the RGB output, e.g. (768, 768)
     "sample_every": 1,         # keep pictures whose index is a multiple of this (30 = 1 fps at 30 fps)
     "device": "cuda",
+    # Boundary selection (K4), opt-in: > 0 moves a requested start/end to the detected scene cut nearest in time within
+    # this many seconds (a score-only GPU pass over the two windows finds the cuts).  0 keeps the reference's times, so
+    # plans and manifests stay value-identical by default.
+    "snap_tolerance_s": 0.0,
 }
 
 
@@ -171,6 +175,7 @@ def _sidecar_path(mp4: Path) -> Path:
 
 _INDEX_CACHE: dict = {}
 _ENGINE_CACHE: dict = {}
+LAST_TIMINGS: dict = {}          # seconds spent in the stages of the most recent extract_segment call (diagnostics)
 
 
 def _file_key(path: Path):
@@ -197,11 +202,20 @@ def _probe_cached(path: Path):
 
 
 def _cut(src: Path, start: float, end: float, dst: Path, stream_copy: bool) -> bool:
+    import time
     from . import container, isobmff, scene
+    t_begin = time.perf_counter()
+    LAST_TIMINGS.clear()
     idx = _probe_cached(src)
     if idx is None or idx.n_frames == 0:
         return False
     times = _picture_times(idx)
+    snapped = None
+    if _OPTIONS["snap_tolerance_s"] > 0 and _OPTIONS["frame_buffers"]:
+        snapped = _snap_window(idx, times, start, end, float(_OPTIONS["snap_tolerance_s"]))
+        if snapped is not None:
+            start, end = snapped["start"], snapped["end"]
+    LAST_TIMINGS["snap"] = time.perf_counter() - t_begin
     if idx.kind == "h264":
         # raw Annex-B elementary stream (the synthetic clips): one slice NAL per picture, wrapped into a new MP4
         if idx.fps_num <= 0:
@@ -249,6 +263,7 @@ def _cut(src: Path, start: float, end: float, dst: Path, stream_copy: bool) -> b
                 kwargs = {"stream_copy": True, "accurate_presentation": True, "selection": (first, last, first_acc)}
         # the stream copy (file -> file, inside the kernel) runs beside the GPU pass
         copier = _Background(isobmff.cut_movie, movie, start, end, dst, **kwargs)
+    LAST_TIMINGS["index"] = time.perf_counter() - t_begin
     try:
         if _OPTIONS["frame_buffers"]:
             reason = None
@@ -259,12 +274,18 @@ def _cut(src: Path, start: float, end: float, dst: Path, stream_copy: bool) -> b
                 reason = ("H.264 stream uses coding tools outside the PCM-intra subset K0 decodes; NVDEC is not "
                           "available on this host")
             if reason is None:
-                _ingest_to_files(idx, first, last, dst)
+                _ingest_to_files(idx, first, last, dst, snapped)
             else:                               # the stream copy needs no decode: the cut stands, the pixel pass is skipped
                 _write_sidecar(dst, idx, first, last, None, reason)
                 log.info("event=segment_pixel_pass_skipped reason=%s", reason)
     finally:
+        t_pix = time.perf_counter()
         res = copier.result() if copier is not None else True
+        LAST_TIMINGS["pixel_pass"] = t_pix - t_begin - LAST_TIMINGS["index"]
+        LAST_TIMINGS["wait_for_stream_copy"] = time.perf_counter() - t_pix
+        if copier is not None:
+            LAST_TIMINGS["stream_copy"] = copier.seconds
+        LAST_TIMINGS["total"] = time.perf_counter() - t_begin
     return res is not None and res is not False
 
 
@@ -276,11 +297,16 @@ class _Background:
         self._out = None
         self._exc = None
 
+        self.seconds = 0.0
+
         def body():
+            import time
+            t0 = time.perf_counter()
             try:
                 self._out = fn(*args, **kwargs)
             except BaseException as e:  # noqa: BLE001
                 self._exc = e
+            self.seconds = time.perf_counter() - t0
 
         self._t = threading.Thread(target=body, daemon=True)
         self._t.start()
@@ -292,25 +318,63 @@ class _Background:
         return self._out
 
 
-def _engine_for(idx):
+def _engine_for(idx, keep_frames: bool = True):
     """SegmentIngestor for (file, options), kept across calls: the segments of one video share plans, pinned staging
-    and device buffers."""
+    and device buffers.  keep_frames=False is the score-only engine of the boundary selection."""
     from . import ingest
     key = (_file_key(idx.path), tuple(sorted((k, str(v)) for k, v in _OPTIONS.items())))
-    eng = _ENGINE_CACHE.get("engine")
+    slot = "engine" if keep_frames else "engine_scores"
+    eng = _ENGINE_CACHE.get(slot)
     if eng is not None and eng[0] == key:
         return eng[1]
-    _ENGINE_CACHE.clear()
+    _ENGINE_CACHE.pop(slot, None)
     opts = ingest.IngestOptions(target_height=_OPTIONS["target_height"], sws_flags=_OPTIONS["sws_flags"],
                                 batch_frames=_OPTIONS["batch_frames"], scene_threshold=_OPTIONS["scene_threshold"],
                                 output=_OPTIONS["output"], rgb_size=_OPTIONS["rgb_size"],
-                                sample_every=_OPTIONS["sample_every"], device=_OPTIONS["device"])
+                                sample_every=_OPTIONS["sample_every"], device=_OPTIONS["device"],
+                                keep_frames=keep_frames)
     engine = ingest.SegmentIngestor(idx, opts)
-    _ENGINE_CACHE["engine"] = (key, engine)
+    _ENGINE_CACHE[slot] = (key, engine)
     return engine
 
 
-def _ingest_to_files(idx, first: int, last: int, dst: Path) -> None:
+def _snap_window(idx, times: np.ndarray, start: float, end: float, tol: float):
+    """Boundary selection for one extract window: score the pictures within +-tol of each requested boundary (K3 on the
+    GPU, frames not kept), select cuts (K4) and move the boundary to the nearest one.  Boundaries at the very start or
+    end of the stream stay.  Returns {"start", "end", "start_snapped", "end_snapped", ...} or None when the stream is
+    not decodable here (then nothing moves)."""
+    from . import container, scene
+    if idx.kind == "mp4" and not (idx.extra.get("decodable") and container.classify_pcm(idx)):
+        return None
+    if idx.kind == "h264" and not idx.extra.get("pcm_intra_only"):
+        return None
+    if idx.fps_num <= 0 or idx.extra.get("times") is not None:
+        return None                                   # the snap rule is defined on the constant-rate picture grid
+    eng = _engine_for(idx, keep_frames=False)
+    n = idx.n_frames
+    out = {"requested_start": float(start), "requested_end": float(end), "start": float(start), "end": float(end),
+           "start_snapped": False, "end_snapped": False, "tolerance_s": tol}
+    last_t = float(times[-1])
+    for name, t in (("start", float(start)), ("end", float(end))):
+        if t <= 0.0 or t > last_t:
+            continue
+        a = int(np.searchsorted(times, t - tol, side="left"))
+        b = int(np.searchsorted(times, t + tol, side="right"))
+        a, b = max(a, 0), min(b, n)
+        if b <= a:
+            continue
+        res = eng.run(a, b, None)
+        rec = scene.snap_boundaries([t], res.cuts, n, idx.fps_num, idx.fps_den, tol)[0]
+        if rec["snapped"]:
+            out[name] = rec["time"]
+            out[name + "_snapped"] = True
+            out[name + "_frame"] = rec["frame"]
+    if out["end"] <= out["start"]:
+        return None
+    return out
+
+
+def _ingest_to_files(idx, first: int, last: int, dst: Path, snapped=None) -> None:
     """GPU pass for pictures [first,last): writes <dst>.frames and <dst>.json.  Raises on any failure."""
     from . import landing
     eng = _engine_for(idx)
@@ -322,12 +386,12 @@ def _ingest_to_files(idx, first: int, last: int, dst: Path) -> None:
     except BaseException:
         land.abort()
         raise
-    _write_sidecar(dst, idx, first, last, res, None, eng.opts, land)
+    _write_sidecar(dst, idx, first, last, res, None, eng.opts, land, snapped)
     log.info("event=segment_ingest frames=%d size=%dx%d cuts=%d landing=%s", res.stats["landed_frames"],
              res.out_width, res.out_height, len(res.cuts), res.stats["landing"])
 
 
-def _write_sidecar(dst: Path, idx, first: int, last: int, res, reason, opts=None, land=None) -> None:
+def _write_sidecar(dst: Path, idx, first: int, last: int, res, reason, opts=None, land=None, snapped=None) -> None:
     side = {"source": str(idx.path), "first_picture": first, "last_picture": last,
             "fps": [idx.fps_num, idx.fps_den], "source_size": [idx.width, idx.height],
             "codec": idx.extra.get("codec", "h264")}
@@ -342,6 +406,8 @@ def _write_sidecar(dst: Path, idx, first: int, last: int, res, reason, opts=None
             "scene_threshold": opts.scene_threshold, "cuts": res.cuts.tolist(),
             "sad": res.sad.tolist(), "score": res.scores.tolist(),
         })
+    if snapped is not None:
+        side["boundaries"] = snapped
     _sidecar_path(dst).write_text(json.dumps(side), encoding="utf-8")
 
 
