@@ -349,6 +349,8 @@ def main():
                     help="pictures per pipeline batch of the end-to-end arms")
     ap.add_argument("--cpu-step-frames", type=int, default=2048, help="pictures per step of --impl reference")
     ap.add_argument("--min-timed-s", type=float, default=1.0, help="the device-resident timed region lasts at least this long")
+    ap.add_argument("--diag", action="store_true", help="also time the engine API with a pinned ring / a direct landing on "
+                    "every rank at once (which part of the plugin call limits multi-GPU scaling)")
     args = ap.parse_args()
     K, Wm = args.steps, max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
@@ -560,6 +562,34 @@ def _run_ours(args, K, Wm, rank, world, local, cores, dev, store, L, barrier, wo
         ceil_gbs = reps * chunk / (time.perf_counter() - tc) / 1e9
     del d_src, h_dst
     barrier()
+    # ---- concurrent file-write ceiling of the box: every rank stream-copies UNIT-sized byte ranges of the clip at once
+    # (the MP4 half of extract_segment is a file -> file copy of the unit's samples; the synthetic bitstream is
+    # uncompressed, ~115 KB per picture, so this path carries far more bytes than a real H.264 stream would) ---------
+    unit_bytes = int(idx.nal_offsets[min(UNIT_PICTURES, n_clip - 1)] - idx.nal_offsets[0])
+    probe_out = os.path.join(my_dir, "write_probe.bin")
+    fi = os.open(raw_path, os.O_RDONLY)
+    fo = os.open(probe_out, os.O_RDWR | os.O_CREAT, 0o644)
+
+    def copy_once():
+        done = 0
+        while done < unit_bytes:
+            done += os.copy_file_range(fi, fo, unit_bytes - done, done, done)
+
+    try:
+        copy_once()
+        if world > 1:
+            dist.barrier()
+        tw = time.perf_counter()
+        for _ in range(3):
+            copy_once()
+        write_gbs = 3 * unit_bytes / (time.perf_counter() - tw) / 1e9
+    except (OSError, AttributeError):
+        write_gbs = 0.0
+    os.close(fi)
+    os.close(fo)
+    os.unlink(probe_out)
+    bytes_per_picture_bs = unit_bytes / UNIT_PICTURES
+    barrier()
 
     # ---- boundaries: shards pulled dynamically by all ranks, merged on rank 0, vs ONE single-GPU pass ---------------
     piece = 240                                          # 8 GOPs per shard: 16 shards over the clip
@@ -589,6 +619,24 @@ def _run_ours(args, K, Wm, rank, world, local, cores, dev, store, L, barrier, wo
         cuts_equal = bool(np.array_equal(cuts_n, single.cuts) and set(cuts_truth) <= set(single.cuts.tolist()))
         n_cuts = int(len(single.cuts))
 
+    diag = None
+    if args.diag:
+        diag = {}
+        for name in ("engine_pinned_ring", "engine_direct_landing"):
+            land = landing.acquire(os.path.join(my_dir, "diag.frames"), UNIT_PICTURES * fb) if "landing" in name else None
+            eng.run(0, UNIT_PICTURES, ingest.PinnedRing() if land is None else None, landing=land)
+            barrier()
+            t0 = time.perf_counter()
+            for r in range(6):
+                a = (r % n_windows) * UNIT_PICTURES
+                eng.run(a, a + UNIT_PICTURES, ingest.PinnedRing() if land is None else None, landing=land)
+            torch.cuda.synchronize(dev)
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            diag[name] = world * 6 * UNIT_PICTURES / float(dt[0])
+            barrier()
+
     # ---- engine API arm (N=1): SegmentIngestor.run into a pinned ring, no file ------------------------------------
     eng_ms = None
     if world == 1:
@@ -604,7 +652,7 @@ def _run_ours(args, K, Wm, rank, world, local, cores, dev, store, L, barrier, wo
         eng_ms = (time.perf_counter() - t0) * 1e3
 
     stats = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    per_rank = torch.tensor([float(my_units), busy, ceil_gbs, float(e2e_d2h), float(e2e_h2d)], dtype=torch.float64,
+    per_rank = torch.tensor([float(my_units), busy, ceil_gbs, float(e2e_d2h), float(e2e_h2d), write_gbs], dtype=torch.float64,
                             device=dev)
     all_rank = [torch.zeros_like(per_rank) for _ in range(world)]
     if world > 1:
@@ -629,8 +677,10 @@ def _run_ours(args, K, Wm, rank, world, local, cores, dev, store, L, barrier, wo
     segs_per_s = value / (720.0 * FPS)                   # shipped plan for 7200 s: 10 segments of 720 s
     ranks = [{"rank": r, "units": int(t[0]), "busy_s": float(t[1]),
               "d2h_gbs": float(t[3]) / float(t[1]) / 1e9 if float(t[1]) > 0 else 0.0,
-              "d2h_ceiling_gbs": float(t[2])} for r, t in enumerate(all_rank)]
+              "d2h_ceiling_gbs": float(t[2]), "file_copy_ceiling_gbs": float(t[5])} for r, t in enumerate(all_rank)]
     ceiling_fps = sum(r["d2h_ceiling_gbs"] for r in ranks) * 1e9 / (fb + 1032)
+    write_fps = sum(r["file_copy_ceiling_gbs"] for r in ranks) * 1e9 / bytes_per_picture_bs
+    binding = min(ceiling_fps, write_fps) if write_fps > 0 else ceiling_fps
     fused_ms = kern_ms["score"] + kern_ms["scale"]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
@@ -649,9 +699,15 @@ def _run_ours(args, K, Wm, rank, world, local, cores, dev, store, L, barrier, wo
                      "note": "first call of the process: index, plans, pinned staging, and a new landing file "
                              "(allocate + cudaHostRegister, ~4 GB/s on this box) -- later calls recycle it"},
         "e2e_ceiling": {"d2h_gbs_per_rank_concurrent": [r["d2h_ceiling_gbs"] for r in ranks],
-                        "frames_per_s": ceiling_fps, "e2e_of_ceiling": e2e_value / ceiling_fps if ceiling_fps else None,
-                        "note": "all ranks copy 44 MB chunks device -> pinned host at once, right after the timed arm; "
-                                "a picture costs frame_bytes + 1032 B of D2H"},
+                        "d2h_frames_per_s": ceiling_fps,
+                        "file_copy_gbs_per_rank_concurrent": [r["file_copy_ceiling_gbs"] for r in ranks],
+                        "file_copy_frames_per_s": write_fps, "bitstream_bytes_per_picture": bytes_per_picture_bs,
+                        "frames_per_s": binding, "binding": "d2h" if binding == ceiling_fps else "file_copy",
+                        "e2e_of_ceiling": e2e_value / binding if binding else None,
+                        "note": "measured right after the timed arm, all ranks at once: (a) 44 MB chunks device -> pinned "
+                                "host (a picture costs frame_bytes + 1032 B of D2H); (b) copy_file_range of one unit's "
+                                "samples on /dev/shm (the stream-copy half of the call; the synthetic bitstream is "
+                                "uncompressed PCM).  The lower of the two bounds the plugin call on this box."},
         "per_rank": ranks,
         "cuts_equal_single_gpu": cuts_equal, "cuts": n_cuts,
         "gpu_launches": int(launches),
@@ -671,6 +727,8 @@ def _run_ours(args, K, Wm, rank, world, local, cores, dev, store, L, barrier, wo
                      "note": "score + scale against the fused-pass roofline (source luma counted once)"},
         "clocks": clocks_dev, "clocks_e2e": clocks_e2e,
     }
+    if diag is not None:
+        line["diag_frames_per_s"] = diag
     if eng_ms is not None:
         line["e2e_engine"] = {"value": n_eng / (eng_ms * 1e-3), "unit": UNIT,
                               "note": "SegmentIngestor.run: host bitstream in, frames into a 3-slot pinned ring that is "
