@@ -349,6 +349,9 @@ def main():
                     help="pictures per pipeline batch of the end-to-end arms")
     ap.add_argument("--cpu-step-frames", type=int, default=2048, help="pictures per step of --impl reference")
     ap.add_argument("--min-timed-s", type=float, default=1.0, help="the device-resident timed region lasts at least this long")
+    ap.add_argument("--workload", default="config1", choices=["config1", "config3"],
+                    help="config1 = BASELINE.json configs[1] (the contract's line); config3 = configs[3], a URL.txt-style batch "
+                         "of 64 synthetic 720p clips through batch.ingest_batch_dynamic (its own JSON line)")
     ap.add_argument("--diag", action="store_true", help="also time the engine API with a pinned ring / a direct landing on "
                     "every rank at once (which part of the plugin call limits multi-GPU scaling)")
     args = ap.parse_args()
@@ -399,6 +402,8 @@ def main():
     barrier()
     cuts_truth = np.load(os.path.join(workdir, "cuts.npy")).tolist()
     try:
+        if args.workload == "config3":
+            return _run_config3(args, rank, world, local, dev, barrier, workdir, torch, dist, video_segmenter)
         return _run_ours(args, K, Wm, rank, world, local, cores, dev, store, L, barrier, workdir, raw_path, mp4_path,
                          n_clip, cuts_truth, torch, dist, c_void_p, _lib, container, ingest, landing, shard,
                          video_segmenter)
@@ -745,6 +750,62 @@ def _run_ours(args, K, Wm, rank, world, local, cores, dev, store, L, barrier, wo
                                                "frames into an in-memory segment buffer (no file)" % (cframes, cdt)},
                                     **desc)
     print(json.dumps(line))
+    return 0
+
+
+def _run_config3(args, rank, world, local, dev, barrier, workdir, torch, dist, video_segmenter):
+    """BASELINE.json configs[3]: 64 synthetic 720p clips, per-video dynamic queue over the ranks (atomic claims on the
+    file system), every clip probed, planned, cut and ingested through the plugin's functions."""
+    from video_transformer_b200 import batch, container, synth
+    n_clips, n_pic, w, h = 64, 300, 1280, 720
+    clips_dir = os.path.join(workdir, "clips")
+    if rank == 0:
+        os.makedirs(clips_dir, exist_ok=True)
+        bs, _meta = synth.make_testsrc_h264(w, h, n_pic, fps=30, gop=30, cuts=[97, 211])
+        raw = os.path.join(clips_dir, "clip.h264")
+        open(raw, "wb").write(bs)
+        first = os.path.join(clips_dir, "clip_00.mp4")
+        container.annexb_to_mp4(raw, first)
+        os.unlink(raw)
+        for i in range(1, n_clips):
+            shutil.copyfile(first, os.path.join(clips_dir, "clip_%02d.mp4" % i))
+    barrier()
+    vids = [os.path.join(clips_dir, "clip_%02d.mp4" % i) for i in range(n_clips)]
+    video_segmenter.configure(target_height=OUT_H, batch_frames=args.batch_frames, device=str(dev), frame_buffers=True)
+    # warm-up on a private copy (engine, plans, landing files of this size)
+    warm = os.path.join(workdir, "warm_rank%d.mp4" % rank)
+    shutil.copyfile(vids[0], warm)
+    batch.ingest_video(warm, os.path.join(workdir, "warm_temp_%d" % rank))
+    barrier()
+    t0 = time.perf_counter()
+    rep = batch.ingest_batch_dynamic(vids, os.path.join(workdir, "temp"), rank=rank, world=world)
+    torch.cuda.synchronize(dev)
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([float(rep.pictures), float(rep.segments_done), float(len(rep.processed)), float(len(rep.failed))],
+                       dtype=torch.float64, device=dev)
+    per = [torch.zeros_like(cnt) for _ in range(world)]
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dist.all_gather(per, cnt)
+    else:
+        per = [cnt]
+    if rank == 0:
+        merged = batch.merge_progress(os.path.join(workdir, "temp"), world)
+        pictures = sum(float(t[0]) for t in per)
+        segs = sum(float(t[1]) for t in per)
+        print(json.dumps({
+            "metric": METRIC, "workload": "configs[3]", "value": pictures / float(dt[0]), "unit": UNIT,
+            "segments_per_sec": segs / float(dt[0]), "videos_per_sec": n_clips / float(dt[0]), "n_gpus": world,
+            "seconds": float(dt[0]), "pictures": int(pictures), "segments": int(segs),
+            "videos_per_rank": [int(t[2]) for t in per], "failed": int(sum(float(t[3]) for t in per)),
+            "progress_json_processed": len(merged["processed"]),
+            "config": {"workload": "configs[3]: %d synthetic %dx%d@30 clips of %d pictures (I_PCM IDR / GOP 30 + P_Skip), "
+                                   "same-height sources are converted NV12 -> YUV420P (not resized) + SAD/hist, one "
+                                   "segment each; probe -> budget plan -> manifest -> extract_segment per clip"
+                                   % (n_clips, w, h, n_pic),
+                       "sharding": "per video, dynamic: ranks claim clips longest-first with O_EXCL files, no collective",
+                       "e2e": "wall clock over batch.ingest_batch_dynamic, host MP4 in, MP4 + .frames + .json out"},
+            "data": "synthetic", "dtype": "u8"}))
     return 0
 
 

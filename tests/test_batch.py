@@ -70,3 +70,68 @@ def test_ingest_batch_on_gpu(cuda, tmp_path):
     side = json.loads(seg.with_suffix(".json").read_text())
     assert side["frames"] == 30 and side["frame_size"] == [160, 120]
     assert np.fromfile(seg.with_suffix(".frames"), np.uint8).size == 30 * 160 * 120 * 3 // 2
+
+
+def test_dynamic_queue_claims_each_video_once_across_processes(tmp_path):
+    """Two worker processes (one per GPU in production) pull from the same list: every video is ingested exactly once,
+    and the merged progress.json has the reference's schema.  frame_buffers off: host logic only."""
+    import multiprocessing as mp
+    vids = [str(_write_clip(tmp_path / ("q%02d.mp4" % i), 64, 48, 20 + 10 * (i % 3), 10)) for i in range(7)]
+    tmp = tmp_path / "temp"
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(2) as pool:
+        reps = pool.starmap(_dynamic_worker, [(vids, str(tmp), r) for r in range(2)])
+    done = sorted(v for rep in reps for v in rep["processed"])
+    assert done == sorted("q%02d" % i for i in range(7))
+    assert all(not rep["failed"] for rep in reps)
+    merged = batch.merge_progress(tmp, 2)
+    assert sorted(merged["processed"]) == done
+    for i in range(7):
+        seg = video_segmenter.get_segment_dir("q%02d" % i, tmp) / "segment_0000.mp4"
+        assert seg.exists() and container.probe(seg).n_frames == 20 + 10 * (i % 3)
+
+
+def _dynamic_worker(vids, tmp, rank):
+    from video_transformer_b200 import batch as b, video_segmenter as vs
+    vs.configure(frame_buffers=False)
+    rep = b.ingest_batch_dynamic(vids, tmp, rank=rank, world=2)
+    return {"processed": rep.processed, "failed": rep.failed}
+
+
+def test_scheduler_overlaps_ingest_with_analysis(tmp_path, monkeypatch):
+    """process_batch_overlapped: while video i is 'with the remote model' (a stub that sleeps), video i+1 is being
+    pre-ingested; the analysis of every video starts only after its own segments are in place."""
+    import threading
+    import time
+    vids = [_write_clip(tmp_path / ("s%d.mp4" % i), 64, 48, 30, 10) for i in range(4)]
+    events = []
+    lock = threading.Lock()
+
+    def slow_extract(*, input_path, start, end, output_path, stream_copy=True):
+        with lock:
+            events.append(("ingest_begin", input_path.stem, time.perf_counter()))
+        time.sleep(0.15)
+        output_path.parent.mkdir(parents=True, exist_ok=True)
+        output_path.write_bytes(b"x")
+        with lock:
+            events.append(("ingest_end", input_path.stem, time.perf_counter()))
+        return True
+
+    monkeypatch.setattr(video_segmenter, "extract_segment", slow_extract)
+
+    def analyze(p):
+        with lock:
+            events.append(("analyze_begin", p.stem, time.perf_counter()))
+        time.sleep(0.15)
+        seg = video_segmenter.get_segment_dir(p.stem, tmp_path / "temp") / "segment_0000.mp4"
+        return seg.exists()
+
+    t0 = time.perf_counter()
+    res = batch.process_batch_overlapped(vids, tmp_path / "temp", analyze)
+    elapsed = time.perf_counter() - t0
+    assert res == [True] * 4
+    t = {(k, v): ts for k, v, ts in events}
+    for i in range(4):
+        assert t[("ingest_end", "s%d" % i)] <= t[("analyze_begin", "s%d" % i)]
+    assert t[("ingest_begin", "s1")] < t[("analyze_begin", "s0")] + 0.15       # s1 was being ingested during s0's analysis
+    assert elapsed < 4 * 0.30 - 0.2                                              # overlapped: well under the serial time

@@ -138,6 +138,130 @@ def ingest_batch(video_paths, temp_dir, *, rank: int | None = None, world: int |
     return rep
 
 
+# ---- dynamic per-video queue and the overlapped batch loop ----------------------------------------------------------
+def _claim(temp_dir: Path, video_id: str, rank: int) -> bool:
+    """Atomically claim a video for this rank (O_EXCL create of temp_dir/claims/<video_id>): the shared queue of the
+    N worker processes is the file system, no collective and no server."""
+    d = temp_dir / "claims"
+    d.mkdir(parents=True, exist_ok=True)
+    try:
+        fd = os.open(d / (video_id + ".claim"), os.O_CREAT | os.O_EXCL | os.O_WRONLY, 0o644)
+    except FileExistsError:
+        return False
+    os.write(fd, str(rank).encode())
+    os.close(fd)
+    return True
+
+
+def ingest_batch_dynamic(video_paths, temp_dir, *, rank: int | None = None, world: int | None = None,
+                         config: dict | None = None, on_done=None) -> BatchReport:
+    """Like ingest_batch, but ranks PULL videos (longest first) instead of owning a static share: a rank behind a slow
+    host link or with longer videos simply claims fewer.  Every rank walks the same order and claims atomically.
+    on_done(video_id, ok) is called after each video this rank ingested (the scheduler's hand-off)."""
+    rank = int(os.environ.get("RANK", "0")) if rank is None else rank
+    world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else world
+    temp_dir = Path(temp_dir)
+    paths = [str(p) for p in video_paths]
+    counts = []
+    for p in paths:
+        idx = container.probe(Path(p))
+        counts.append(int(idx.n_frames) if idx is not None else 0)
+    order = sorted(range(len(paths)), key=lambda k: (-counts[k], k))
+    rep = BatchReport(rank=rank, world=world)
+    ppath = _progress_path(temp_dir, rank)
+    prog = _load_progress(ppath)
+    for i in order:
+        vid = Path(paths[i]).stem
+        if not _claim(temp_dir, vid, rank):
+            continue
+        rep.assigned.append(paths[i])
+        ok = True
+        try:
+            done, pics = ingest_video(paths[i], temp_dir, config)
+            rep.segments_done += done
+            rep.pictures += pics
+            rep.processed.append(vid)
+            prog["processed"].append(vid)
+            prog["failed"].pop(vid, None)
+        except Exception as exc:  # noqa: BLE001 - one bad video must not stop the batch (pipeline.py:340-359)
+            ok = False
+            log.warning("event=batch_ingest_failed video=%s error=%s", vid, exc)
+            rep.failed[vid] = str(exc)
+            prog["failed"][vid] = {"error": str(exc), "timestamp": datetime.now().isoformat()}
+        _save_progress(ppath, prog)
+        if on_done is not None:
+            on_done(vid, ok)
+    _save_progress(ppath, prog)
+    return rep
+
+
+class IngestScheduler:
+    """Pre-ingests a list of videos on a worker thread while the caller analyses earlier ones.
+
+    The reference's batch loop (/root/reference/src/pipeline.py:361-396) handles one video at a time: probe, cut, upload,
+    wait for the remote model, next video -- the GPU would idle during every remote call.  Here the local half (probe,
+    plan, manifest, cut + GPU pass of every segment) of video i+1 runs while video i is with the remote model; when the
+    unmodified analyzer reaches video i+1 it finds every segment file present and skips extraction
+    (/root/reference/src/analyzer/content_analyzer.py:749).  Several processes (one per GPU) may run a scheduler over
+    the same list: videos are claimed atomically, whoever is free takes the next one."""
+
+    def __init__(self, video_paths, temp_dir, *, rank: int | None = None, world: int | None = None,
+                 config: dict | None = None):
+        import threading
+        self.paths = [str(p) for p in video_paths]
+        self.temp_dir = Path(temp_dir)
+        self.rank, self.world, self.config = rank, world, config
+        self._done: dict[str, bool] = {}
+        self._cv = threading.Condition()
+        self._finished = False
+        self.report: BatchReport | None = None
+        self._thread = threading.Thread(target=self._work, daemon=True)
+
+    def start(self) -> "IngestScheduler":
+        self._thread.start()
+        return self
+
+    def _work(self) -> None:
+        def on_done(vid, ok):
+            with self._cv:
+                self._done[vid] = ok
+                self._cv.notify_all()
+        try:
+            self.report = ingest_batch_dynamic(self.paths, self.temp_dir, rank=self.rank, world=self.world,
+                                               config=self.config, on_done=on_done)
+        finally:
+            with self._cv:
+                self._finished = True
+                self._cv.notify_all()
+
+    def wait(self, video_path, timeout: float | None = None) -> bool:
+        """Block until this video's pre-ingest has finished here.  True when its segments are in place; False when it
+        failed, was claimed by another process, or the timeout expired (the analyzer then cuts on demand, as the
+        reference does)."""
+        vid = Path(video_path).stem
+        with self._cv:
+            self._cv.wait_for(lambda: vid in self._done or self._finished, timeout)
+            return bool(self._done.get(vid, False))
+
+    def join(self) -> BatchReport | None:
+        self._thread.join()
+        return self.report
+
+
+def process_batch_overlapped(video_paths, temp_dir, analyze, *, config: dict | None = None,
+                             rank: int | None = None, world: int | None = None) -> list:
+    """The reference's batch loop with the ingest of later videos overlapped: for each video in order, wait for its
+    pre-ingest, then call analyze(video_path) (in the reference: VideoPipeline.process_single_video -> the analyzer's
+    segment loop -> remote model).  Returns analyze's results in order."""
+    sched = IngestScheduler(video_paths, temp_dir, rank=rank, world=world, config=config).start()
+    out = []
+    for p in video_paths:
+        sched.wait(p)
+        out.append(analyze(p))
+    sched.join()
+    return out
+
+
 def merge_progress(temp_dir, world: int) -> dict:
     """Fold progress.rank*.json into the progress.json the reference's ProgressTracker loads."""
     temp_dir = Path(temp_dir)
