@@ -107,6 +107,22 @@ int vt_sad_hist_u8(const uint8_t *luma_dev, int pitch, size_t frame_stride, int 
 int vt_gather_frames(const uint8_t *src_dev, size_t src_frame_stride, size_t frame_bytes, const int32_t *index_dev,
                      int count, uint8_t *dst_dev, void *stream);
 
+/* ---- upload-size reducer: baseline JPEG of planar YUV420P pictures (Motion-JPEG samples) ------------------------------
+ * Replaces: the libx264 encode inside `ffmpeg -vf scale=-2:360 -c:v libx264 -crf 28` of
+ * ContentAnalyzer._compress_video_for_upload (src/analyzer/content_analyzer.py:193-217); a B200 has no video encoder.
+ * ITU-T T.81 baseline, 4:2:0, Annex-K Huffman tables, IJG integer DCT and quality scaling, one restart interval per MCU
+ * row.  expand_range = 1 expands limited-range video samples (16..235 / 16..240) to JFIF's full range first.
+ *   src: picture f at src_dev + f*src_frame_stride, tightly packed Y (w*h), U, V (ceil(w/2)*ceil(h/2) each)
+ *   out: pictures packed back to back; offsets_dev[f] = first byte of picture f, offsets_dev[n_frames] = total bytes
+ *   status_dev: 0 ok, 1 an MCU row did not compress below its raw size, 2 out_cap too small (then nothing is valid) */
+typedef struct vt_jpeg_plan vt_jpeg_plan;
+int vt_jpeg_plan_create(int w, int h, int quality, int expand_range, vt_jpeg_plan **out);
+void vt_jpeg_plan_destroy(vt_jpeg_plan *plan);
+size_t vt_jpeg_max_frame_bytes(const vt_jpeg_plan *plan);
+int vt_jpeg_header(const vt_jpeg_plan *plan, uint8_t *out, size_t cap, size_t *len);
+int vt_jpeg_encode_yuv420p(vt_jpeg_plan *plan, const uint8_t *src_dev, size_t src_frame_stride, int n_frames,
+                           uint8_t *out_dev, size_t out_cap, uint64_t *offsets_dev, int32_t *status_dev, void *stream);
+
 /* Landing of K5: frames go from the device straight into a page-locked mapping of the segment's `.frames` file.
  * vt_host_register pins an existing host range (VT_ERR_CUDA when the range cannot be pinned; the CUDA error state is
  * cleared), vt_copy_to_host_async is the D2H copy on `stream`. */

@@ -16,7 +16,8 @@ BILINEAR, BICUBIC, AREA = 2, 4, 0x20
 def build() -> str:
     so = os.path.join(_HERE, "libvtoracle.so")
     src = os.path.join(_HERE, "vt_oracle.c")
-    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    src2 = os.path.join(_HERE, "jpeg_oracle.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(src2)):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
 
@@ -41,6 +42,14 @@ def lib():
         L.vto_pcm_picture_to_yuv420p.restype = None
         L.vto_yuv_to_rgb24.argtypes = [u8p, ctypes.c_int, u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        u8p, ctypes.c_int, ctypes.c_int]
+        L.vtj_encode.argtypes = [u8p, ctypes.c_int, u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                 ctypes.c_int, ctypes.c_int, u8p, ctypes.c_size_t]
+        L.vtj_encode.restype = ctypes.c_size_t
+        L.vtj_quant_table.argtypes = [ctypes.c_int, ctypes.c_int, u8p]
+        L.vtj_quant_table.restype = None
+        L.vtj_block_coefficients.argtypes = [u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, u8p,
+                                             ctypes.c_int, u8p]
+        L.vtj_block_coefficients.restype = None
         _lib = L
     return _lib
 
@@ -119,3 +128,33 @@ def nv12_to_rgb24(nv12: np.ndarray, w: int, h: int, pitch: int, dw: int | None =
     if rc:
         raise RuntimeError("vto_yuv_to_rgb24 failed")
     return out
+
+
+def jpeg_encode(y: np.ndarray, u: np.ndarray | None = None, v: np.ndarray | None = None, quality: int = 75,
+                restart_interval: int = 0, expand_range: bool = False) -> bytes:
+    """Baseline JPEG of a grey (y only) or YCbCr 4:2:0 picture (jpeg_oracle.c)."""
+    y = np.ascontiguousarray(y)
+    h, w = y.shape
+    cap = 4 * w * h + 4096
+    out = np.zeros(cap, np.uint8)
+    if u is not None:
+        u, v = np.ascontiguousarray(u), np.ascontiguousarray(v)
+        n = lib().vtj_encode(y.ctypes.data, y.strides[0], u.ctypes.data, v.ctypes.data, u.strides[0], w, h, quality,
+                             restart_interval, int(expand_range), out.ctypes.data, cap)
+    else:
+        n = lib().vtj_encode(y.ctypes.data, y.strides[0], None, None, 0, w, h, quality, restart_interval,
+                             int(expand_range), out.ctypes.data, cap)
+    if n == 0:
+        raise RuntimeError("vtj_encode overflow")
+    return out[:n].tobytes()
+
+
+def jpeg_block(plane: np.ndarray, bx: int, by: int, quality: int, chroma: bool, expand: int = 0) -> np.ndarray:
+    """Quantised coefficients (zigzag order) of one 8x8 block."""
+    plane = np.ascontiguousarray(plane)
+    h, w = plane.shape
+    q = np.zeros(64, np.uint8)
+    lib().vtj_quant_table(quality, int(chroma), q.ctypes.data)
+    zz = np.zeros(64, np.int16)
+    lib().vtj_block_coefficients(plane.ctypes.data, plane.strides[0], w, h, bx, by, q.ctypes.data, expand, zz.ctypes.data)
+    return zz

@@ -35,42 +35,69 @@ def test_failure_returns_the_input_and_leaves_nothing_behind(tmp_path):
 
 
 @pytest.mark.gpu
-def test_reduced_artifact_holds_the_swscale_exact_360p_frames(cuda, oracle_c, tmp_path):
-    from video_transformer_b200 import container, synth
-    w, h, n, gop = 1280, 720, 95, 10
-    bs, meta = synth.make_testsrc_h264(w, h, n, fps=30, gop=gop, cuts=[33])
-    raw = tmp_path / "clip.h264"
-    raw.write_bytes(bs)
-    src = tmp_path / "clip.mp4"
-    container.annexb_to_mp4(raw, src)
-    out = ur.compress_video_for_upload(src, max_size_mb=1.0)
-    assert out == tmp_path / "compressed_clip.mp4" and out.stat().st_size < src.stat().st_size
-    idx = container.probe(out)
-    assert (idx.width, idx.height, idx.n_frames) == (640, 360, 4) and all(idx.keyframe)   # pictures 0, 30, 60, 90
-    side = json.loads(out.with_suffix(".json").read_text())
-    assert side["frame_size"] == [640, 360] and side["sample_every"] == 30 and side["frames"] == 4
-    assert side["cuts"] == [33]
-    frames = np.fromfile(out.with_suffix(".frames"), np.uint8).reshape(4, -1)
-    # expected: the decoded source pictures (samples >= 1, held from the last IDR) through the oracle's bicubic scaler
-    scene, ref, exp = 0, None, {}
+def test_reduced_artifact_is_a_smaller_mjpeg_mp4_with_the_audio_kept(cuda, oracle_c, tmp_path):
+    """720p source with a PCM audio trak -> compressed_<name>: a Motion-JPEG MP4 whose samples are byte-identical to the
+    oracle's JPEG of the oracle's bicubic 360p frames (pictures 0, 30, 60, 90), decodable by libavcodec, with the audio
+    track's samples copied verbatim; the artefact is smaller than the input."""
+    import struct
+    from mp4_fixture import write_av_mp4
+    from video_transformer_b200 import container, isobmff, synth
+    cv2 = pytest.importorskip("cv2")
+    w, h, n, gop, fps = 1280, 720, 95, 10, 30
+    wr = synth.H264PcmWriter(w, h, fps, 1)
+    nal_samples, keys, exp, ref, scene = [], [], {}, None, 0
     for k in range(n):
         if k == 33:
             scene += 1
-        if k in meta["idr_frames"]:
-            ref = tuple(np.maximum(p, 1) for p in synth.testsrc_frame(w, h, k, scene))
+        if k % gop == 0 or k == 33:
+            pic = synth.testsrc_frame(w, h, k, scene)
+            nal_samples.append([wr.idr(*pic, with_params=False)[4:]])
+            keys.append(True)
+            ref = tuple(np.maximum(p, 1) for p in pic)
+        else:
+            nal_samples.append([wr.skip()[4:]])
+            keys.append(False)
         if k % 30 == 0:
             exp[k] = ref
+    rate = 16000
+    pcm = (np.arange(n * rate // fps) % 977).astype(np.int16)[:, None]
+    src = tmp_path / "clip.mp4"
+    meta = write_av_mp4(src, sps=wr._sps[4:], pps=wr._pps[4:], video_samples=nal_samples, keyframes=keys, width=w,
+                        height=h, timescale=30000, delta=1000, audio_pcm=pcm, audio_rate=rate, audio_channels=1)
+    out = ur.compress_video_for_upload(src, max_size_mb=1.0)
+    assert out == tmp_path / "compressed_clip.mp4" and out.stat().st_size < src.stat().st_size / 10
+    movie = isobmff.read_movie(out)
+    assert [(t.codec, t.n) for t in movie.tracks] == [(b"jpeg", 4), (b"sowt", len(pcm))]
+    side = json.loads(out.with_suffix(".json").read_text())
+    assert side["frame_size"] == [640, 360] and side["sample_every"] == 30 and side["frames"] == 4
+    assert side["cuts"] == [33] and side["audio_tracks"] == 1 and side["codec"] == "mjpeg"
+    data = out.read_bytes()
+    vt_, at_ = movie.tracks
     for i, k in enumerate(sorted(exp)):
         ey, eu, ev = oracle_c.scale_yuv420p(*exp[k], 640, 360, oracle_c.BICUBIC)
-        assert np.array_equal(frames[i], np.concatenate([ey.reshape(-1), eu.reshape(-1), ev.reshape(-1)])), k
-    # the MP4 pictures are those frames with PCM's "no zero sample" rule applied; any H.264 decoder reads them
-    cv2 = pytest.importorskip("cv2")
+        want = oracle_c.jpeg_encode(ey, eu, ev, quality=ur.JPEG_QUALITY, restart_interval=40, expand_range=True)
+        got = data[int(vt_.offsets[i]):int(vt_.offsets[i]) + int(vt_.sizes[i])]
+        assert got == want, k
+    # audio: every PCM frame of the source, byte for byte, same duration
+    offs, sizes = at_.offsets.astype(np.int64), at_.sizes.astype(np.int64)
+    brk = np.nonzero(offs[1:] != offs[:-1] + sizes[:-1])[0] + 1
+    audio = b"".join(data[offs[a_]:offs[b_ - 1] + sizes[b_ - 1]]
+                     for a_, b_ in zip(np.concatenate(([0], brk)), np.concatenate((brk, [offs.size]))))
+    assert audio == meta["audio_bytes"]
+    assert abs(movie.duration_seconds() - max(4 * 1.0, len(pcm) / rate)) < 2e-3
+    # libavformat/libavcodec read it: 4 pictures at 1 fps whose luma is the JPEG's luma
     cap = cv2.VideoCapture(str(out), cv2.CAP_FFMPEG)
-    cap.set(cv2.CAP_PROP_CONVERT_RGB, 0)
-    ok, img = cap.read()
-    assert ok
-    y0 = np.asarray(img).reshape(-1)[:640 * 360]
-    assert np.array_equal(y0, np.maximum(frames[0][:640 * 360], 1))
+    assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == 4 and abs(cap.get(cv2.CAP_PROP_FPS) - 1.0) < 1e-6
+    shown = 0
+    while True:
+        ok, img = cap.read()
+        if not ok:
+            break
+        want = cv2.imdecode(np.frombuffer(data[int(vt_.offsets[shown]):int(vt_.offsets[shown]) + int(vt_.sizes[shown])],
+                                          np.uint8), cv2.IMREAD_COLOR)
+        assert img.shape == (360, 640, 3) and np.abs(img.astype(int) - want.astype(int)).mean() < 4.0
+        shown += 1
+    assert shown == 4
     # second call: cache hit
     assert ur.compress_video_for_upload(src, max_size_mb=1.0) == out
 

@@ -45,6 +45,12 @@ SIGNATURES = {
     "vt_scale_nv12_to_rgb24": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_size_t, c_int, c_void_p]),
     "vt_sad_hist_u8": (c_int, [c_void_p, c_int, c_size_t, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "vt_gather_frames": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_int, c_void_p, c_void_p]),
+    "vt_jpeg_plan_create": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
+    "vt_jpeg_plan_destroy": (None, [c_void_p]),
+    "vt_jpeg_max_frame_bytes": (c_size_t, [c_void_p]),
+    "vt_jpeg_header": (c_int, [c_void_p, c_void_p, c_size_t, POINTER(c_size_t)]),
+    "vt_jpeg_encode_yuv420p": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_size_t, c_void_p, c_void_p,
+                                       c_void_p]),
     "vt_host_register": (c_int, [c_void_p, c_size_t]),
     "vt_host_unregister": (c_int, [c_void_p]),
     "vt_copy_to_host_async": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),

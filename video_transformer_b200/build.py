@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 OUT = os.path.join(HERE, "libvtseg.so")
 SOURCES = ["vt_api.cu", "vt_score.cu", "vt_convert.cu", "vt_rgb.cu", "vt_scale.cu", "vt_scale_pair.cu",
-           "vt_swsfilter.cpp", "vt_h264.cu", "vt_nvdec.cpp"]
+           "vt_swsfilter.cpp", "vt_h264.cu", "vt_nvdec.cpp", "vt_jpeg.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC,-O2,-Wall"]
 

@@ -562,15 +562,7 @@ def cut_movie(movie: Movie, start: float, end: float, dst: str | Path, *, stream
         pres_ticks = max(0, (media_dur - (media_time - min_cts)) * mts + t.timescale - 1) // t.timescale
         # chunking: consecutive samples up to chunk_seconds / chunk_bytes
         rel = (t.dts[a:b] - t.dts[a]).astype(np.float64) / t.timescale
-        n = b - a
-        bucket_t = np.floor(rel / chunk_seconds).astype(np.int64)
-        csum = np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(np.int64)
-        bucket_b = csum // chunk_bytes
-        key = bucket_t * (1 << 20) + (bucket_b - bucket_b[np.searchsorted(bucket_t, bucket_t, side="left")])
-        brk = np.nonzero(np.diff(key))[0] + 1
-        chunk_first = np.concatenate(([0], brk)).astype(np.int64)
-        chunk_count = np.diff(np.concatenate((chunk_first, [n]))).astype(np.int64)
-        chunk_bytes_ = np.add.reduceat(sizes.astype(np.int64), chunk_first)
+        chunk_first, chunk_count, chunk_bytes_ = _chunk_plan(rel, sizes, chunk_seconds, chunk_bytes)
         chunk_time = tp[chunk_first] if cts_off is None else (t.dts[a:b][chunk_first] - mt_src) / t.timescale
         plans.append({"t": t, "a": a, "b": b, "sizes": sizes, "deltas": deltas, "cts_off": cts_off, "sync": sync,
                       "override": override, "empty_ticks": empty_ticks, "media_time": media_time,
@@ -579,7 +571,82 @@ def cut_movie(movie: Movie, start: float, end: float, dst: str | Path, *, stream
                       "chunk_time": np.asarray(chunk_time, np.float64)})
     if not plans:
         return None
+    total_bytes = write_plans(dst, plans, mts, movie.ftyp, movie.path)
+    return CutResult(first, last, first_acc, len(plans), total_bytes, t_present)
 
+
+def _chunk_plan(rel_seconds: np.ndarray, sizes: np.ndarray, chunk_seconds: float, chunk_bytes: int):
+    """Group consecutive samples into chunks of at most chunk_seconds / chunk_bytes -> (first, count, bytes) per chunk."""
+    n = sizes.size
+    bucket_t = np.floor(rel_seconds / chunk_seconds).astype(np.int64)
+    csum = np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(np.int64)
+    bucket_b = csum // chunk_bytes
+    key = bucket_t * (1 << 20) + (bucket_b - bucket_b[np.searchsorted(bucket_t, bucket_t, side="left")])
+    brk = np.nonzero(np.diff(key))[0] + 1
+    chunk_first = np.concatenate(([0], brk)).astype(np.int64)
+    chunk_count = np.diff(np.concatenate((chunk_first, [n]))).astype(np.int64)
+    chunk_bytes_ = np.add.reduceat(sizes.astype(np.int64), chunk_first)
+    return chunk_first, chunk_count, chunk_bytes_
+
+
+def plan_whole_track(t: Track, movie_timescale: int, chunk_seconds: float = 0.5, chunk_bytes: int = 4 << 20) -> dict:
+    """Plan that carries every sample of a source track unchanged (its own edit list semantics re-expressed)."""
+    empty_s, mt = t.edit_shift(movie_timescale)
+    media_dur = int(t.deltas.sum())
+    rel = t.dts.astype(np.float64) / t.timescale
+    cf, cc, cb = _chunk_plan(rel, t.sizes, chunk_seconds, chunk_bytes)
+    empty_ticks = int(round(empty_s * movie_timescale))
+    pres_ticks = max(0, (media_dur - mt) * movie_timescale + t.timescale - 1) // t.timescale
+    return {"t": t, "a": 0, "b": t.n, "sizes": t.sizes.copy(), "deltas": t.deltas, "cts_off": t.cts_off,
+            "sync": t.sync.copy(), "override": None, "empty_ticks": empty_ticks, "media_time": mt,
+            "media_dur": media_dur, "pres_ticks": pres_ticks + empty_ticks, "chunk_first": cf, "chunk_count": cc,
+            "chunk_bytes": cb, "chunk_time": rel[cf] + empty_s}
+
+
+def make_video_track(track_id: int, codec: bytes, width: int, height: int, timescale: int,
+                     compressor: bytes = b"", extra_boxes: bytes = b"") -> Track:
+    """Header boxes of a new video track (no samples yet): tkhd, mdhd, hdlr, vmhd + dinf, stsd with one
+    VisualSampleEntry `codec`."""
+    matrix = struct.pack(">9I", 0x10000, 0, 0, 0, 0x10000, 0, 0, 0, 0x40000000)
+    tkhd = struct.pack(">I", 3) + struct.pack(">IIIII", 0, 0, track_id, 0, 0) + bytes(8) + \
+        struct.pack(">hhhH", 0, 0, 0, 0) + matrix + struct.pack(">II", width << 16, height << 16)
+    mdhd = struct.pack(">I", 0) + struct.pack(">IIIIHH", 0, 0, timescale, 0, 0x55C4, 0)
+    hdlr = struct.pack(">I", 0) + struct.pack(">I4s12x", 0, b"vide") + b"VideoHandler\x00"
+    dinf = box(b"dinf", full_box(b"dref", 0, 0, struct.pack(">I", 1) + full_box(b"url ", 0, 1, b"")))
+    name = compressor[:31]
+    entry = struct.pack(">6xH", 1) + bytes(16) + struct.pack(">HH", width, height) + \
+        struct.pack(">IIIH", 0x00480000, 0x00480000, 0, 1) + bytes([len(name)]) + name + bytes(31 - len(name)) + \
+        struct.pack(">Hh", 0x18, -1) + extra_boxes
+    stsd = full_box(b"stsd", 0, 0, struct.pack(">I", 1) + box(codec, entry))
+    z64, z = np.zeros(0, np.uint64), np.zeros(0, np.int64)
+    return Track(track_id, b"vide", codec, timescale, 0, width, height, tkhd, mdhd, hdlr,
+                 full_box(b"vmhd", 0, 1, bytes(8)) + dinf, stsd, z64, z64, z, z, None, np.zeros(0, bool), False, [])
+
+
+def plan_memory_track(t: Track, samples: list, deltas, sync=None, chunk_seconds: float = 0.5,
+                      chunk_bytes: int = 4 << 20) -> dict:
+    """Plan for a track whose samples are byte strings in memory (e.g. the reducer's Motion-JPEG pictures)."""
+    n = len(samples)
+    sizes = np.asarray([len(x) for x in samples], np.uint64)
+    deltas = np.asarray(deltas, np.int64)
+    if deltas.size != n:
+        raise BmffError("one duration per sample expected")
+    dts = np.concatenate(([0], np.cumsum(deltas)[:-1])).astype(np.int64) if n else np.zeros(0, np.int64)
+    sync = np.ones(n, bool) if sync is None else np.asarray(sync, bool)
+    rel = dts.astype(np.float64) / t.timescale
+    cf, cc, cb = _chunk_plan(rel, sizes, chunk_seconds, chunk_bytes)
+    return {"t": t, "a": 0, "b": n, "sizes": sizes, "deltas": deltas, "cts_off": None, "sync": sync, "override": None,
+            "empty_ticks": 0, "media_time": 0, "media_dur": int(deltas.sum()), "pres_ticks": None, "chunk_first": cf,
+            "chunk_count": cc, "chunk_bytes": cb, "chunk_time": rel[cf], "mem": samples, "all_sync": bool(sync.all())}
+
+
+def write_plans(dst: str | Path, plans: list, mts: int, ftyp: bytes = b"", src_path: Path | None = None) -> int:
+    """Write the planned tracks into a faststart MP4: ftyp, moov, mdat with the tracks' chunks interleaved by time.
+    Sample bytes come from src_path (plans made from a parsed file) or from memory (plan_memory_track).  Returns the
+    media bytes written."""
+    for p in plans:
+        if p["pres_ticks"] is None:
+            p["pres_ticks"] = (p["media_dur"] * mts + p["t"].timescale - 1) // p["t"].timescale
     # interleave: chunks of all tracks ordered by time (stable by track order)
     order = []
     for ti, p in enumerate(plans):
@@ -609,7 +676,7 @@ def cut_movie(movie: Movie, start: float, end: float, dst: str | Path, *, stream
                 ctts = full_box(b"ctts", ver, 0, struct.pack(">I", c.size) +
                                 np.stack([c, v & 0xFFFFFFFF], 1).astype(">u4").tobytes())
             stss = b""
-            if t.has_stss or not p["sync"].all():
+            if (t.has_stss and not p.get("all_sync")) or not p["sync"].all():
                 k = np.nonzero(p["sync"])[0] + 1
                 stss = full_box(b"stss", 0, 0, struct.pack(">I", k.size) + k.astype(">u4").tobytes())
             c, v = _runs(p["chunk_count"])
@@ -647,7 +714,7 @@ def cut_movie(movie: Movie, start: float, end: float, dst: str | Path, *, stream
                         struct.pack(">I", next_id))
         return box(b"moov", mvhd + traks)
 
-    ftyp = movie.ftyp or box(b"ftyp", b"isom" + struct.pack(">I", 0x200) + b"isomiso2mp41")
+    ftyp = ftyp or box(b"ftyp", b"isom" + struct.pack(">I", 0x200) + b"isomiso2mp41")
     wide = False
     moov = build_moov(0, wide)
     base = len(ftyp) + len(moov) + 16
@@ -664,6 +731,12 @@ def cut_movie(movie: Movie, start: float, end: float, dst: str | Path, *, stream
         t = p["t"]
         f0 = p["a"] + int(p["chunk_first"][ci])
         cnt = int(p["chunk_count"][ci])
+        if "mem" in p:
+            blob = b"".join(bytes(x) for x in p["mem"][f0:f0 + cnt])
+            over_at[len(src_lo)] = blob
+            src_lo.append(-1)
+            src_len.append(len(blob))
+            continue
         o = t.offsets[f0:f0 + cnt].astype(np.int64)
         z = t.sizes[f0:f0 + cnt].astype(np.int64)
         if p["override"] is not None and ci == 0:
@@ -685,11 +758,14 @@ def cut_movie(movie: Movie, start: float, end: float, dst: str | Path, *, stream
                 src_lo.append(lo)
                 src_len.append(ln)
     dst = Path(dst)
-    src_size = os.path.getsize(movie.path)
+    need_src = any(lo >= 0 for lo in src_lo)
+    if need_src and src_path is None:
+        raise BmffError("plans refer to a source file but none was given")
+    src_size = os.path.getsize(src_path) if need_src else 0
     # An existing output is overwritten IN PLACE and trimmed at the end: rewriting pages a file already owns is faster
     # than allocating fresh ones (tmpfs on the GPU box: 5.1 vs 3.8 GB/s, tools/copy_probe.py), which matters when a
     # segment is re-cut (retries, `ffmpeg -y` semantics).
-    in_fd = os.open(movie.path, os.O_RDONLY)
+    in_fd = os.open(src_path, os.O_RDONLY) if need_src else -1
     try:
         out_fd = os.open(dst, os.O_RDWR | os.O_CREAT, 0o644)
         try:
@@ -707,8 +783,9 @@ def cut_movie(movie: Movie, start: float, end: float, dst: str | Path, *, stream
         finally:
             os.close(out_fd)
     finally:
-        os.close(in_fd)
-    return CutResult(first, last, first_acc, len(plans), total_bytes, t_present)
+        if in_fd >= 0:
+            os.close(in_fd)
+    return total_bytes
 
 
 def _write_all(fd: int, data: bytes, offset: int) -> int:

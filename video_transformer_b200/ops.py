@@ -166,3 +166,50 @@ class RgbPlan:
         check(lib().vt_scale_nv12_to_rgb24(self._h, c_void_p(src.data_ptr()), pitch, sfs, c_void_p(out.data_ptr()),
                                            self.dw * self.dh * 3, n_frames, _stream()))
         return out
+
+
+class JpegPlan:
+    """Baseline-JPEG encoder for planar YUV420P pictures of one size (the Motion-JPEG samples of the upload reducer)."""
+
+    def __init__(self, w: int, h: int, quality: int = 75, expand_range: bool = True):
+        self.w, self.h, self.quality, self.expand_range = w, h, quality, expand_range
+        self._h = c_void_p()
+        check(lib().vt_jpeg_plan_create(w, h, quality, 1 if expand_range else 0, byref(self._h)))
+        self.frame_bytes_in = w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2)
+        self.max_frame_bytes = int(lib().vt_jpeg_max_frame_bytes(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            lib().vt_jpeg_plan_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def encode(self, frames: torch.Tensor, out: torch.Tensor | None = None):
+        """frames: [n, frame_bytes_in] uint8 CUDA tensor -> (packed bytes CUDA tensor, offsets int64 CUDA tensor [n+1],
+        status int32 CUDA tensor [1]).  Asynchronous on the current stream; offsets[n] is the number of valid bytes."""
+        _need_cuda(frames, "frames")
+        n = frames.shape[0]
+        if out is None:
+            out = torch.empty(n * max(self.frame_bytes_in // 2, 65536), dtype=torch.uint8, device=frames.device)
+        offsets = torch.empty(n + 1, dtype=torch.int64, device=frames.device)
+        status = torch.empty(1, dtype=torch.int32, device=frames.device)
+        check(lib().vt_jpeg_encode_yuv420p(self._h, c_void_p(frames.data_ptr()), frames.stride(0), n,
+                                           c_void_p(out.data_ptr()), out.numel(), c_void_p(offsets.data_ptr()),
+                                           c_void_p(status.data_ptr()), _stream()))
+        return out, offsets, status
+
+    def encode_to_host(self, frames: torch.Tensor) -> list[bytes]:
+        """Synchronous convenience: one `bytes` per picture.  Raises when the encoder refused (status != 0)."""
+        out, offsets, status = self.encode(frames)
+        off = offsets.cpu().numpy()
+        st = int(status.cpu()[0])
+        if st != 0:
+            raise VtError(_lib.VT_ERR_UNSUPPORTED, "JPEG encoder refused the batch (status %d: %s)" % (
+                st, "an MCU row did not compress below its raw size" if st == 1 else "output buffer too small"))
+        host = out[: int(off[-1])].cpu().numpy()
+        return [host[int(off[i]):int(off[i + 1])].tobytes() for i in range(len(off) - 1)]

@@ -8,12 +8,15 @@ file already exists (cache), or when anything fails.  This module keeps that con
 
     decode (K0) -> SAD/hist (K3) -> libswscale-exact bicubic to height 360, width rounded to even (K2) -> frames (K5)
 
-A B200 has no NVENC, so the artefact is not libx264 output.  It is a valid H.264 MP4 whose pictures are the downscaled
-frames sampled at `sample_fps` (default 1 picture per second, the granularity the remote model consumes), each
-written as an I_PCM IDR picture -- decodable by any H.264 decoder, bit-identical to the scaled frames except that
-PCM samples cannot be 0 and are raised to 1 -- plus the exact frames and scene scores in `compressed_<stem>.frames`
-/ `.json`.  When that artefact would not be smaller than the input, the input path is returned: the function exists
-to reduce upload size and must never enlarge it.
+A B200 has no NVENC and the image has no software H.264 encoder, so the artefact is not libx264 output.  It is a
+Motion-JPEG MP4: the downscaled pictures sampled at `sample_fps` (default 1 picture per second, the granularity the
+remote model consumes), each encoded on the GPU as a baseline JPEG (csrc/vt_jpeg.cu: IJG integer DCT, Annex-K Huffman
+tables, quality 75 by default; limited-range video samples are expanded to JFIF's full range), in a `jpeg` video track
+at the sampled rate -- readable by libavformat/libavcodec and every MP4 player -- with the source's AUDIO TRACKS COPIED
+VERBATIM (the reference re-encodes audio to AAC 64k; a stream copy keeps the speech the lecture analysis depends on
+without needing an audio encoder).  Scene scores of every picture land in `compressed_<stem>.json`.  When the artefact
+would not be smaller than the input, the input path is returned: the function exists to reduce upload size and must
+never enlarge it.
 """
 from __future__ import annotations
 
@@ -27,6 +30,7 @@ log = logging.getLogger(__name__)
 
 MAX_SIZE_MB = 30            # content_analyzer.py:174
 TARGET_HEIGHT = 360         # `scale=-2:360`, content_analyzer.py:199
+JPEG_QUALITY = 75           # IJG quality of the Motion-JPEG pictures (the reference's knob is x264's CRF 28)
 
 
 def compressed_path_for(video_path: str | Path) -> Path:
@@ -53,7 +57,7 @@ def compress_video_for_upload(video_path: str | Path, *, max_size_mb: float = MA
         log.warning("event=upload_reduce_failed error=%s", str(exc)[:200])
         ok = False
     if not ok:
-        for p in (out, out.with_suffix(".frames"), out.with_suffix(".json")):
+        for p in (out, out.with_suffix(".json")):
             if p.exists():
                 p.unlink()
         return video_path
@@ -61,50 +65,61 @@ def compress_video_for_upload(video_path: str | Path, *, max_size_mb: float = MA
     return out
 
 
-def _reduce(src: Path, out: Path, target_height: int, sample_fps: float, device: str) -> bool:
-    from . import container, ingest, synth
+def _reduce(src: Path, out: Path, target_height: int, sample_fps: float, device: str, quality: int = JPEG_QUALITY) -> bool:
+    import torch
+    from . import container, ingest, isobmff, ops
     idx = container.probe(src)
     if idx is None or idx.n_frames == 0 or idx.fps_num <= 0:
         return False
+    if idx.kind == "mp4" and not (idx.extra.get("decodable") and container.classify_pcm(idx)):
+        raise RuntimeError("video track %r cannot be decoded by this build (K0 handles PCM-intra H.264; NVDEC is not "
+                           "available on this host)" % idx.extra.get("codec"))
     fps = idx.fps_num / idx.fps_den
     every = max(1, int(round(fps / sample_fps))) if sample_fps > 0 else 1
     opts = ingest.IngestOptions(target_height=target_height, sample_every=every, device=device)
     eng = ingest.SegmentIngestor(idx, opts)
     dw, dh = eng.out_w, eng.out_h
-    n_keep = (idx.n_frames + every - 1) // every
-    # the I_PCM picture is a fixed 384 bytes per macroblock plus a few header bytes: decide before running the pass
-    est = n_keep * (((dw + 15) // 16) * ((dh + 15) // 16) * 384 + 64)
-    if est >= src.stat().st_size:
-        log.info("event=upload_reduce_not_smaller est_bytes=%d input_bytes=%d", est, src.stat().st_size)
-        return False
-    wr = synth.H264PcmWriter(dw, dh, max(1, int(round(fps))), every)   # picture k of the output shows at k*every/fps
-    start = len(synth._START)
+    jpeg = ops.JpegPlan(dw, dh, quality, expand_range=True)
     samples: list[bytes] = []
-    ysz, csz = dw * dh, (dw // 2) * (dh // 2)
-    frames_file = open(out.with_suffix(".frames"), "wb")
+    pending: list = []
 
-    def sink(chunk, first_picture):
-        a = chunk.numpy()
-        frames_file.write(a.tobytes())
-        for row in a:
-            y = row[:ysz].reshape(dh, dw)
-            u = row[ysz:ysz + csz].reshape(dh // 2, dw // 2)
-            v = row[ysz + csz:ysz + 2 * csz].reshape(dh // 2, dw // 2)
-            samples.append(wr.idr(y, u, v, with_params=False)[start:])
+    def flush():
+        for data, offsets, status in pending:
+            off = offsets.cpu().numpy()                       # synchronises the compute stream up to this batch
+            if int(status.cpu()[0]) != 0:
+                raise RuntimeError("JPEG encoder refused a batch (status %d)" % int(status.cpu()[0]))
+            host = data[: int(off[-1])].cpu().numpy()
+            samples.extend(host[int(off[i]):int(off[i + 1])].tobytes() for i in range(len(off) - 1))
+        pending.clear()
+
+    def on_device(chunk, first_picture):
+        # called with the compute stream current, right after the kernels that produced `chunk` were enqueued: the
+        # encoder's launches are ordered after them and before the buffers are reused
+        pending.append(jpeg.encode(chunk))
+        if len(pending) >= 32:
+            flush()
 
     try:
-        res = eng.run(0, idx.n_frames, sink)
+        with torch.cuda.device(eng.dev):
+            res = eng.run(0, idx.n_frames, None, device_sink=on_device)
+            flush()
     finally:
-        frames_file.close()
+        jpeg.close()
     if not samples:
         return False
-    g = np.gcd(idx.fps_num, idx.fps_den * every)
-    container.write_mp4(out, sps=wr._sps[start:], pps=wr._pps[start:], samples=samples, width=dw, height=dh,
-                        fps_num=int(idx.fps_num // g), fps_den=int(idx.fps_den * every // g),
-                        keyframes=[True] * len(samples))
+    g = int(np.gcd(idx.fps_num, idx.fps_den * every))
+    timescale, delta = int(idx.fps_num // g), int(idx.fps_den * every // g)
+    movie = idx.extra.get("movie")
+    mts = (movie.timescale if movie is not None else 0) or 1000
+    audio = [t for t in movie.tracks if t.handler == b"soun" and t.n] if movie is not None else []
+    vid = isobmff.make_video_track(max([t.track_id for t in audio] + [0]) + 1, b"jpeg", dw, dh, timescale,
+                                   b"Photo - JPEG")
+    plans = [isobmff.plan_memory_track(vid, samples, [delta] * len(samples))]
+    plans += [isobmff.plan_whole_track(t, mts) for t in audio]
+    isobmff.write_plans(out, plans, mts, b"", movie.path if movie is not None else None)
     out.with_suffix(".json").write_text(json.dumps({
-        "source": str(src), "source_size": [idx.width, idx.height], "frame_size": [dw, dh], "pixel_format": "yuv420p",
-        "sample_every": every, "frames": len(samples), "frame_bytes": res.frame_bytes,
+        "source": str(src), "source_size": [idx.width, idx.height], "frame_size": [dw, dh], "codec": "mjpeg",
+        "jpeg_quality": quality, "sample_every": every, "frames": len(samples), "audio_tracks": len(audio),
         "cuts": [int(c) for c in res.cuts], "sad": [int(s) for s in res.sad],
         "score": [float(s) for s in res.scores]}), encoding="utf-8")
     return out.stat().st_size < src.stat().st_size
