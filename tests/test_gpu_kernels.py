@@ -174,16 +174,27 @@ def test_gather_frames(cuda):
                                                (640, 360, 640, 640, 360), (322, 182, 336, 160, 90),
                                                (1920, 1080, 1920, 1280, 720), (854, 480, 896, 768, 768),
                                                (640, 360, 640, 1280, 720),          # upscale: 4-tap banks
+                                               (1280, 720, 1280, 700, 394),         # ragged tiles (700 = 10 x 64 + 60)
                                                (1280, 720, 1283, 768, 768),         # pitch not a multiple of 4: general kernels
                                                (3840, 2160, 3840, 768, 768)])       # 20 horizontal taps: general kernels
-def test_nv12_to_rgb24_scaled_bit_exact(cuda, oracle_c, sw, sh, pitch, dw, dh):
-    """K1b / config 5: NV12 -> RGB24 with scaling equals the oracle (itself bit-exact against libswscale)."""
+@pytest.mark.parametrize("path", ["fused", "split"])
+def test_nv12_to_rgb24_scaled_bit_exact(cuda, oracle_c, sw, sh, pitch, dw, dh, path, monkeypatch):
+    """K1b / config 5: NV12 -> RGB24 with scaling equals the oracle (itself bit-exact against libswscale).  `fused` is
+    the default dispatch (the one-pass tile kernel where the plan qualifies), `split` forces the three-launch path."""
+    if path == "split":
+        monkeypatch.setenv("VT_RGB_KERNEL", "split")
+    else:
+        monkeypatch.delenv("VT_RGB_KERNEL", raising=False)
     rng = np.random.default_rng(sw + dw)
     n = 3
     buf = _nv12_batch(rng, n, sw, sh, pitch)
     buf[1, : sh // 2] = 235                      # flat bright area next to noise: exercises the clamps
     plan = ops.RgbPlan(sw, sh, dw, dh)
+    launches = ops.lib().vt_launch_count()
     out = plan.scale_nv12(torch.from_numpy(buf).to(cuda).view(-1), pitch, n).cpu().numpy()
+    launches = ops.lib().vt_launch_count() - launches
+    if path == "fused" and pitch % 4 == 0 and sw <= 1920:
+        assert launches == 1                     # one pass: no int16 planes in HBM
     for f in range(n):
         exp = oracle_c.nv12_to_rgb24(buf[f].reshape(-1), sw, sh, pitch, dw, dh)
         assert np.array_equal(out[f], exp), (f, np.abs(out[f].astype(int) - exp.astype(int)).max())

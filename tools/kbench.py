@@ -93,3 +93,28 @@ if "rgb" in ks:
     F = Fr
     run("nv12_to_rgb24_768", lambda: rp.scale_nv12(surf.view(-1), pitch, Fr, rows * pitch, out=orgb), sw * sh * 3 // 2 + 768 * 768 * 3)
     F = F_save
+if "jpeg" in ks:
+    # the reducer's Motion-JPEG encoder on 640x360 YUV420P pictures (smooth content + mild noise)
+    Fj = min(F, 64)
+    w2, h2 = 640, 360
+    g = torch.Generator(device="cpu").manual_seed(5)
+    yy = torch.arange(h2).view(-1, 1).float(); xx = torch.arange(w2).view(1, -1).float()
+    base = (128 + 60 * torch.sin(xx / 37.0) * torch.cos(yy / 23.0)).clamp(16, 235)
+    pics = []
+    for k in range(Fj):
+        y = (base + torch.randint(-6, 7, (h2, w2), generator=g)).clamp(16, 235).to(torch.uint8)
+        u = (128 + 30 * torch.sin(xx[:, ::2] / 50.0 + k)).expand(h2 // 2, -1).clamp(16, 240).to(torch.uint8)
+        v = (128 + 30 * torch.cos(yy[::2] / 40.0 + k)).expand(-1, w2 // 2).clamp(16, 240).to(torch.uint8)
+        pics.append(torch.cat([y.reshape(-1), u.reshape(-1), v.reshape(-1)]))
+    frames = torch.stack(pics).to(dev)
+    jp = ops.JpegPlan(w2, h2, 75, True)
+    outj = torch.empty(Fj * 200000, dtype=torch.uint8, device=dev)
+    F_save = F
+    F = Fj
+    res = {}
+    def enc():
+        res["r"] = jp.encode(frames, out=outj)
+    run("jpeg_640x360_q75", enc, w2 * h2 * 3 // 2)
+    off = res["r"][1].cpu()
+    print(json.dumps({"jpeg_bytes_per_picture": int(off[-1]) // Fj, "status": int(res["r"][2].cpu()[0])}))
+    F = F_save

@@ -40,6 +40,11 @@ struct vt_rgb_plan {
     int hpl, hpc, vtl, vtc;                   // 0 = that bank is outside what the fast kernels take
     uint32_t *lhc2, *chc2;                    // dw x hpl, cdw x hpc
     int16_t *lvc2, *cvc2;                     // dh x vtl, dh x vtc
+    // fused tile kernel: one horizontal pair count for both plane kinds, rows of intermediates a tile needs at most
+    int fhp;                                  // 0 = the fused kernel does not take this plan
+    uint32_t *lhcf, *chcf;                    // dw x fhp, cdw x fhp
+    int nrl_max, nrc_max;
+    size_t fused_smem;
 };
 
 namespace vt {
@@ -246,6 +251,156 @@ rgb_vscale_fast8(const int16_t *__restrict__ my, const int16_t *__restrict__ mu,
                           rgb_pack4(px[8 * i + 7], px[8 * i + 6], px[8 * i + 5], px[8 * i + 4]));
 }
 
+// ---- fused tile kernel ------------------------------------------------------------------------------------------------
+// One block produces a tile of RGB_TW x RGB_TH output pixels of one picture in a single pass over the source:
+//   phase 1  the horizontal taps of every source row the tile's vertical windows touch, straight from the NV12
+//            surface (dp2a on funnel-shifted words, U and V from one permuted word) into SHARED memory as libswscale's
+//            15-bit intermediates -- they never travel to HBM (the three-launch path writes and re-reads 3.3 MB of
+//            int16 planes per 768x768 picture, twice the algorithmic bytes of the whole conversion);
+//   phase 2  vertical taps + BT.601 matrix out of shared memory, four pixels (two chroma samples) per thread and row,
+//            clamp folded into cvt.pack.sat, 12 bytes per thread as three 32-bit stores.
+// Source rows shared by vertically adjacent tiles are re-read (L2 hits) and their horizontal taps recomputed:
+// (LVT - 1) / (RGB_TH x vertical ratio) extra, ~10 % for 720p -> 768x768.
+constexpr int RGB_TW = 64, RGB_TH = 32, RGB_THREADS = 256;
+
+struct RgbTileArgs {
+    const uint8_t *src;
+    int pitch;
+    unsigned long long src_fs;
+    int sw, sh, csh, dw, dh, cdw;
+    const uint32_t *lhc, *chc;                // coefficient pairs, HP per output sample
+    const int32_t *lhp, *chp, *lvp, *cvp;
+    const int16_t *lvc, *cvc;                 // vertical banks padded to LVT / CVT
+    int nrl_max, nrc_max;
+    uint8_t *dst;
+    unsigned long long dst_fs;
+    RgbConst k;
+};
+
+template <int HP, int LVT, int CVT>
+__global__ void __launch_bounds__(RGB_THREADS)
+rgb_tile_kernel(const __grid_constant__ RgbTileArgs a) {
+    extern __shared__ __align__(16) int16_t rgb_sm[];
+    int16_t *ys = rgb_sm;                                        // [nrl_max][RGB_TW]
+    int16_t *us = ys + (size_t)a.nrl_max * RGB_TW;               // [nrc_max][RGB_TW / 2]
+    int16_t *vs = us + (size_t)a.nrc_max * (RGB_TW / 2);
+    const int x0 = blockIdx.x * RGB_TW, y0 = blockIdx.y * RGB_TH;
+    const int y1 = min(a.dh, y0 + RGB_TH);
+    const int lrow0 = __ldg(a.lvp + y0), lrow1 = min(__ldg(a.lvp + y1 - 1) + LVT - 1, a.sh - 1);
+    const int crow0 = __ldg(a.cvp + y0), crow1 = min(__ldg(a.cvp + y1 - 1) + CVT - 1, a.csh - 1);
+    const int nrl = lrow1 - lrow0 + 1, nrc = crow1 - crow0 + 1;
+    const uint8_t *frame = a.src + (size_t)blockIdx.z * a.src_fs;
+    const int pw = a.pitch >> 2, wl = pw - 1;
+    // ---- phase 1, luma: thread = (column, row group)
+    {
+        constexpr int G = RGB_THREADS / RGB_TW;
+        const int col = threadIdx.x % RGB_TW, g = threadIdx.x / RGB_TW, x = x0 + col;
+        if (x < a.dw) {
+            constexpr int NAW = (HP + 1) / 2, NW = NAW + 1;
+            const int p = __ldg(a.lhp + x);
+            const int w0 = p >> 2;
+            const uint32_t sh = (uint32_t)(p & 3) * 8u;
+            int wi[NW];
+#pragma unroll
+            for (int i = 0; i < NW; i++) wi[i] = min(w0 + i, wl);
+            uint32_t c[HP];
+            hs_load_pairs<HP>(a.lhc + (size_t)x * HP, c);
+            const uint32_t *row = reinterpret_cast<const uint32_t *>(frame + (size_t)(lrow0 + g) * a.pitch);
+#pragma unroll 2
+            for (int r = g; r < nrl; r += G) {
+                uint32_t w[NW];
+#pragma unroll
+                for (int i = 0; i < NW; i++) w[i] = __ldg(row + wi[i]);
+                int v = 0;
+#pragma unroll
+                for (int i = 0; i < HP; i++) {
+                    const uint32_t al = __funnelshift_r(w[i >> 1], w[(i >> 1) + 1], sh);
+                    v = (i & 1) ? hs_dp2a_hi(c[i], al, v) : hs_dp2a_lo(c[i], al, v);
+                }
+                ys[r * RGB_TW + col] = (int16_t)min(v >> 7, 32767);
+                row += (size_t)G * pw;
+            }
+        }
+    }
+    // ---- phase 1, chroma: thread = (chroma column, row group), U and V together
+    {
+        constexpr int CW = RGB_TW / 2, G = RGB_THREADS / CW;
+        const int col = threadIdx.x % CW, g = threadIdx.x / CW, x = (x0 >> 1) + col;
+        if (x < a.cdw) {
+            const int p = 2 * __ldg(a.chp + x);
+            const int w0 = p >> 2;
+            const uint32_t sh = (uint32_t)(p & 3) * 8u;
+            int wi[HP + 1];
+#pragma unroll
+            for (int i = 0; i < HP + 1; i++) wi[i] = min(w0 + i, wl);
+            uint32_t c[HP];
+            hs_load_pairs<HP>(a.chc + (size_t)x * HP, c);
+            const uint32_t *row = reinterpret_cast<const uint32_t *>(frame + (size_t)a.pitch * a.sh + (size_t)(crow0 + g) * a.pitch);
+#pragma unroll 2
+            for (int r = g; r < nrc; r += G) {
+                uint32_t w[HP + 1];
+#pragma unroll
+                for (int i = 0; i < HP + 1; i++) w[i] = __ldg(row + wi[i]);
+                int u = 0, v = 0;
+#pragma unroll
+                for (int i = 0; i < HP; i++) {
+                    const uint32_t pw4 = __byte_perm(__funnelshift_r(w[i], w[i + 1], sh), 0u, 0x3120);
+                    u = hs_dp2a_lo(c[i], pw4, u);
+                    v = hs_dp2a_hi(c[i], pw4, v);
+                }
+                us[r * CW + col] = (int16_t)min(u >> 7, 32767);
+                vs[r * CW + col] = (int16_t)min(v >> 7, 32767);
+                row += (size_t)G * pw;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: thread = (quad of four pixels, row group)
+    constexpr int NQ = RGB_TW / 4, RG = RGB_THREADS / NQ;
+    const int q = threadIdx.x % NQ, rg = threadIdx.x / NQ;
+    if (x0 + 4 * q >= a.dw) return;
+    const int base = 326 * a.k.cy - (400 << 16) + 0x8000;
+    for (int y = y0 + rg; y < y1; y += RG) {
+        const int lr = __ldg(a.lvp + y), cr = __ldg(a.cvp + y);
+        int ya[4] = {1 << 18, 1 << 18, 1 << 18, 1 << 18}, ua[2] = {1 << 18, 1 << 18}, va[2] = {1 << 18, 1 << 18};
+#pragma unroll
+        for (int j = 0; j < LVT; j++) {
+            const int c = __ldg(a.lvc + y * LVT + j);
+            const uint2 w = *reinterpret_cast<const uint2 *>(ys + (min(lr + j, a.sh - 1) - lrow0) * RGB_TW + 4 * q);
+            ya[0] += ((int)(w.x << 16) >> 16) * c; ya[1] += ((int)w.x >> 16) * c;
+            ya[2] += ((int)(w.y << 16) >> 16) * c; ya[3] += ((int)w.y >> 16) * c;
+        }
+#pragma unroll
+        for (int j = 0; j < CVT; j++) {
+            const int c = __ldg(a.cvc + y * CVT + j);
+            const int o = (min(cr + j, a.csh - 1) - crow0) * (RGB_TW / 2) + 2 * q;
+            const uint32_t wu = *reinterpret_cast<const uint32_t *>(us + o), wv = *reinterpret_cast<const uint32_t *>(vs + o);
+            ua[0] += ((int)(wu << 16) >> 16) * c; ua[1] += ((int)wu >> 16) * c;
+            va[0] += ((int)(wv << 16) >> 16) * c; va[1] += ((int)wv >> 16) * c;
+        }
+        int px[12];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int uc = max(0, min(255, ua[h] >> 19)), vc = max(0, min(255, va[h] >> 19));
+            const int r_off = ((vc * a.k.crv) >> 16) - (a.k.crv >> 9);
+            const int g_off = ((uc * a.k.cgu) >> 16) - (a.k.cgu >> 9) + ((vc * a.k.cgv) >> 16) - (a.k.cgv >> 9);
+            const int b_off = ((uc * a.k.cbu) >> 16) - (a.k.cbu >> 9);
+            const int ar = r_off * a.k.cy + base, ag = g_off * a.k.cy + base, ab = b_off * a.k.cy + base;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int yv = ya[2 * h + e] >> 19;
+                px[6 * h + 3 * e] = (yv * a.k.cy + ar) >> 16;
+                px[6 * h + 3 * e + 1] = (yv * a.k.cy + ag) >> 16;
+                px[6 * h + 3 * e + 2] = (yv * a.k.cy + ab) >> 16;
+            }
+        }
+        uint32_t *d = reinterpret_cast<uint32_t *>(a.dst + (size_t)blockIdx.z * a.dst_fs + ((size_t)y * a.dw + x0 + 4 * q) * 3);
+        d[0] = rgb_pack4(px[3], px[2], px[1], px[0]);
+        d[1] = rgb_pack4(px[7], px[6], px[5], px[4]);
+        d[2] = rgb_pack4(px[11], px[10], px[9], px[8]);
+    }
+}
+
 }  // namespace vt
 
 namespace {
@@ -327,6 +482,28 @@ extern "C" int vt_rgb_plan_create(int sw, int sh, int dw, int dh, int flags, vt_
             p->hpl = p->hpc = p->vtl = p->vtc = 0;
         }
     }
+    // fused tile kernel: both plane kinds with one pair count (padded to 2/4/6/8), output width a multiple of 4
+    if (rc == VT_OK && p->vtl && p->vtc && dw % 4 == 0) {
+        auto pad_f = [](int taps) { const int hp = (taps + 1) / 2; return hp <= 2 ? 2 : hp <= 4 ? 4 : hp <= 6 ? 6 : hp <= 8 ? 8 : 0; };
+        const int fl = pad_f(p->lht), fc = pad_f(p->cht);
+        if (fl && fc) {
+            p->fhp = std::max(fl, fc);
+            const auto a = pairs(hl, dw, p->lht, p->fhp), b = pairs(hc, p->cdw, p->cht, p->fhp);
+            rc = upload(a.data(), a.size() * 4, (void **)&p->lhcf);
+            if (rc == VT_OK) rc = upload(b.data(), b.size() * 4, (void **)&p->chcf);
+            // rows of intermediates the tallest tile needs (positions are monotonic)
+            std::vector<int32_t> lvp(dh), cvp(dh);
+            if (rc == VT_OK && cudaMemcpy(lvp.data(), p->lvp, 4 * (size_t)dh, cudaMemcpyDeviceToHost) != cudaSuccess) rc = VT_ERR_CUDA;
+            if (rc == VT_OK && cudaMemcpy(cvp.data(), p->cvp, 4 * (size_t)dh, cudaMemcpyDeviceToHost) != cudaSuccess) rc = VT_ERR_CUDA;
+            for (int y0 = 0; rc == VT_OK && y0 < dh; y0 += vt::RGB_TH) {
+                const int y1 = std::min(dh, y0 + vt::RGB_TH);
+                p->nrl_max = std::max(p->nrl_max, std::min(lvp[y1 - 1] + p->vtl - 1, sh - 1) - lvp[y0] + 1);
+                p->nrc_max = std::max(p->nrc_max, std::min(cvp[y1 - 1] + p->vtc - 1, p->csh - 1) - cvp[y0] + 1);
+            }
+            p->fused_smem = ((size_t)p->nrl_max * vt::RGB_TW + (size_t)p->nrc_max * vt::RGB_TW) * sizeof(int16_t);
+            if (p->fused_smem > 96 * 1024 || p->nrl_max <= 0 || p->nrc_max <= 0) p->fhp = 0;   // very steep ratios: three-launch path
+        }
+    }
     // intermediates: as many frames per launch group as fit 256 MB
     const size_t per_frame = ((size_t)dw * sh + 2 * (size_t)p->cdw * p->csh) * sizeof(int16_t);
     p->chunk = (int)std::max<size_t>(1, std::min<size_t>(32, ((size_t)256 << 20) / per_frame));
@@ -348,6 +525,7 @@ extern "C" void vt_rgb_plan_destroy(vt_rgb_plan *p) {
     cudaFree(p->lhp); cudaFree(p->lvp); cudaFree(p->chp); cudaFree(p->cvp);
     cudaFree(p->my); cudaFree(p->mu); cudaFree(p->mv);
     cudaFree(p->lhc2); cudaFree(p->chc2); cudaFree(p->lvc2); cudaFree(p->cvc2);
+    cudaFree(p->lhcf); cudaFree(p->chcf);
     delete p;
 }
 
@@ -366,9 +544,43 @@ extern "C" int vt_scale_nv12_to_rgb24(const vt_rgb_plan *p, const uint8_t *src, 
     k.cgv = (int)cdiv(-53279LL * 65536 + 0x8000, k.cy);
     const size_t my_fs = (size_t)p->dw * p->sh, mc_fs = (size_t)p->cdw * p->csh;
     // VT_RGB_KERNEL=generic selects the general kernels (A/B measurements and their own parity test)
-    static const char *force = getenv("VT_RGB_KERNEL");
+    const char *force = getenv("VT_RGB_KERNEL");      // read per call: tests switch paths inside one process
     const bool fast = p->hpl && !(force && !strcmp(force, "generic")) && (uintptr_t)src % 4 == 0 && pitch % 4 == 0 &&
                       src_fs % 4 == 0 && (uintptr_t)dst % 2 == 0 && dst_fs % 2 == 0;
+    // VT_RGB_KERNEL=split keeps the three-launch fast path (A/B measurements and its own parity test)
+    const bool fused = fast && p->fhp && !(force && !strcmp(force, "split")) && (uintptr_t)dst % 4 == 0 && dst_fs % 4 == 0;
+    if (fused) {
+        vt::RgbTileArgs a;
+        a.src = src; a.pitch = pitch; a.src_fs = src_fs;
+        a.sw = p->sw; a.sh = p->sh; a.csh = p->csh; a.dw = p->dw; a.dh = p->dh; a.cdw = p->cdw;
+        a.lhc = p->lhcf; a.chc = p->chcf; a.lhp = p->lhp; a.chp = p->chp; a.lvp = p->lvp; a.cvp = p->cvp;
+        a.lvc = p->lvc2; a.cvc = p->cvc2; a.nrl_max = p->nrl_max; a.nrc_max = p->nrc_max;
+        a.dst = dst; a.dst_fs = dst_fs; a.k = k;
+        const dim3 grid((p->dw + vt::RGB_TW - 1) / vt::RGB_TW, (p->dh + vt::RGB_TH - 1) / vt::RGB_TH, 1);
+        for (int f0 = 0; f0 < n_frames; f0 += 65535) {
+            const int nf = std::min(65535, n_frames - f0);
+            a.src = src + (size_t)f0 * src_fs;
+            a.dst = dst + (size_t)f0 * dst_fs;
+            const dim3 g(grid.x, grid.y, (unsigned)nf);
+            bool launched = false;
+#define VT_T(H, L, C) if (p->fhp == H && p->vtl == L && p->vtc == C) { \
+        static bool attr_dev[VT_MAX_DEVICES] = {false}; \
+        if (p->fused_smem > 48 * 1024 && !attr_dev[vt::current_device()]) { \
+            VT_CUDA(cudaFuncSetAttribute(vt::rgb_tile_kernel<H, L, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
+            attr_dev[vt::current_device()] = true; } \
+        vt::rgb_tile_kernel<H, L, C><<<g, vt::RGB_THREADS, p->fused_smem, st>>>(a); launched = true; }
+#define VT_TH(H) VT_T(H, 4, 4) VT_T(H, 4, 6) VT_T(H, 4, 8) VT_T(H, 6, 4) VT_T(H, 6, 6) VT_T(H, 6, 8) VT_T(H, 8, 4) VT_T(H, 8, 6) VT_T(H, 8, 8)
+            VT_TH(2) VT_TH(4) VT_TH(6) VT_TH(8)
+#undef VT_TH
+#undef VT_T
+            if (!launched) {
+                vt::set_error("vt_scale_nv12_to_rgb24: no fused instantiation for %d/%d/%d", p->fhp, p->vtl, p->vtc);
+                return VT_ERR_UNSUPPORTED;
+            }
+            VT_LAUNCHED("rgb_tile_kernel");
+        }
+        return VT_OK;
+    }
     for (int f0 = 0; f0 < n_frames; f0 += p->chunk) {
         const int nf = std::min(p->chunk, n_frames - f0);
         const uint8_t *s = src + (size_t)f0 * src_fs;
