@@ -128,6 +128,10 @@ int vt_jpeg_encode_yuv420p(vt_jpeg_plan *plan, const uint8_t *src_dev, size_t sr
  * cleared), vt_copy_to_host_async is the D2H copy on `stream`. */
 int vt_host_register(void *ptr, size_t n_bytes);
 int vt_host_unregister(void *ptr);
+/* Source side: pin a (private) mapping of the bitstream file so that the H2D copy reads the page cache directly;
+ * vt_copy_to_device_async is that copy.  VT_ERR_CUDA when the mapping cannot be pinned (then the caller stages). */
+int vt_host_register_source(void *ptr, size_t n_bytes);
+int vt_copy_to_device_async(void *dst_dev, const void *src_host, size_t n_bytes, void *stream);
 int vt_copy_to_host_async(void *dst_host, const void *src_dev, size_t n_bytes, void *stream);
 
 /* ---- K0: decode front end --------------------------------------------------------------------------------

@@ -53,6 +53,8 @@ SIGNATURES = {
                                        c_void_p]),
     "vt_host_register": (c_int, [c_void_p, c_size_t]),
     "vt_host_unregister": (c_int, [c_void_p]),
+    "vt_host_register_source": (c_int, [c_void_p, c_size_t]),
+    "vt_copy_to_device_async": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "vt_copy_to_host_async": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "vt_h264_scan": (c_int, [c_void_p, c_size_t, POINTER(StreamInfo), c_void_p, c_void_p, c_void_p, c_int]),
     "vt_h264_pcm_layout": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_void_p]),

@@ -70,6 +70,34 @@ int vt_host_unregister(void *ptr) {
     return VT_OK;
 }
 
+/* The same for a read-only use: the bitstream file is mapped privately and the copy engine reads the page cache
+ * directly (no staging memcpy).  Tries cudaHostRegisterReadOnly first where the device supports it. */
+int vt_host_register_source(void *ptr, size_t n_bytes) {
+    if (!ptr || !n_bytes) {
+        vt::set_error("vt_host_register_source: bad arguments");
+        return VT_ERR_INVALID;
+    }
+    cudaError_t e = cudaHostRegister(ptr, n_bytes, cudaHostRegisterReadOnly);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        e = cudaHostRegister(ptr, n_bytes, cudaHostRegisterDefault);
+    }
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return vt::cuda_fail(e, "cudaHostRegister (source mapping)");
+    }
+    return VT_OK;
+}
+
+int vt_copy_to_device_async(void *dst_dev, const void *src_host, size_t n_bytes, void *stream) {
+    if (!dst_dev || !src_host) {
+        vt::set_error("vt_copy_to_device_async: bad arguments");
+        return VT_ERR_INVALID;
+    }
+    VT_CUDA(cudaMemcpyAsync(dst_dev, src_host, n_bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return VT_OK;
+}
+
 /* Asynchronous device -> host copy on `stream` (the landing copy of K5; the host range must be page-locked for the copy
  * to overlap with kernels). */
 int vt_copy_to_host_async(void *dst_host, const void *src_dev, size_t n_bytes, void *stream) {

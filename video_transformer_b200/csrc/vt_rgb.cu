@@ -255,13 +255,15 @@ rgb_vscale_fast8(const int16_t *__restrict__ my, const int16_t *__restrict__ mu,
 // One block produces a tile of RGB_TW x RGB_TH output pixels of one picture in a single pass over the source:
 //   phase 1  the horizontal taps of every source row the tile's vertical windows touch, straight from the NV12
 //            surface (dp2a on funnel-shifted words, U and V from one permuted word) into SHARED memory as libswscale's
-//            15-bit intermediates -- they never travel to HBM (the three-launch path writes and re-reads 3.3 MB of
-//            int16 planes per 768x768 picture, twice the algorithmic bytes of the whole conversion);
-//   phase 2  vertical taps + BT.601 matrix out of shared memory, four pixels (two chroma samples) per thread and row,
-//            clamp folded into cvt.pack.sat, 12 bytes per thread as three 32-bit stores.
+//            15-bit intermediates, already widened to 32 bits -- they never travel to HBM (the three-launch path writes
+//            and re-reads 3.3 MB of int16 planes per 768x768 picture, twice the algorithmic bytes of the conversion);
+//   phase 2  vertical taps + BT.601 matrix out of shared memory: a thread owns two quads of four pixels in a row; the
+//            row's coefficients and the shared-memory offsets of its (clamped) tap rows were tabulated once per tile,
+//            every operand arrives through a 128-bit shared load and feeds IMAD directly; the clamp is folded into
+//            cvt.pack.sat and 12 bytes per quad leave as three 32-bit stores.
 // Source rows shared by vertically adjacent tiles are re-read (L2 hits) and their horizontal taps recomputed:
-// (LVT - 1) / (RGB_TH x vertical ratio) extra, ~10 % for 720p -> 768x768.
-constexpr int RGB_TW = 64, RGB_TH = 32, RGB_THREADS = 256;
+// about 5 % (luma) / 13 % (chroma) extra for 720p -> 768x768.
+constexpr int RGB_TW = 64, RGB_TH = 64, RGB_THREADS = 256;
 
 struct RgbTileArgs {
     const uint8_t *src;
@@ -277,13 +279,25 @@ struct RgbTileArgs {
     RgbConst k;
 };
 
+__device__ __forceinline__ int4 lds_s32x4(uint32_t addr) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+#ifndef VT_RGB_MIN_BLOCKS
+#define VT_RGB_MIN_BLOCKS 5
+#endif
 template <int HP, int LVT, int CVT>
-__global__ void __launch_bounds__(RGB_THREADS)
+__global__ void __launch_bounds__(RGB_THREADS, VT_RGB_MIN_BLOCKS)
 rgb_tile_kernel(const __grid_constant__ RgbTileArgs a) {
-    extern __shared__ __align__(16) int16_t rgb_sm[];
-    int16_t *ys = rgb_sm;                                        // [nrl_max][RGB_TW]
-    int16_t *us = ys + (size_t)a.nrl_max * RGB_TW;               // [nrc_max][RGB_TW / 2]
-    int16_t *vs = us + (size_t)a.nrc_max * (RGB_TW / 2);
+    extern __shared__ __align__(16) int rgb_sm[];
+    constexpr int VT = LVT + CVT;                                // table entries per output row ...
+    constexpr int VTP = (VT + 3) & ~3;                           // ... padded so that rows are 16-byte aligned
+    int *ys = rgb_sm;                                            // [nrl_max][RGB_TW]
+    int *cs = ys + a.nrl_max * RGB_TW;                           // [nrc_max][RGB_TW / 4][U0 U1 V0 V1]
+    int *tcoef = cs + a.nrc_max * RGB_TW;                        // [RGB_TH][VT] coefficients, luma taps then chroma taps
+    int *toff = tcoef + RGB_TH * VTP;                            // [RGB_TH][VT] byte offsets of the tap rows in ys / cs
     const int x0 = blockIdx.x * RGB_TW, y0 = blockIdx.y * RGB_TH;
     const int y1 = min(a.dh, y0 + RGB_TH);
     const int lrow0 = __ldg(a.lvp + y0), lrow1 = min(__ldg(a.lvp + y1 - 1) + LVT - 1, a.sh - 1);
@@ -291,38 +305,69 @@ rgb_tile_kernel(const __grid_constant__ RgbTileArgs a) {
     const int nrl = lrow1 - lrow0 + 1, nrc = crow1 - crow0 + 1;
     const uint8_t *frame = a.src + (size_t)blockIdx.z * a.src_fs;
     const int pw = a.pitch >> 2, wl = pw - 1;
-    // ---- phase 1, luma: thread = (column, row group)
+    // ---- per-tile tables: coefficient and shared-memory offset of every (output row, tap)
+    for (int i = threadIdx.x; i < (y1 - y0) * VT; i += RGB_THREADS) {
+        const int yr = i / VT, j = i - yr * VT, y = y0 + yr, t = yr * VTP + j;
+        if (j < LVT) {
+            tcoef[t] = __ldg(a.lvc + y * LVT + j);
+            toff[t] = (min(__ldg(a.lvp + y) + j, a.sh - 1) - lrow0) * (RGB_TW * 4);
+        } else {
+            tcoef[t] = __ldg(a.cvc + y * CVT + (j - LVT));
+            toff[t] = (min(__ldg(a.cvp + y) + (j - LVT), a.csh - 1) - crow0) * (RGB_TW * 4);
+        }
+    }
+    // ---- phase 1, luma: thread = (column, row group); the common case addresses its words with immediates
     {
         constexpr int G = RGB_THREADS / RGB_TW;
+        constexpr int NAW = (HP + 1) / 2, NW = NAW + 1;
         const int col = threadIdx.x % RGB_TW, g = threadIdx.x / RGB_TW, x = x0 + col;
         if (x < a.dw) {
-            constexpr int NAW = (HP + 1) / 2, NW = NAW + 1;
             const int p = __ldg(a.lhp + x);
             const int w0 = p >> 2;
             const uint32_t sh = (uint32_t)(p & 3) * 8u;
-            int wi[NW];
-#pragma unroll
-            for (int i = 0; i < NW; i++) wi[i] = min(w0 + i, wl);
             uint32_t c[HP];
             hs_load_pairs<HP>(a.lhc + (size_t)x * HP, c);
-            const uint32_t *row = reinterpret_cast<const uint32_t *>(frame + (size_t)(lrow0 + g) * a.pitch);
-#pragma unroll 2
-            for (int r = g; r < nrl; r += G) {
-                uint32_t w[NW];
+            int *o = ys + g * RGB_TW + col;
+            if (w0 + NW - 1 <= wl) {
+                const uint32_t *row = reinterpret_cast<const uint32_t *>(frame) + (size_t)(lrow0 + g) * pw + w0;
+#pragma unroll 4
+                for (int r = g; r < nrl; r += G) {
+                    uint32_t w[NW];
 #pragma unroll
-                for (int i = 0; i < NW; i++) w[i] = __ldg(row + wi[i]);
-                int v = 0;
+                    for (int i = 0; i < NW; i++) w[i] = __ldg(row + i);
+                    int v = 0;
 #pragma unroll
-                for (int i = 0; i < HP; i++) {
-                    const uint32_t al = __funnelshift_r(w[i >> 1], w[(i >> 1) + 1], sh);
-                    v = (i & 1) ? hs_dp2a_hi(c[i], al, v) : hs_dp2a_lo(c[i], al, v);
+                    for (int i = 0; i < HP; i++) {
+                        const uint32_t al = __funnelshift_r(w[i >> 1], w[(i >> 1) + 1], sh);
+                        v = (i & 1) ? hs_dp2a_hi(c[i], al, v) : hs_dp2a_lo(c[i], al, v);
+                    }
+                    *o = min(v >> 7, 32767);
+                    row += G * pw;
+                    o += G * RGB_TW;
                 }
-                ys[r * RGB_TW + col] = (int16_t)min(v >> 7, 32767);
-                row += (size_t)G * pw;
+            } else {                                             // last columns of a row: words clamped to the row's end
+                int wi[NW];
+#pragma unroll
+                for (int i = 0; i < NW; i++) wi[i] = min(w0 + i, wl);
+                const uint32_t *row = reinterpret_cast<const uint32_t *>(frame) + (size_t)(lrow0 + g) * pw;
+                for (int r = g; r < nrl; r += G) {
+                    uint32_t w[NW];
+#pragma unroll
+                    for (int i = 0; i < NW; i++) w[i] = __ldg(row + wi[i]);
+                    int v = 0;
+#pragma unroll
+                    for (int i = 0; i < HP; i++) {
+                        const uint32_t al = __funnelshift_r(w[i >> 1], w[(i >> 1) + 1], sh);
+                        v = (i & 1) ? hs_dp2a_hi(c[i], al, v) : hs_dp2a_lo(c[i], al, v);
+                    }
+                    *o = min(v >> 7, 32767);
+                    row += G * pw;
+                    o += G * RGB_TW;
+                }
             }
         }
     }
-    // ---- phase 1, chroma: thread = (chroma column, row group), U and V together
+    // ---- phase 1, chroma: thread = (chroma column, row group), U and V together; a quad's four values are adjacent
     {
         constexpr int CW = RGB_TW / 2, G = RGB_THREADS / CW;
         const int col = threadIdx.x % CW, g = threadIdx.x / CW, x = (x0 >> 1) + col;
@@ -330,74 +375,107 @@ rgb_tile_kernel(const __grid_constant__ RgbTileArgs a) {
             const int p = 2 * __ldg(a.chp + x);
             const int w0 = p >> 2;
             const uint32_t sh = (uint32_t)(p & 3) * 8u;
-            int wi[HP + 1];
-#pragma unroll
-            for (int i = 0; i < HP + 1; i++) wi[i] = min(w0 + i, wl);
             uint32_t c[HP];
             hs_load_pairs<HP>(a.chc + (size_t)x * HP, c);
-            const uint32_t *row = reinterpret_cast<const uint32_t *>(frame + (size_t)a.pitch * a.sh + (size_t)(crow0 + g) * a.pitch);
+            int *o = cs + g * RGB_TW + (col >> 1) * 4 + (col & 1);
+            const uint32_t *plane = reinterpret_cast<const uint32_t *>(frame + (size_t)a.pitch * a.sh);
+            if (w0 + HP <= wl) {
+                const uint32_t *row = plane + (size_t)(crow0 + g) * pw + w0;
 #pragma unroll 2
-            for (int r = g; r < nrc; r += G) {
-                uint32_t w[HP + 1];
+                for (int r = g; r < nrc; r += G) {
+                    uint32_t w[HP + 1];
 #pragma unroll
-                for (int i = 0; i < HP + 1; i++) w[i] = __ldg(row + wi[i]);
-                int u = 0, v = 0;
+                    for (int i = 0; i < HP + 1; i++) w[i] = __ldg(row + i);
+                    int u = 0, v = 0;
 #pragma unroll
-                for (int i = 0; i < HP; i++) {
-                    const uint32_t pw4 = __byte_perm(__funnelshift_r(w[i], w[i + 1], sh), 0u, 0x3120);
-                    u = hs_dp2a_lo(c[i], pw4, u);
-                    v = hs_dp2a_hi(c[i], pw4, v);
+                    for (int i = 0; i < HP; i++) {
+                        const uint32_t pw4 = __byte_perm(__funnelshift_r(w[i], w[i + 1], sh), 0u, 0x3120);
+                        u = hs_dp2a_lo(c[i], pw4, u);
+                        v = hs_dp2a_hi(c[i], pw4, v);
+                    }
+                    o[0] = min(u >> 7, 32767);
+                    o[2] = min(v >> 7, 32767);
+                    row += G * pw;
+                    o += G * RGB_TW;
                 }
-                us[r * CW + col] = (int16_t)min(u >> 7, 32767);
-                vs[r * CW + col] = (int16_t)min(v >> 7, 32767);
-                row += (size_t)G * pw;
+            } else {
+                int wi[HP + 1];
+#pragma unroll
+                for (int i = 0; i < HP + 1; i++) wi[i] = min(w0 + i, wl);
+                const uint32_t *row = plane + (size_t)(crow0 + g) * pw;
+                for (int r = g; r < nrc; r += G) {
+                    uint32_t w[HP + 1];
+#pragma unroll
+                    for (int i = 0; i < HP + 1; i++) w[i] = __ldg(row + wi[i]);
+                    int u = 0, v = 0;
+#pragma unroll
+                    for (int i = 0; i < HP; i++) {
+                        const uint32_t pw4 = __byte_perm(__funnelshift_r(w[i], w[i + 1], sh), 0u, 0x3120);
+                        u = hs_dp2a_lo(c[i], pw4, u);
+                        v = hs_dp2a_hi(c[i], pw4, v);
+                    }
+                    o[0] = min(u >> 7, 32767);
+                    o[2] = min(v >> 7, 32767);
+                    row += G * pw;
+                    o += G * RGB_TW;
+                }
             }
         }
     }
     __syncthreads();
-    // ---- phase 2: thread = (quad of four pixels, row group)
-    constexpr int NQ = RGB_TW / 4, RG = RGB_THREADS / NQ;
-    const int q = threadIdx.x % NQ, rg = threadIdx.x / NQ;
-    if (x0 + 4 * q >= a.dw) return;
+    // ---- phase 2: thread = (row, quad group); quads qg and qg + 8 of the row
+    constexpr int QPR = RGB_TW / 4 / 2;                          // threads per row
+    constexpr int RG = RGB_THREADS / QPR;                        // rows per pass
+    const int qg = threadIdx.x % QPR, rg = threadIdx.x / QPR;
     const int base = 326 * a.k.cy - (400 << 16) + 0x8000;
-    for (int y = y0 + rg; y < y1; y += RG) {
-        const int lr = __ldg(a.lvp + y), cr = __ldg(a.cvp + y);
-        int ya[4] = {1 << 18, 1 << 18, 1 << 18, 1 << 18}, ua[2] = {1 << 18, 1 << 18}, va[2] = {1 << 18, 1 << 18};
+    const int cy = a.k.cy;
+    const uint32_t ysb = smem_u32(ys), csb = smem_u32(cs);       // 32-bit shared addresses: one add per load
+    uint8_t *dframe = a.dst + (size_t)blockIdx.z * a.dst_fs;
+    for (int yr = rg; yr < y1 - y0; yr += RG) {
+        int tc[VTP], to[VTP];
 #pragma unroll
-        for (int j = 0; j < LVT; j++) {
-            const int c = __ldg(a.lvc + y * LVT + j);
-            const uint2 w = *reinterpret_cast<const uint2 *>(ys + (min(lr + j, a.sh - 1) - lrow0) * RGB_TW + 4 * q);
-            ya[0] += ((int)(w.x << 16) >> 16) * c; ya[1] += ((int)w.x >> 16) * c;
-            ya[2] += ((int)(w.y << 16) >> 16) * c; ya[3] += ((int)w.y >> 16) * c;
+        for (int j = 0; j < VTP; j += 4) {
+            const int4 c4 = *reinterpret_cast<const int4 *>(tcoef + yr * VTP + j);
+            const int4 o4 = *reinterpret_cast<const int4 *>(toff + yr * VTP + j);
+            tc[j] = c4.x; tc[j + 1] = c4.y; tc[j + 2] = c4.z; tc[j + 3] = c4.w;
+            to[j] = o4.x; to[j + 1] = o4.y; to[j + 2] = o4.z; to[j + 3] = o4.w;
         }
+        uint32_t *drow = reinterpret_cast<uint32_t *>(dframe + ((size_t)(y0 + yr) * a.dw + x0) * 3);
 #pragma unroll
-        for (int j = 0; j < CVT; j++) {
-            const int c = __ldg(a.cvc + y * CVT + j);
-            const int o = (min(cr + j, a.csh - 1) - crow0) * (RGB_TW / 2) + 2 * q;
-            const uint32_t wu = *reinterpret_cast<const uint32_t *>(us + o), wv = *reinterpret_cast<const uint32_t *>(vs + o);
-            ua[0] += ((int)(wu << 16) >> 16) * c; ua[1] += ((int)wu >> 16) * c;
-            va[0] += ((int)(wv << 16) >> 16) * c; va[1] += ((int)wv >> 16) * c;
-        }
-        int px[12];
+        for (int h2 = 0; h2 < 2; h2++) {
+            const int q = qg + h2 * QPR;
+            if (x0 + 4 * q >= a.dw) break;
+            int ya[4] = {1 << 18, 1 << 18, 1 << 18, 1 << 18}, ca[4] = {1 << 18, 1 << 18, 1 << 18, 1 << 18};
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int uc = max(0, min(255, ua[h] >> 19)), vc = max(0, min(255, va[h] >> 19));
-            const int r_off = ((vc * a.k.crv) >> 16) - (a.k.crv >> 9);
-            const int g_off = ((uc * a.k.cgu) >> 16) - (a.k.cgu >> 9) + ((vc * a.k.cgv) >> 16) - (a.k.cgv >> 9);
-            const int b_off = ((uc * a.k.cbu) >> 16) - (a.k.cbu >> 9);
-            const int ar = r_off * a.k.cy + base, ag = g_off * a.k.cy + base, ab = b_off * a.k.cy + base;
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int yv = ya[2 * h + e] >> 19;
-                px[6 * h + 3 * e] = (yv * a.k.cy + ar) >> 16;
-                px[6 * h + 3 * e + 1] = (yv * a.k.cy + ag) >> 16;
-                px[6 * h + 3 * e + 2] = (yv * a.k.cy + ab) >> 16;
+            for (int j = 0; j < LVT; j++) {
+                const int4 w = lds_s32x4(ysb + (uint32_t)to[j] + (uint32_t)q * 16u);
+                ya[0] += w.x * tc[j]; ya[1] += w.y * tc[j]; ya[2] += w.z * tc[j]; ya[3] += w.w * tc[j];
             }
+#pragma unroll
+            for (int j = 0; j < CVT; j++) {
+                const int4 w = lds_s32x4(csb + (uint32_t)to[LVT + j] + (uint32_t)q * 16u);      // U0 U1 V0 V1
+                ca[0] += w.x * tc[LVT + j]; ca[1] += w.y * tc[LVT + j]; ca[2] += w.z * tc[LVT + j]; ca[3] += w.w * tc[LVT + j];
+            }
+            int px[12];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int uc = max(0, min(255, ca[h] >> 19)), vc = max(0, min(255, ca[2 + h] >> 19));
+                const int r_off = ((vc * a.k.crv) >> 16) - (a.k.crv >> 9);
+                const int g_off = ((uc * a.k.cgu) >> 16) - (a.k.cgu >> 9) + ((vc * a.k.cgv) >> 16) - (a.k.cgv >> 9);
+                const int b_off = ((uc * a.k.cbu) >> 16) - (a.k.cbu >> 9);
+                const int ar = r_off * cy + base, ag = g_off * cy + base, ab = b_off * cy + base;
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int yv = ya[2 * h + e] >> 19;
+                    px[6 * h + 3 * e] = (yv * cy + ar) >> 16;
+                    px[6 * h + 3 * e + 1] = (yv * cy + ag) >> 16;
+                    px[6 * h + 3 * e + 2] = (yv * cy + ab) >> 16;
+                }
+            }
+            drow[3 * q] = rgb_pack4(px[3], px[2], px[1], px[0]);
+            drow[3 * q + 1] = rgb_pack4(px[7], px[6], px[5], px[4]);
+            drow[3 * q + 2] = rgb_pack4(px[11], px[10], px[9], px[8]);
         }
-        uint32_t *d = reinterpret_cast<uint32_t *>(a.dst + (size_t)blockIdx.z * a.dst_fs + ((size_t)y * a.dw + x0 + 4 * q) * 3);
-        d[0] = rgb_pack4(px[3], px[2], px[1], px[0]);
-        d[1] = rgb_pack4(px[7], px[6], px[5], px[4]);
-        d[2] = rgb_pack4(px[11], px[10], px[9], px[8]);
     }
 }
 
@@ -500,7 +578,8 @@ extern "C" int vt_rgb_plan_create(int sw, int sh, int dw, int dh, int flags, vt_
                 p->nrl_max = std::max(p->nrl_max, std::min(lvp[y1 - 1] + p->vtl - 1, sh - 1) - lvp[y0] + 1);
                 p->nrc_max = std::max(p->nrc_max, std::min(cvp[y1 - 1] + p->vtc - 1, p->csh - 1) - cvp[y0] + 1);
             }
-            p->fused_smem = ((size_t)p->nrl_max * vt::RGB_TW + (size_t)p->nrc_max * vt::RGB_TW) * sizeof(int16_t);
+            p->fused_smem = ((size_t)p->nrl_max * vt::RGB_TW + (size_t)p->nrc_max * vt::RGB_TW +
+                             2 * (size_t)vt::RGB_TH * ((p->vtl + p->vtc + 3) & ~3)) * sizeof(int);
             if (p->fused_smem > 96 * 1024 || p->nrl_max <= 0 || p->nrc_max <= 0) p->fhp = 0;   // very steep ratios: three-launch path
         }
     }

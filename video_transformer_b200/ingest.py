@@ -87,6 +87,7 @@ class SegmentIngestor:
         if self.dev.type == "cuda" and self.dev.index is None:
             self.dev = torch.device("cuda", torch.cuda.current_device())
         self.host = host_bytes if host_bytes is not None else np.memmap(index.path, dtype=np.uint8, mode="r")
+        self._src_map = None             # private mapping of the file, page-locked: H2D straight from the page cache
         n = index.n_frames
         L = lib()
         self.payload = np.zeros(n, np.uint64)
@@ -148,7 +149,7 @@ class SegmentIngestor:
         self.stage_thread = os.environ.get("VT_INGEST_THREAD", "1") == "1"
         for _ in range(self.n_slots):
             self.slots.append({
-                "bs_host": torch.empty(self.bs_cap, dtype=torch.uint8, pin_memory=True),
+                "bs_host": None, "src_lo": 0,
                 "bs_dev": torch.empty(self.bs_cap + 64, dtype=torch.uint8, device=self.dev),
                 "surf": torch.empty((B, self.rows, self.pitch), dtype=torch.uint8, device=self.dev),
                 "out": torch.empty((B, self.frame_bytes), dtype=torch.uint8, device=self.dev),
@@ -165,6 +166,7 @@ class SegmentIngestor:
                 "used": False, "pending": None, "kept": None, "land": None, "wfut": None,
             })
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
+        self._register_source()
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self._pool = None
@@ -175,6 +177,50 @@ class SegmentIngestor:
             self._copy_pool = ThreadPoolExecutor(max_workers=self._copy_threads)
 
     # ------------------------------------------------------------------------------------------------------
+    def _register_source(self) -> None:
+        """Map the bitstream file privately and page-lock the mapping, so that the copy-in stream reads the page cache
+        directly and the staging memcpy (one more pass over the host's memory per batch) disappears.  Off with
+        VT_INGEST_DIRECT_H2D=0; files over VT_INGEST_DIRECT_MAX_GB (default 16) and file systems whose mappings cannot be
+        pinned keep the staging path."""
+        import mmap
+        import os
+        if os.environ.get("VT_INGEST_DIRECT_H2D", "1") != "1" or self.dev.type != "cuda":
+            return
+        try:
+            size = os.path.getsize(self.idx.path)
+            if size == 0 or size > float(os.environ.get("VT_INGEST_DIRECT_MAX_GB", "16")) * (1 << 30):
+                return
+            fd = os.open(self.idx.path, os.O_RDONLY)
+            try:
+                mm = mmap.mmap(fd, size, flags=mmap.MAP_PRIVATE, prot=mmap.PROT_READ | mmap.PROT_WRITE)
+            finally:
+                os.close(fd)
+        except (OSError, ValueError):
+            return
+        arr = np.frombuffer(mm, dtype=np.uint8)
+        if lib().vt_host_register_source(c_void_p(arr.ctypes.data), size) != 0:
+            del arr
+            mm.close()
+            return
+        self._src_map = (mm, arr, arr.ctypes.data)
+
+    def close(self) -> None:
+        if self._src_map is not None:
+            mm, arr, base = self._src_map
+            self._src_map = None
+            lib().vt_host_unregister(c_void_p(base))
+            del arr
+            try:
+                mm.close()
+            except (BufferError, ValueError):
+                pass
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
     def _stage_bitstream(self, slot, b0: int, b1: int):
         """Copy the file bytes pictures [b0,b1) need into the slot's pinned buffer; return payload offsets
         relative to the device copy (or NO_PAYLOAD for pictures that repeat one from before b0)."""
@@ -187,6 +233,13 @@ class SegmentIngestor:
         nbytes = hi - lo
         if nbytes > self.bs_cap:
             raise _lib.VtError(_lib.VT_ERR_NOMEM, "batch bitstream %d B exceeds staging %d B" % (nbytes, self.bs_cap))
+        slot["src_lo"] = lo
+        if self._src_map is not None:        # the copy engine reads the file's pages itself
+            first_idr = idr[0]
+            pay[first_idr - b0:] = self.payload[first_idr:b1] - np.uint64(lo)
+            return pay, nbytes
+        if slot["bs_host"] is None:
+            slot["bs_host"] = torch.empty(self.bs_cap, dtype=torch.uint8, pin_memory=True)
         dst = slot["bs_host"].numpy()
         if self._copy_pool is not None and nbytes >= (4 << 20):
             # PCM-intra streams are uncompressed (115 KB per 1080p picture on average): one thread copies ~8 GB/s out of
@@ -307,7 +360,12 @@ class SegmentIngestor:
                 pay, nbytes = self._stage_bitstream(slot, b0, b1)
             with torch.cuda.stream(self.s_in):
                 if nbytes:
-                    slot["bs_dev"][:nbytes].copy_(slot["bs_host"][:nbytes], non_blocking=True)
+                    if self._src_map is not None:
+                        check(L.vt_copy_to_device_async(c_void_p(slot["bs_dev"].data_ptr()),
+                                                        c_void_p(self._src_map[2] + slot["src_lo"]), nbytes,
+                                                        c_void_p(self.s_in.cuda_stream)))
+                    else:
+                        slot["bs_dev"][:nbytes].copy_(slot["bs_host"][:nbytes], non_blocking=True)
                     self.h2d_bytes += nbytes
                 slot["ev_in"].record(self.s_in)
             with torch.cuda.stream(self.s_cmp):
