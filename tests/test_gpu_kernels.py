@@ -284,3 +284,38 @@ def test_scale_into_a_destination_that_is_not_8_byte_aligned(cuda, oracle_c, off
         ey, eu, ev = oracle_c.scale_yuv420p(y, u, v, dw, dh, oracle_c.BICUBIC)
         assert np.array_equal(got[f], np.concatenate([ey.reshape(-1), eu.reshape(-1), ev.reshape(-1)])), f
     assert int(raw[:offset].sum()) == 0 and int(raw[offset + n * fb:].sum()) == 0    # nothing written outside
+
+
+@pytest.mark.parametrize("sw,sh,pitch,dw,dh,fused", [(1920, 1080, 2048, 1280, 720, True), (1920, 1080, 1920, 1280, 720, True),
+                                                     (3840, 2160, 3840, 2560, 1440, True), (768, 432, 768, 512, 288, True),
+                                                     (960, 540, 1024, 640, 360, False),      # 640 is not a whole number of strips
+                                                     (1280, 720, 1280, 640, 360, False)])    # 2:1: separate kernels
+def test_fused_scale_and_score_equals_the_separate_kernels(cuda, oracle_c, sw, sh, pitch, dw, dh, fused):
+    """K3 inside K2's luma pass: frames, SADs and histograms equal the two standalone kernels bit for bit (and the
+    oracle), with and without a picture preceding the batch; every source pixel is counted exactly once."""
+    rng = np.random.default_rng(sw * 3 + dh)
+    n = 5
+    buf = _nv12_batch(rng, n, sw, sh, pitch)
+    buf[2, : sh // 3] = 200                              # a flat region: every lane hits the same counter row
+    buf[3] = buf[2]                                      # identical pictures: SAD 0
+    prev = _nv12_batch(rng, 1, sw, sh, pitch)[0]
+    plan = ops.ScalePlan(sw, sh, dw, dh)
+    assert plan.fuses_score == fused
+    d = torch.from_numpy(buf).to(cuda)
+    dprev = torch.from_numpy(prev).to(cuda)
+    rows = sh + sh // 2
+    ref_out = plan.scale_nv12(d.view(-1), pitch, n).cpu().numpy()
+    for p0 in (None, dprev):
+        ref_sad, ref_hist = ops.sad_hist(d.view(-1), sw, sh, pitch, rows * pitch, n, prev0=None if p0 is None else p0.view(-1))
+        before = ops.lib().vt_launch_count()
+        out, sad, hist = plan.scale_score_nv12(d.view(-1), pitch, n, prev0=None if p0 is None else p0.view(-1))
+        launches = ops.lib().vt_launch_count() - before
+        assert launches == (2 if fused else 3)           # luma(+score) and chroma / score, luma, chroma
+        assert np.array_equal(out.cpu().numpy(), ref_out)
+        assert np.array_equal(sad.cpu().numpy(), ref_sad.cpu().numpy())
+        assert np.array_equal(hist.cpu().numpy(), ref_hist.cpu().numpy())
+        assert int(hist.cpu().numpy().view(np.uint32).sum()) == n * sw * sh
+    y0 = buf[0, :sh, :sw]
+    s, h = oracle_c.sad_hist(y0, prev[:sh, :sw])
+    assert int(sad.cpu()[0]) == s and np.array_equal(hist.cpu().numpy()[0].view(np.uint32), h)
+    assert int(sad.cpu()[3]) == 0

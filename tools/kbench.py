@@ -77,6 +77,11 @@ if "overlap" in ks:
         _lib.check(L.vt_sad_hist_u8(c_void_p(surf.data_ptr()), pitch, rows * pitch, sw, sh, None, F,
                                     c_void_p(sad.data_ptr()), c_void_p(hist.data_ptr()), sp))
     run("scale;score", serial, sw * sh * 3 // 2 + fb + 2 * sw * sh)
+if "fused" in ks:
+    print(json.dumps({"fuses_score": plan.fuses_score}))
+    run("scale+score (one call)", lambda: _lib.check(L.vt_scale_score_nv12_to_yuv420p(plan._h, c_void_p(surf.data_ptr()), pitch,
+        rows * pitch, None, c_void_p(out.data_ptr()), fb, F, c_void_p(sad.data_ptr()), c_void_p(hist.data_ptr()), sp)),
+        sw * sh * 3 // 2 + fb + sw * sh)
 if "score" in ks:
     run("score", lambda: _lib.check(L.vt_sad_hist_u8(c_void_p(surf.data_ptr()), pitch, rows * pitch, sw, sh, None, F,
         c_void_p(sad.data_ptr()), c_void_p(hist.data_ptr()), sp)), 2 * sw * sh)

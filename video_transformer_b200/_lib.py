@@ -38,6 +38,9 @@ SIGNATURES = {
     "vt_scale_plan_stream_info": (c_int, [c_void_p, c_int, c_void_p]),
     "vt_scale_plane_u8": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "vt_scale_nv12_to_yuv420p": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_size_t, c_int, c_void_p]),
+    "vt_scale_plan_fuses_score": (c_int, [c_void_p]),
+    "vt_scale_score_nv12_to_yuv420p": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_size_t, c_int,
+                                               c_void_p, c_void_p, c_void_p]),
     "vt_nv12_to_yuv420p": (c_int, [c_void_p, c_int, c_size_t, c_int, c_int, c_void_p, c_size_t, c_int, c_void_p]),
     "vt_nv12_to_rgb24": (c_int, [c_void_p, c_int, c_size_t, c_int, c_int, c_void_p, c_size_t, c_int, c_void_p]),
     "vt_rgb_plan_create": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p)]),

@@ -505,6 +505,9 @@ extern "C" int vt_ingest_batch_pcm(const vt_scale_plan *plan, const uint8_t *bs_
                                    uint8_t *out_dev, size_t out_frame_bytes, void *stream) {
     int rc = vt_h264_pcm_decode(bs_dev, payload_off, n_frames, width, height, prev_dev, nv12_dev, pitch, surface_bytes, stream);
     if (rc) return rc;
+    if (plan && out_dev)                      // K2 + K3 (one luma pass where the plan fuses them)
+        return vt_scale_score_nv12_to_yuv420p(plan, nv12_dev, pitch, surface_bytes, prev_dev, out_dev, out_frame_bytes,
+                                              n_frames, sad_dev, hist_dev, stream);
     rc = vt_sad_hist_u8(nv12_dev, pitch, surface_bytes, width, height, prev_dev, n_frames, sad_dev, hist_dev, stream);
     if (rc || !out_dev) return rc;
     if (plan) return vt_scale_nv12_to_yuv420p(plan, nv12_dev, pitch, surface_bytes, out_dev, out_frame_bytes, n_frames, stream);

@@ -335,6 +335,41 @@ extern "C" int vt_scale_plane_u8(const vt_scale_plan *plan, int chroma, const ui
     return vt::scale_plane_generic(plan, chroma, src, src_pitch, 1, 0, dst, dst_pitch, 1, 0, 0, (cudaStream_t)stream);
 }
 
+// 1 when vt_scale_score_nv12_to_yuv420p runs K3 inside the luma pass of K2 for this plan (suitably aligned buffers)
+extern "C" int vt_scale_plan_fuses_score(const vt_scale_plan *p) { return p && p->pair[0].ok && p->pair[0].score_ok ? 1 : 0; }
+
+// K2 + K3 in one call: scaled frames plus SAD / histogram of the SOURCE luma.  Where the plan allows (exact 3:2 luma on
+// the adjacent-column layout: 1080p -> 720p, 2160p -> 1440p ...) the luma kernel counts the source rows it already
+// holds in shared memory, so the source luma is fetched from HBM once for both results; otherwise the score kernel runs
+// first and the scaler after it.  Results are identical either way.
+extern "C" int vt_scale_score_nv12_to_yuv420p(const vt_scale_plan *p, const uint8_t *src, int src_pitch, size_t src_fs,
+                                              const uint8_t *prev0, uint8_t *dst, size_t dst_fs, int n_frames,
+                                              uint64_t *sad_dev, uint32_t *hist_dev, void *stream) {
+    if (!p || !src || !dst || !sad_dev || !hist_dev || n_frames <= 0 || src_pitch < p->sw) {
+        vt::set_error("vt_scale_score_nv12_to_yuv420p: bad arguments");
+        return VT_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool aligned = ((uintptr_t)src % 16 == 0) && (src_pitch % 16 == 0) && (src_fs % 16 == 0) &&
+                         ((uintptr_t)dst % 8 == 0) && (dst_fs % 8 == 0) && (p->sw % 2 == 0) && (p->sh % 2 == 0) &&
+                         (!prev0 || (uintptr_t)prev0 % 4 == 0);
+    const char *force = getenv("VT_SCALE_KERNEL");
+    if (aligned && vt_scale_plan_fuses_score(p) && !force) {
+        VT_CUDA(cudaMemsetAsync(sad_dev, 0, sizeof(uint64_t) * (size_t)n_frames, st));
+        VT_CUDA(cudaMemsetAsync(hist_dev, 0, sizeof(uint32_t) * 256 * (size_t)n_frames, st));
+        const vt::PairScore sc{prev0, sad_dev, hist_dev};
+        int rc = vt::launch_pair(p, 0, src, src_pitch, src_fs, dst, dst_fs, n_frames, st, &sc);
+        if (rc) return rc;
+        if (p->pair[1].ok) return vt::launch_pair(p, 1, src, src_pitch, src_fs, dst, dst_fs, n_frames, st);
+        // (the chroma planes of such plans always qualify; kept for completeness)
+        vt::set_error("vt_scale_score_nv12_to_yuv420p: chroma plane outside the pair kernel");
+        return VT_ERR_UNSUPPORTED;
+    }
+    int rc = vt::launch_score(src, src_pitch, src_fs, p->sw, p->sh, prev0, n_frames, sad_dev, hist_dev, st);
+    if (rc) return rc;
+    return vt_scale_nv12_to_yuv420p(p, src, src_pitch, src_fs, dst, dst_fs, n_frames, stream);
+}
+
 extern "C" int vt_scale_nv12_to_yuv420p(const vt_scale_plan *p, const uint8_t *src, int src_pitch, size_t src_fs,
                                         uint8_t *dst, size_t dst_fs, int n_frames, void *stream) {
     if (!p || !src || !dst || n_frames <= 0 || src_pitch < p->sw) {

@@ -79,7 +79,20 @@ struct PairArgs {
     int reg_lo, reg_hi, align_p, align_r0;
     unsigned long long *dbg_times;     // VT_PAIR_TIMES builds: per warp {start, end} globaltimer (null otherwise)
     int sc[24];                        // [phase][TV] front-padded coefficients of the pattern's output rows
+    // fused scene score (kernels instantiated with SC = true): SAD and 256-bin histogram of the SOURCE luma, taken from
+    // the rows the scaler already has in shared memory.  Every source pixel is counted by exactly one warp: a lane
+    // owns the 12 source bytes under its 8 output columns, an item owns the source rows from the end of the previous
+    // item's last window to the end of its own.
+    const uint8_t *sc_src;             // frame 0's luma plane (the surface the tensor map describes)
+    const uint8_t *sc_prev0;           // luma of the picture preceding frame 0, or null (then frame 0's SAD is 0)
+    unsigned long long sc_fs;          // bytes between frames
+    int sc_pitch, sc_rows;             // source pitch and rows
+    unsigned long long *sc_sad;        // [n_frames], zeroed before the launch
+    uint32_t *sc_hist;                 // [n_frames][256], zeroed before the launch
+    int sc_cnt_off;                    // byte offset of the warp's counters inside its shared memory
 };
+
+constexpr int PAIR_SC_COUNTER_BYTES = 128 * 32 * 4;   // per warp: 128 rows x 32 lanes of packed u16 pairs (bins r, r + 128)
 
 __device__ __forceinline__ int dp2a_lo(uint32_t coef_pair, uint32_t pix, int acc) {
     int d;
@@ -234,8 +247,8 @@ __host__ __device__ constexpr int hs_words(int hs, bool uv, int ncol, int hp) {
 //     between the loaded words and ONE byte-shifted copy of them (luma), or one byte permute per sample pair that
 //     serves U (dp2a.lo) and V (dp2a.hi) at once (chroma).  Five loads per source row per lane instead of twelve,
 //     no per-pair shifts or selectors, and the lane's output bytes leave as one 8-byte (2 x 4-byte) store.
-template <int HP, int TV, bool UV, int MASK, int Q, int HS>
-__global__ void __launch_bounds__(128, pair_min_blocks(HP, TV))
+template <int HP, int TV, bool UV, int MASK, int Q, int HS, bool SC = false>
+__global__ void __launch_bounds__(128, SC ? 2 : pair_min_blocks(HP, TV))
 scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ PairArgs a,
                   const __grid_constant__ VTab<TV> vtab) {
     constexpr int BN = HP + 1;
@@ -264,6 +277,15 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         fence_barrier_init();
     }
     __syncwarp();
+    const uint32_t cnt_lane = wsm + (uint32_t)a.sc_cnt_off + 4u * (uint32_t)lane;   // this lane's column of counters
+    if constexpr (SC) {
+        static_assert(!SC || (HS == 1 && !UV), "the fused score is written for the 3:2 luma layout");
+        const uint32_t z = wsm + (uint32_t)a.sc_cnt_off + 16u * (uint32_t)lane;
+#pragma unroll 4
+        for (int i = 0; i < PAIR_SC_COUNTER_BYTES / (32 * 16); i++)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(z + 512u * i), "r"(0u) : "memory");
+        __syncwarp();
+    }
     const uint32_t bar0 = smem_u32(bars);
     constexpr uint32_t group_bytes = (uint32_t)TV * PAIR_TILE_W;   // tile rows are PAIR_TILE_W bytes apart: row offsets
     uint32_t phases = 0;                                           // inside a group are immediates of the loads
@@ -377,14 +399,61 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                                                                              // the "does a row end here" branch never waits on a load
         uint8_t *dptr = a.dst + (size_t)f * a.dst_fs + (size_t)y0 * a.dw + strip_byte;
 
+        // fused score: rows and bytes this item owns, the previous picture's bytes under them
+        int own_lo = 0;
+        unsigned own_span = 0;
+        uint32_t sad_acc = 0;
+        const uint8_t *prev_lane = nullptr;
+        if constexpr (SC) {
+            own_lo = y0 == a.y_begin ? 0 : vtab.t[(y0 - 1 - a.y_begin) * VS + TV] + 1;
+            const int own_hi = y1 >= a.y_end ? a.sc_rows : vtab.t[(y1 - 1 - a.y_begin) * VS + TV] + 1;
+            own_span = (unsigned)(own_hi - own_lo);
+            // no predecessor: compare the picture with itself (SAD 0 without a branch in the row code)
+            const uint8_t *pf = f > 0 ? a.sc_src + (size_t)(f - 1) * a.sc_fs : (a.sc_prev0 ? a.sc_prev0 : a.sc_src);
+            prev_lane = pf + (a.box_x0[strip] + 4) + 12 * lane;
+        }
         uint32_t ga[NP];
-        auto hpass = [&](int k, int (&out)[NM]) {                            // horizontal pass of the group's row k
+        // ALL:   every row this call may see is owned by the item (the straight-line block must stay branch-free); a
+        //        literal at both call sites, so the tests on it fold at compile time once the lambda is inlined
+        // pvrow: the previous picture's three words under this lane for that row, already in registers (the static
+        //        block requests a whole stage's worth one stage ahead: issued just in time, each row would expose a
+        //        memory latency with only two warps per scheduler to hide it)
+        auto hpass = [&](int k, int (&out)[NM], int srow, const bool ALL, const uint32_t *pvrow) {   // horizontal pass of row k
             if constexpr (HS != 0) {
                 constexpr int NWD = hs_words(HS, UV, NCOL, HP);
                 const uint32_t ra = ga[0] + (uint32_t)k * PAIR_TILE_W;
                 uint32_t w[NWD];
 #pragma unroll
                 for (int i = 0; i < NWD; i++) w[i] = lds_u32(ra + 4u * i);
+                if constexpr (SC) {
+                    // words 1..3 are the 12 source bytes under this lane's 8 output columns
+                    if (ALL || (unsigned)(srow - own_lo) < own_span) {      // warp-uniform
+                        if (ALL) {
+                            sad_acc = sad4(w[1], pvrow[0], sad_acc);
+                            sad_acc = sad4(w[2], pvrow[1], sad_acc);
+                            sad_acc = sad4(w[3], pvrow[2], sad_acc);
+                        } else {
+                            const uint32_t *pp = reinterpret_cast<const uint32_t *>(prev_lane + (size_t)srow * a.sc_pitch);
+                            sad_acc = sad4(w[1], __ldg(pp), sad_acc);
+                            sad_acc = sad4(w[2], __ldg(pp + 1), sad_acc);
+                            sad_acc = sad4(w[3], __ldg(pp + 2), sad_acc);
+                        }
+#pragma unroll
+                        for (int i = 1; i <= 3; i++) {
+                            const uint32_t lo7 = w[i] & 0x7F7F7F7Fu;        // counter row = bin & 127
+                            const uint32_t hi16 = (w[i] >> 3) & 0x10101010u; // shift count of the increment: 16 * (bin >> 7)
+#pragma unroll
+                            for (int b = 0; b < 4; b++) {
+                                // address on the multiply pipe (one-hot dp4a: cnt_lane + 128 * byte_b), increment on the ALU.
+                                // No "memory" clobber: the counters alias nothing the scaler reads and the flush sits
+                                // behind __syncwarp().  (atomicAdd instead of the asm measured 5 % slower.)
+                                const uint32_t addr = (uint32_t)__dp4a(lo7, 0x80u << (8 * b), cnt_lane);
+                                const uint32_t inc = 1u << __byte_perm(hi16, 0u, 0x4440 + b);
+                                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(inc));
+                            }
+                        }
+                    }
+                }
                 if constexpr (!UV) {
                     uint32_t s1[NWD - 1];                                    // the same bytes, one byte further on
 #pragma unroll
@@ -481,6 +550,8 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             }
         };
         int rbase = rs;                                                      // absolute source row of the group's row 0
+        uint32_t pv[SC ? SG * TV : 1][3], pn[SC ? SG * TV : 1][3];           // fused score: previous picture, this / next stage
+        int pn_row = -1;                                                     // first row pn[] holds (-1: nothing requested)
         auto advance = [&]() -> bool {                                       // next output row; false when the item is done
             y++;
             dptr += a.dw;
@@ -506,13 +577,40 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 #pragma unroll
                 for (int g = 0; g < (HS ? 1 : NP); g++) ga[g] = addr[g] + goff;
                 int adv = 1;                                                 // groups this iteration consumes
-                if (MASK && gis + SG <= ng && vrel == FIRSTK && y >= a.reg_lo && y + SG * NOUT <= ylim) {
+                if (MASK && gis + SG <= ng && vrel == FIRSTK && y >= a.reg_lo && y + SG * NOUT <= ylim &&
+                    (!SC || ((unsigned)(rbase - own_lo) < own_span && (unsigned)(rbase + SG * TV - 1 - own_lo) < own_span))) {
                     // ---- a whole stage of regular groups: the schedule is static (no branch, no table fetch), the
                     // coefficients are parameter-space constants, and horizontal / vertical work of neighbouring rows
                     // interleaves freely because it is one basic block
+                    if constexpr (SC) {
+                        // the previous picture's words for THIS stage were requested one stage ago; request the next
+                        // stage's now, so that their latency hides behind this stage's arithmetic
+                        const int ppw = a.sc_pitch >> 2;
+                        if (pn_row == rbase) {
+#pragma unroll
+                            for (int r = 0; r < SG * TV; r++) { pv[r][0] = pn[r][0]; pv[r][1] = pn[r][1]; pv[r][2] = pn[r][2]; }
+                        } else {
+                            const uint32_t *pp = reinterpret_cast<const uint32_t *>(prev_lane + (size_t)rbase * a.sc_pitch);
+#pragma unroll
+                            for (int r = 0; r < SG * TV; r++) {
+                                pv[r][0] = __ldg(pp + r * ppw); pv[r][1] = __ldg(pp + r * ppw + 1); pv[r][2] = __ldg(pp + r * ppw + 2);
+                            }
+                        }
+                        const int nxt = rbase + SG * TV;
+                        if (nxt + SG * TV <= rs + nrows) {
+                            const uint32_t *pp = reinterpret_cast<const uint32_t *>(prev_lane + (size_t)nxt * a.sc_pitch);
+#pragma unroll
+                            for (int r = 0; r < SG * TV; r++) {
+                                pn[r][0] = __ldg(pp + r * ppw); pn[r][1] = __ldg(pp + r * ppw + 1); pn[r][2] = __ldg(pp + r * ppw + 2);
+                            }
+                            pn_row = nxt;
+                        } else {
+                            pn_row = -1;
+                        }
+                    }
                     static_for<0, SG * TV>([&](auto kc) {
                         constexpr int kk = decltype(kc)::value, k = kk % TV;
-                        hpass(kk, m[k]);
+                        hpass(kk, m[k], rbase + kk, true, pv[SC ? kk : 0]);
                         if constexpr ((MASK >> k) & 1) {
                             constexpr int q = (popc_c((unsigned)MASK & ((1u << k) - 1u)) + (kk / TV) * NOUT) % Q;
                             int acc[NM];
@@ -542,7 +640,7 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                     }
 #pragma unroll
                     for (int k = 0; k < TV; k++) {
-                        hpass(k, m[k]);
+                        hpass(k, m[k], rbase + k, false, nullptr);
                         // ---- vertical pass for every output row whose window ends at this source row
                         while (vrel == k) {
                             int acc[NM];
@@ -579,6 +677,30 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             }
         }
     item_done:;
+        if constexpr (SC) {
+            // ---- flush this item's counters into the picture's histogram and SAD; leave the counters zeroed
+            __syncwarp();
+            const uint32_t cbase = wsm + (uint32_t)a.sc_cnt_off;
+#pragma unroll 1
+            for (int r = 0; r < 4; r++) {
+                const uint32_t row = 4u * (uint32_t)lane + (uint32_t)r;
+                uint32_t lo = 0, hi = 0;
+#pragma unroll 8
+                for (int j = 0; j < 32; j++) {
+                    const uint32_t ad = cbase + row * 128u + (((uint32_t)j + (uint32_t)lane) & 31u) * 4u;   // rotated: no bank conflicts
+                    uint32_t wv;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv) : "r"(ad) : "memory");
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(ad), "r"(0u) : "memory");
+                    lo += wv & 0xFFFFu;
+                    hi += wv >> 16;
+                }
+                if (lo) atomicAdd(a.sc_hist + (size_t)f * 256 + row, lo);
+                if (hi) atomicAdd(a.sc_hist + (size_t)f * 256 + 128 + row, hi);
+            }
+            const uint32_t tot = __reduce_add_sync(0xffffffffu, sad_acc);
+            if (lane == 0 && tot) atomicAdd(a.sc_sad + f, (unsigned long long)tot);
+            __syncwarp();
+        }
     }
 #if VT_PAIR_TIMES
     if (a.dbg_times && lane == 0) {
@@ -605,11 +727,15 @@ int upload(const void *h, size_t n, void **d) {
     return VT_OK;
 }
 
-template <int HP, int TV, bool UV, int MASK, int Q, int HS = 0>
+template <int HP, int TV, bool UV, int MASK, int Q, int HS = 0, bool SC = false>
 int launch_t(const vt_scale_plan::Pair &s, const CUtensorMap &tm, PairArgs a, int rows_total, cudaStream_t st) {
-    auto k = scale_pair_kernel<HP, TV, UV, MASK, Q, HS>;
+    auto k = scale_pair_kernel<HP, TV, UV, MASK, Q, HS, SC>;
     static int smem_set_dev[VT_MAX_DEVICES] = {0}, blocks_per_sm_dev[VT_MAX_DEVICES] = {0};   // per device ordinal
-    const int smem = s.warp_smem * 4;
+    if (SC) {                                 // the warp's counters follow its ring
+        a.sc_cnt_off = s.warp_smem;
+        a.warp_smem = s.warp_smem + PAIR_SC_COUNTER_BYTES;
+    }
+    const int smem = a.warp_smem * 4;
     static std::mutex mu;
     std::lock_guard<std::mutex> lock(mu);
     int &smem_set = smem_set_dev[current_device()], &blocks_per_sm = blocks_per_sm_dev[current_device()];
@@ -624,6 +750,10 @@ int launch_t(const vt_scale_plan::Pair &s, const CUtensorMap &tm, PairArgs a, in
     }
     static VTab<TV> vt_host;                 // 28 KB staging for the parameter copy; filled under the launch lock
     const int cap = VCfg<TV>::ROWS - 1;      // the kernel reads one table entry ahead
+    if (SC && rows_total > cap) {
+        set_error("scale_pair_kernel: fused score needs the whole picture in one launch (%d rows > %d)", rows_total, cap);
+        return VT_ERR_UNSUPPORTED;
+    }
     for (int yb = 0; yb < rows_total; yb += cap) {
         const int ye = std::min(rows_total, yb + cap);
         for (size_t i = 0, n = (size_t)(ye - yb) * s.vstride; i < n; i++) vt_host.t[i] = (int16_t)s.vtab[(size_t)yb * s.vstride + i];
@@ -672,6 +802,14 @@ int launch_t(const vt_scale_plan::Pair &s, const CUtensorMap &tm, PairArgs a, in
 template <bool UV>
 int dispatch(int hp, int tv, bool hs, const vt_scale_plan::Pair &s, const CUtensorMap &tm, const PairArgs &a, int rows,
              cudaStream_t st) {
+    if constexpr (!UV) {
+        if (a.sc_hist) {                      // fused score: only the 3:2 luma layout is instantiated (checked by the caller)
+            if (hs && s.mask == 0x36 && s.n_phases == 2 && hp == 3 && tv == 6)
+                return launch_t<3, 6, false, 0x36, 2, 1, true>(s, tm, a, rows, st);
+            set_error("scale_pair: no fused-score instantiation for this plan");
+            return VT_ERR_UNSUPPORTED;
+        }
+    }
     // static horizontal pattern + static vertical schedule (exact 3:2 both ways: 1080p -> 720p)
     if (hs && s.mask == 0x36 && s.n_phases == 2 && hp == 3 && tv == 6) return launch_t<3, 6, UV, 0x36, 2, 1>(s, tm, a, rows, st);
     if (hs && s.mask == 0xAA && s.n_phases == 1 && hp == 4 && tv == 8) return launch_t<4, 8, UV, 0xAA, 1, 2>(s, tm, a, rows, st);
@@ -895,6 +1033,12 @@ int build_pair(vt_scale_plan *p, int c) {
     if (rc == VT_OK && hs) rc = upload(bx_hs.data(), bx_hs.size() * 4, (void **)&s.box_x0_hs);
     if (rc == VT_OK && hs) rc = upload(lt_hs.data(), lt_hs.size() * 4, (void **)&s.lane_tab_hs);
     s.hs = hs && rc == VT_OK;
+    // fused scene score (luma, exact 3:2): strips tile the source exactly (no slid last strip), a lane's 8 columns sit
+    // on 12 source bytes, the last window ends on the last source row and the picture fits one launch
+    s.score_ok = s.hs && !uv && hsid == 1 && dw % s.strip_cols == 0 && (long long)p->sw * 2 == (long long)dw * 3 &&
+                 vpos[dh - 1] + vtaps == p->sh && dh <= VCfg<6>::ROWS - 1;
+    for (int strip = 0; s.score_ok && strip < s.n_strips; strip++)
+        if (bx_hs[strip] + 4 != scol[strip] / 2 * 3) s.score_ok = false;
     if (rc == VT_OK) rc = upload(scol.data(), scol.size() * 4, (void **)&s.strip_col);
     if (rc == VT_OK) rc = upload(lt.data(), lt.size() * 4, (void **)&s.lane_tab);
     if (rc != VT_OK) return rc;
@@ -915,7 +1059,7 @@ void free_pair(vt_scale_plan *p) {
 }
 
 int launch_pair(const vt_scale_plan *p, int c, const uint8_t *src, int pitch, size_t src_fs, uint8_t *dst, size_t dst_fs,
-                int n_frames, cudaStream_t st) {
+                int n_frames, cudaStream_t st, const PairScore *score) {
     const vt_scale_plan::Pair &s = p->pair[c];
     const bool uv = c == 1;
     CUtensorMap tm;
@@ -949,6 +1093,18 @@ int launch_pair(const vt_scale_plan *p, int c, const uint8_t *src, int pitch, si
     a.warp_smem = s.warp_smem;
     a.round_bias = 1 << 18;
     a.dbg_times = nullptr;
+    a.sc_src = src;
+    a.sc_prev0 = score ? score->prev0 : nullptr;
+    a.sc_fs = src_fs;
+    a.sc_pitch = pitch;
+    a.sc_rows = p->sh;
+    a.sc_sad = score ? (unsigned long long *)score->sad : nullptr;
+    a.sc_hist = score ? score->hist : nullptr;
+    a.sc_cnt_off = 0;
+    if (score && (uv || !hs || !s.score_ok)) {
+        set_error("scale_pair: this plan / alignment has no fused score path");
+        return VT_ERR_UNSUPPORTED;
+    }
     a.reg_lo = s.reg_lo;
     a.reg_hi = s.reg_hi;
     a.align_p = s.align_p;

@@ -44,6 +44,7 @@ struct vt_scale_plan {
         // static horizontal pattern (exact 3:2): a lane owns 8 ADJACENT output columns (luma) / 4 (chroma); every
         // column's tap alignment is then a compile-time constant.  Tables beside the generic ones; see build_pair()
         bool hs = false;
+        bool score_ok = false;         // the luma kernel can also produce SAD + histogram of the source (fused K3)
         int32_t *box_x0_hs = nullptr;  // n_strips: first source byte of the strip's single TMA box (multiple of 4, may be < 0)
         uint32_t *lane_tab_hs = nullptr;  // (n_strips*32) x (columns per lane * hp) coefficient pairs
     } pair[2];
@@ -52,8 +53,15 @@ struct vt_scale_plan {
 namespace vt {
 int build_pair(vt_scale_plan *p, int c);
 void free_pair(vt_scale_plan *p);
+struct PairScore {                     // outputs of the fused scene score; sad/hist must be zeroed before the launch
+    const uint8_t *prev0;
+    uint64_t *sad;
+    uint32_t *hist;
+};
 int launch_pair(const vt_scale_plan *p, int c, const uint8_t *src, int pitch, size_t src_fs, uint8_t *dst, size_t dst_fs,
-                int n_frames, cudaStream_t st);
+                int n_frames, cudaStream_t st, const PairScore *score = nullptr);
+int launch_score(const uint8_t *luma, int pitch, size_t frame_stride, int w, int h, const uint8_t *prev0, int n_frames,
+                 uint64_t *sad, uint32_t *hist, cudaStream_t st);
 int make_tmap_u32_3d(void *tmap_out, const uint8_t *base, int row_bytes, int rows, int n_frames, int pitch,
                      size_t frame_stride, int tile_w, int tile_h);
 int make_tmap_u8_3d(void *tmap_out, const uint8_t *base, int row_bytes, int rows, int n_frames, int pitch,

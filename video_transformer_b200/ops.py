@@ -138,6 +138,27 @@ class ScalePlan:
         return out
 
 
+    @property
+    def fuses_score(self) -> bool:
+        """True when scale_score_nv12 runs SAD/histogram inside the luma pass of the scaler (one read of the source)."""
+        return bool(lib().vt_scale_plan_fuses_score(self._h))
+
+    def scale_score_nv12(self, src: torch.Tensor, pitch: int, n_frames: int, src_frame_stride: int | None = None,
+                         prev0: torch.Tensor | None = None, out: torch.Tensor | None = None):
+        """K2 + K3: (frames, sad[n] int64, hist[n,256] int32) of a batch of NV12 surfaces."""
+        _need_cuda(src, "src")
+        sfs = src_frame_stride or nv12_frame_bytes(pitch, self.sh)
+        if out is None:
+            out = torch.empty((n_frames, self.out_frame_bytes), dtype=torch.uint8, device=src.device)
+        sad = torch.empty(n_frames, dtype=torch.int64, device=src.device)
+        hist = torch.empty((n_frames, 256), dtype=torch.int32, device=src.device)
+        p0 = c_void_p(prev0.data_ptr()) if prev0 is not None else None
+        check(lib().vt_scale_score_nv12_to_yuv420p(self._h, c_void_p(src.data_ptr()), pitch, sfs, p0,
+                                                   c_void_p(out.data_ptr()), self.out_frame_bytes, n_frames,
+                                                   c_void_p(sad.data_ptr()), c_void_p(hist.data_ptr()), _stream()))
+        return out, sad, hist
+
+
 class RgbPlan:
     """Device-resident filter banks for NV12 -> RGB24 at (dw, dh): `ffmpeg -vf scale=dw:dh -pix_fmt rgb24` semantics."""
 
