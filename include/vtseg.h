@@ -76,10 +76,10 @@ int vt_scale_nv12_to_yuv420p(const vt_scale_plan *plan, const uint8_t *src_dev, 
                              void *stream);
 
 /* K2 + K3 in one call: the scaled frames of vt_scale_nv12_to_yuv420p plus the SAD / histogram of vt_sad_hist_u8 on the
- * SOURCE luma (prev0_dev: luma of the picture before frame 0, or NULL).  Where the plan allows
- * (vt_scale_plan_fuses_score == 1: exact 3:2 luma, e.g. 1080p -> 720p) the luma pass of the scaler counts the source rows
- * it already holds in shared memory, so the source luma is fetched from HBM once; otherwise the two kernels run one after
- * the other.  Results are identical either way.  Replaces the same reference work as the two calls it combines. */
+ * SOURCE luma (prev0_dev: luma of the picture before frame 0, or NULL).  With VT_FUSED_SCORE=1 in the environment and a
+ * plan that allows it (vt_scale_plan_fuses_score == 1: exact 3:2 luma, e.g. 1080p -> 720p) the luma pass of the scaler
+ * counts the source rows it already holds in shared memory, so the source luma is fetched from HBM once (20 % less DRAM
+ * traffic, same time -- see DESIGN.md); otherwise the two kernels run one after the other.  Results are identical.  Replaces the same reference work as the two calls it combines. */
 int vt_scale_plan_fuses_score(const vt_scale_plan *plan);
 int vt_scale_score_nv12_to_yuv420p(const vt_scale_plan *plan, const uint8_t *src_dev, int src_pitch, size_t src_frame_stride,
                                    const uint8_t *prev0_dev, uint8_t *dst_dev, size_t dst_frame_stride, int n_frames,

@@ -290,9 +290,15 @@ def test_scale_into_a_destination_that_is_not_8_byte_aligned(cuda, oracle_c, off
                                                      (3840, 2160, 3840, 2560, 1440, True), (768, 432, 768, 512, 288, True),
                                                      (960, 540, 1024, 640, 360, False),      # 640 is not a whole number of strips
                                                      (1280, 720, 1280, 640, 360, False)])    # 2:1: separate kernels
-def test_fused_scale_and_score_equals_the_separate_kernels(cuda, oracle_c, sw, sh, pitch, dw, dh, fused):
-    """K3 inside K2's luma pass: frames, SADs and histograms equal the two standalone kernels bit for bit (and the
-    oracle), with and without a picture preceding the batch; every source pixel is counted exactly once."""
+@pytest.mark.parametrize("opt_in", [True, False])
+def test_fused_scale_and_score_equals_the_separate_kernels(cuda, oracle_c, sw, sh, pitch, dw, dh, fused, opt_in, monkeypatch):
+    """K3 inside K2's luma pass (opt-in, VT_FUSED_SCORE=1): frames, SADs and histograms equal the two standalone
+    kernels bit for bit (and the oracle), with and without a picture preceding the batch; every source pixel is counted
+    exactly once.  Without the opt-in the same call runs the kernels one after the other."""
+    if opt_in:
+        monkeypatch.setenv("VT_FUSED_SCORE", "1")
+    else:
+        monkeypatch.delenv("VT_FUSED_SCORE", raising=False)
     rng = np.random.default_rng(sw * 3 + dh)
     n = 5
     buf = _nv12_batch(rng, n, sw, sh, pitch)
@@ -310,7 +316,7 @@ def test_fused_scale_and_score_equals_the_separate_kernels(cuda, oracle_c, sw, s
         before = ops.lib().vt_launch_count()
         out, sad, hist = plan.scale_score_nv12(d.view(-1), pitch, n, prev0=None if p0 is None else p0.view(-1))
         launches = ops.lib().vt_launch_count() - before
-        assert launches == (2 if fused else 3)           # luma(+score) and chroma / score, luma, chroma
+        assert launches == (2 if fused and opt_in else 3)   # luma(+score) and chroma / score, luma, chroma
         assert np.array_equal(out.cpu().numpy(), ref_out)
         assert np.array_equal(sad.cpu().numpy(), ref_sad.cpu().numpy())
         assert np.array_equal(hist.cpu().numpy(), ref_hist.cpu().numpy())
