@@ -197,6 +197,22 @@ int vt_ingest_batch_pcm(const vt_scale_plan *plan, const uint8_t *bitstream_dev,
  * support; VT_ERR_NVDEC otherwise (message in vt_last_error()). */
 int vt_nvdec_probe(int *n_engines, int *max_w, int *max_h);
 
+/* ---- K0 proper: NVDEC sessions (libnvcuvid parser + decoder behind dlopen) --------------------------------------
+ * Replaces libavcodec inside the ffmpeg child processes (src/utils/video_segmenter.py:141-154,
+ * src/analyzer/content_analyzer.py:193-211) for real H.264 / HEVC / VP9 / AV1 content.  codec uses cudaVideoCodec
+ * numbering (4 H.264, 8 HEVC, 9 VP9, 11 AV1).  Feed elementary-stream bytes (Annex-B for H.264/HEVC) with their
+ * timestamps; next_surface returns VT_OK with a mapped pitch-linear NV12 surface in device memory (chroma plane at
+ * surface + pitch * surface_rows) -- the input layout of every kernel above -- or 1 when no picture is displayable
+ * yet; release the surface when the kernels reading it have been enqueued on `stream` and completed.
+ * vt_decode_open returns VT_ERR_NVDEC (vt_nvdec_probe's message) where the driver exposes no video decode. */
+typedef struct vt_decoder vt_decoder;
+int vt_decode_open(int codec, int max_surfaces, void *stream, vt_decoder **out);
+int vt_decode_feed(vt_decoder *dec, const uint8_t *data, size_t n_bytes, int64_t pts, int end_of_stream);
+int vt_decode_next_surface(vt_decoder *dec, uint64_t *surface_dev, int *pitch, int *width, int *height,
+                           int *surface_rows, int64_t *pts);
+int vt_decode_release_surface(vt_decoder *dec, uint64_t surface_dev);
+void vt_decode_close(vt_decoder *dec);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,12 @@ SIGNATURES = {
     "vt_ingest_batch_pcm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_size_t,
                                     c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vt_nvdec_probe": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "vt_decode_open": (c_int, [c_int, c_int, c_void_p, POINTER(c_void_p)]),
+    "vt_decode_feed": (c_int, [c_void_p, c_void_p, c_size_t, ctypes.c_int64, c_int]),
+    "vt_decode_next_surface": (c_int, [c_void_p, POINTER(c_uint64), POINTER(c_int), POINTER(c_int), POINTER(c_int),
+                                       POINTER(c_int), POINTER(ctypes.c_int64)]),
+    "vt_decode_release_surface": (c_int, [c_void_p, c_uint64]),
+    "vt_decode_close": (None, [c_void_p]),
 }
 
 _lib = None

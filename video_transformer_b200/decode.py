@@ -94,3 +94,47 @@ class H264PcmDecoder:
                                        c_void_p(out.data_ptr()), pitch, rows * pitch,
                                        c_void_p(torch.cuda.current_stream().cuda_stream)))
         return out
+
+
+class NvdecSession:
+    """K0 proper: an NVDEC session (vt_decode_open / feed / next_surface / release_surface / close).
+
+    Raises VtError(VT_ERR_NVDEC) where the driver exposes no video decode (this pool: see DESIGN.md section 2).
+    Surfaces are mapped device memory in the NV12 pitch-linear layout the kernels consume; `surfaces()` yields
+    (device pointer, pitch, width, height, surface rows, pts) and releases each surface when the caller asks for the
+    next one."""
+
+    H264, HEVC, VP9, AV1 = 4, 8, 9, 11
+
+    def __init__(self, codec: int = 4, max_surfaces: int = 8, stream=None):
+        import ctypes
+        self._h = ctypes.c_void_p()
+        st = ctypes.c_void_p(stream.cuda_stream) if stream is not None else None
+        _lib.check(_lib.lib().vt_decode_open(codec, max_surfaces, st, ctypes.byref(self._h)))
+
+    def feed(self, data: bytes, pts: int = 0, end_of_stream: bool = False) -> None:
+        import ctypes
+        buf = (ctypes.c_ubyte * len(data)).from_buffer_copy(data) if data else None
+        _lib.check(_lib.lib().vt_decode_feed(self._h, buf, len(data), pts, 1 if end_of_stream else 0))
+
+    def surfaces(self):
+        import ctypes
+        L = _lib.lib()
+        held = None
+        while True:
+            ptr, pitch, w, h, rows = ctypes.c_uint64(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+            pts = ctypes.c_int64()
+            rc = _lib.check(L.vt_decode_next_surface(self._h, ctypes.byref(ptr), ctypes.byref(pitch), ctypes.byref(w),
+                                                     ctypes.byref(h), ctypes.byref(rows), ctypes.byref(pts)))
+            if held is not None:
+                _lib.check(L.vt_decode_release_surface(self._h, held))
+                held = None
+            if rc == 1:
+                return
+            held = ptr.value
+            yield ptr.value, pitch.value, w.value, h.value, rows.value, pts.value
+
+    def close(self) -> None:
+        if self._h:
+            _lib.lib().vt_decode_close(self._h)
+            self._h = None
