@@ -35,7 +35,7 @@ _NO_PAYLOAD = np.uint64(0xFFFFFFFFFFFFFFFF)
 class IngestOptions:
     target_height: int = 720           # downloader.max_resolution (config/config.yaml:75, README sample: 720)
     sws_flags: int = _lib.SWS_BICUBIC  # ffmpeg's scale filter default
-    batch_frames: int = 32
+    batch_frames: int = 64             # 32-picture launches run the scaler at about half its 256-picture rate
     scene_threshold: float = 0.10
     keep_frames: bool = True           # deliver output frames to the sink (False: scores only, config 3)
     never_upscale: bool = True         # sources at or below the target height are converted, not resized

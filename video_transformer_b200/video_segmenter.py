@@ -65,7 +65,7 @@ _OPTIONS = {
     "target_height": 720,      # downloader.max_resolution
     "sws_flags": 4,            # SWS_BICUBIC
     "scene_threshold": 0.10,
-    "batch_frames": 32,
+    "batch_frames": 64,        # pictures per pipeline batch (32-picture launches run the scaler at half its rate)
     "frame_buffers": True,     # run the GPU pass and write .frames/.json beside the MP4
     "output": "yuv420p",       # or "rgb24" (the upload product: BASELINE.json configs[4])
     "rgb_size": None,          # (width, height) of the RGB output, e.g. (768, 768)
