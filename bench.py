@@ -352,6 +352,9 @@ def main():
     ap.add_argument("--workload", default="config1", choices=["config1", "config3"],
                     help="config1 = BASELINE.json configs[1] (the contract's line); config3 = configs[3], a URL.txt-style batch "
                          "of 64 synthetic 720p clips through batch.ingest_batch_dynamic (its own JSON line)")
+    ap.add_argument("--consume", action="store_true",
+                    help="config3: a consumer deletes every clip's .frames right after its ingest (the landing files are "
+                         "then recycled instead of being allocated and page-locked anew for every clip)")
     ap.add_argument("--diag", action="store_true", help="also time the engine API with a pinned ring / a direct landing on "
                     "every rank at once (which part of the plugin call limits multi-GPU scaling)")
     args = ap.parse_args()
@@ -778,8 +781,14 @@ def _run_config3(args, rank, world, local, dev, barrier, workdir, torch, dist, v
     batch.ingest_video(warm, os.path.join(workdir, "warm_temp_%d" % rank))
     barrier()
     t0 = time.perf_counter()
-    rep = batch.ingest_batch_dynamic(vids, os.path.join(workdir, "temp"), rank=rank, world=world)
+    def consume(vid, ok):
+        if args.consume and ok:
+            for fp in video_segmenter.get_segment_dir(vid, os.path.join(workdir, "temp")).glob("*.frames"):
+                fp.unlink()
+
+    rep = batch.ingest_batch_dynamic(vids, os.path.join(workdir, "temp"), rank=rank, world=world, on_done=consume)
     torch.cuda.synchronize(dev)
+    last_call = {k: round(v * 1e3, 2) for k, v in video_segmenter.LAST_TIMINGS.items()}
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     cnt = torch.tensor([float(rep.pictures), float(rep.segments_done), float(len(rep.processed)), float(len(rep.failed))],
                        dtype=torch.float64, device=dev)
@@ -798,13 +807,16 @@ def _run_config3(args, rank, world, local, dev, barrier, workdir, torch, dist, v
             "segments_per_sec": segs / float(dt[0]), "videos_per_sec": n_clips / float(dt[0]), "n_gpus": world,
             "seconds": float(dt[0]), "pictures": int(pictures), "segments": int(segs),
             "videos_per_rank": [int(t[2]) for t in per], "failed": int(sum(float(t[3]) for t in per)),
-            "progress_json_processed": len(merged["processed"]),
+            "progress_json_processed": len(merged["processed"]), "last_call_ms": last_call,
             "config": {"workload": "configs[3]: %d synthetic %dx%d@30 clips of %d pictures (I_PCM IDR / GOP 30 + P_Skip), "
                                    "same-height sources are converted NV12 -> YUV420P (not resized) + SAD/hist, one "
                                    "segment each; probe -> budget plan -> manifest -> extract_segment per clip"
                                    % (n_clips, w, h, n_pic),
                        "sharding": "per video, dynamic: ranks claim clips longest-first with O_EXCL files, no collective",
-                       "e2e": "wall clock over batch.ingest_batch_dynamic, host MP4 in, MP4 + .frames + .json out"},
+                       "e2e": "wall clock over batch.ingest_batch_dynamic, host MP4 in, MP4 + .frames + .json out",
+                       "consumer": ("deletes each clip's .frames after its ingest: landing files are recycled"
+                                    if args.consume else "keeps every .frames (26.5 GB): each clip allocates and "
+                                    "page-locks a fresh landing file")},
             "data": "synthetic", "dtype": "u8"}))
     return 0
 

@@ -29,6 +29,9 @@ from ._lib import check, lib
 from .container import StreamIndex
 
 _NO_PAYLOAD = np.uint64(0xFFFFFFFFFFFFFFFF)
+# Pipeline buffers (device surfaces / outputs, pinned score buffers) of released engines, by geometry: the videos of a
+# batch mostly share one geometry, and page-locked allocations are the slow part of building an engine.
+_SLOT_POOL: dict = {}
 
 
 @dataclass
@@ -143,11 +146,19 @@ class SegmentIngestor:
         max_nal = int(sizes.max()) if n else 0
         # worst case bytes one batch needs on the device: B pictures + their container framing
         self.bs_cap = (max_nal + 64) * min(B, max(1, int(index.keyframe.sum()))) + 4096 * B + 4096
+        self.bs_cap = (self.bs_cap + (1 << 20) - 1) >> 20 << 20          # whole MiB: engines of one geometry share buffers
         self.slots = []
+        self._pool_key = (str(self.dev), B, self.rows, self.pitch, self.frame_bytes, self.bs_cap, self.opts.sample_every > 1)
+        pooled = _SLOT_POOL.get(self._pool_key) or []
         import os
         self.n_slots = int(os.environ.get("VT_INGEST_SLOTS", "3"))   # batch i+1 is staged by a helper thread while i computes, i-1 copies out
         self.stage_thread = os.environ.get("VT_INGEST_THREAD", "1") == "1"
         for _ in range(self.n_slots):
+            if pooled:
+                sl = pooled.pop()
+                sl.update(used=False, pending=None, kept=None, land=None, wfut=None, src_lo=0)
+                self.slots.append(sl)
+                continue
             self.slots.append({
                 "bs_host": None, "src_lo": 0,
                 "bs_dev": torch.empty(self.bs_cap + 64, dtype=torch.uint8, device=self.dev),
@@ -203,6 +214,15 @@ class SegmentIngestor:
             mm.close()
             return
         self._src_map = (mm, arr, arr.ctypes.data)
+
+    def release(self) -> None:
+        """Give the pipeline buffers back to the pool (the engine must not run afterwards) and unpin the source."""
+        if self.slots:
+            torch.cuda.synchronize(self.dev)
+            _SLOT_POOL.setdefault(self._pool_key, []).extend(self.slots)
+            del _SLOT_POOL[self._pool_key][6:]           # keep at most two engines' worth per geometry
+            self.slots = []
+        self.close()
 
     def close(self) -> None:
         if self._src_map is not None:

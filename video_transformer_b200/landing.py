@@ -33,6 +33,8 @@ _libc.posix_fallocate.argtypes = [ctypes.c_int, ctypes.c_long, ctypes.c_long]
 _lock = threading.Lock()
 _slots: list["_Slot"] = []
 _seq = 0
+_arena_of_device: dict = {}      # st_dev -> arena directory: hard links work anywhere on one file system, so the
+                                 # segments of every video written there share one arena
 
 
 class _Slot:
@@ -141,7 +143,11 @@ def _pwrite_all(fd: int, mv: memoryview, offset: int) -> None:
 
 
 def _arena_cap() -> int:
-    return int(float(os.environ.get("VT_LANDING_CAP_GB", "64")) * (1 << 30))
+    """Page-locked landing memory this process keeps (registered files, in use or free).  Beyond it the oldest files are
+    released: unregistered, unmapped, their arena name removed -- the `.frames` hard link stays an ordinary file.  (An
+    unbounded arena made every later page-locking call of the process slower: 64 retained 415 MB files took engine
+    set-up from 30 ms to 530 ms in the configs[3] batch.)"""
+    return int(float(os.environ.get("VT_LANDING_CAP_GB", "12")) * (1 << 30))
 
 
 def acquire(path: str | Path, nbytes: int, direct: bool | None = None) -> Landing:
@@ -160,7 +166,14 @@ def acquire(path: str | Path, nbytes: int, direct: bool | None = None) -> Landin
         if path.exists() or path.is_symlink():
             path.unlink()                       # a replaced artefact frees its arena file for the search below
         if direct:
-            arena = path.parent / ARENA_DIR
+            try:
+                dev_id = os.stat(path.parent).st_dev
+            except OSError:
+                dev_id = None
+            arena = _arena_of_device.get(dev_id)
+            if arena is None or not arena.is_dir():
+                arena = path.parent / ARENA_DIR
+                _arena_of_device[dev_id] = arena
             slot = None
             for s in _slots:
                 if s.nbytes == nbytes and s.path.parent == arena and s.free():
@@ -168,9 +181,9 @@ def acquire(path: str | Path, nbytes: int, direct: bool | None = None) -> Landin
                     break
             recycled = slot is not None
             if slot is None:
-                # drop free files of other sizes when the arena is over its cap
+                # over the cap: release the oldest files, free ones first (busy ones keep their `.frames` name)
                 used = sum(s.nbytes for s in _slots)
-                for s in sorted([s for s in _slots if s.free()], key=lambda s: s.stamp):
+                for s in sorted(_slots, key=lambda s: (not s.free(), s.stamp)):
                     if used + nbytes <= _arena_cap():
                         break
                     s.destroy()

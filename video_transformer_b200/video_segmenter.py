@@ -327,7 +327,9 @@ def _engine_for(idx, keep_frames: bool = True):
     eng = _ENGINE_CACHE.get(slot)
     if eng is not None and eng[0] == key:
         return eng[1]
-    _ENGINE_CACHE.pop(slot, None)
+    old = _ENGINE_CACHE.pop(slot, None)
+    if old is not None:
+        old[1].release()                 # its buffers serve the next engine of the same geometry
     opts = ingest.IngestOptions(target_height=_OPTIONS["target_height"], sws_flags=_OPTIONS["sws_flags"],
                                 batch_frames=_OPTIONS["batch_frames"], scene_threshold=_OPTIONS["scene_threshold"],
                                 output=_OPTIONS["output"], rgb_size=_OPTIONS["rgb_size"],
@@ -376,13 +378,20 @@ def _snap_window(idx, times: np.ndarray, start: float, end: float, tol: float):
 
 def _ingest_to_files(idx, first: int, last: int, dst: Path, snapped=None) -> None:
     """GPU pass for pictures [first,last): writes <dst>.frames and <dst>.json.  Raises on any failure."""
+    import time
     from . import landing
+    t0 = time.perf_counter()
     eng = _engine_for(idx)
     n_out = eng.kept_pictures(first, last)
+    t1 = time.perf_counter()
     land = landing.acquire(_frames_path(dst), max(n_out, 1) * eng.frame_bytes)
+    t2 = time.perf_counter()
+    LAST_TIMINGS["engine"] = t1 - t0
+    LAST_TIMINGS["landing_acquire"] = t2 - t1
     try:
         res = eng.run(first, last, landing=land)
         land.finish(res.stats["landed_frames"] * eng.frame_bytes)
+        LAST_TIMINGS["gpu_pass"] = time.perf_counter() - t2
     except BaseException:
         land.abort()
         raise
