@@ -1,0 +1,58 @@
+"""K5 landing, host logic that needs no GPU: the staged writer (file systems / machines whose mappings cannot be
+page-locked) and the clean-up of arena names left by dead processes.  The direct path (registered mapping, recycling)
+is a GPU test: tests/test_ingest.py::test_frames_land_directly_in_the_file_and_landing_files_are_recycled."""
+import os
+
+import numpy as np
+import torch
+
+from video_transformer_b200 import landing
+
+
+def test_staged_landing_writes_chunks_at_their_offsets(tmp_path):
+    path = tmp_path / "seg" / "segment_0000.frames"
+    fb, n = 1000, 7
+    land = landing.acquire(path, fb * n, direct=False)
+    assert not land.direct and land.tensor is None
+    rng = np.random.default_rng(0)
+    data = rng.integers(0, 256, (n, fb), dtype=np.uint8)
+    futs = []
+    for a, b in ((4, 7), (0, 2), (2, 4)):                       # out of order on purpose: offsets decide, not call order
+        futs.append(land.write_chunk(torch.from_numpy(data[a:b].copy()), a * fb))
+    for f in futs:
+        f.result()
+    land.finish(fb * n)
+    assert path.read_bytes() == data.tobytes()
+    # a replaced artefact starts from an empty file
+    land = landing.acquire(path, fb * 2, direct=False)
+    land.write_chunk(torch.from_numpy(data[:2].copy()), 0).result()
+    land.finish(fb * 2)
+    assert path.stat().st_size == fb * 2
+    land = landing.acquire(path, fb, direct=False)
+    land.abort()
+    assert not path.exists()
+
+
+def test_without_a_gpu_the_direct_request_falls_back_to_the_staged_writer(tmp_path):
+    if torch.cuda.is_available():
+        return                                                   # covered by the GPU test
+    land = landing.acquire(tmp_path / "x.frames", 4096)          # registration fails: no device
+    assert not land.direct
+    land.abort()
+    assert landing.stats()["files"] == 0
+    assert not any((tmp_path / landing.ARENA_DIR).glob("*")) if (tmp_path / landing.ARENA_DIR).exists() else True
+
+
+def test_stale_arena_names_are_swept(tmp_path):
+    arena = tmp_path / landing.ARENA_DIR
+    arena.mkdir()
+    dead = arena / "landing_999999_3.bin"
+    mine = arena / ("landing_%d_1.bin" % os.getpid())
+    other = arena / "notes.txt"
+    for p in (dead, mine, other):
+        p.write_bytes(b"x")
+    frames = tmp_path / "segment_0001.frames"
+    os.link(dead, frames)                                        # a crashed process left both names
+    landing._sweep_stale(arena)
+    assert not dead.exists() and mine.exists() and other.exists()
+    assert frames.read_bytes() == b"x"                           # the artefact survives, only the extra name went

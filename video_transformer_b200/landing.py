@@ -174,6 +174,7 @@ def acquire(path: str | Path, nbytes: int, direct: bool | None = None) -> Landin
             if arena is None or not arena.is_dir():
                 arena = path.parent / ARENA_DIR
                 _arena_of_device[dev_id] = arena
+                _sweep_stale(arena)
             slot = None
             for s in _slots:
                 if s.nbytes == nbytes and s.path.parent == arena and s.free():
@@ -213,6 +214,31 @@ def acquire(path: str | Path, nbytes: int, direct: bool | None = None) -> Landin
             if direct is True and os.environ.get("VT_LANDING") == "direct-only":
                 raise OSError("cannot register a mapping of %s" % path)
         return Landing(path, nbytes, None, False)
+
+
+def _sweep_stale(arena: Path) -> None:
+    """Remove arena names left behind by processes that no longer exist (a crash skips release_all).  The data of a
+    `.frames` file that is still linked survives: only the extra name goes."""
+    try:
+        names = list(arena.iterdir())
+    except OSError:
+        return
+    for p in names:
+        parts = p.name.split("_")
+        if len(parts) != 3 or parts[0] != "landing" or not parts[1].isdigit():
+            continue
+        pid = int(parts[1])
+        if pid == os.getpid():
+            continue
+        try:
+            os.kill(pid, 0)
+        except ProcessLookupError:
+            try:
+                p.unlink()
+            except OSError:
+                pass
+        except OSError:
+            pass                                # exists but not ours to signal: leave it
 
 
 def stats() -> dict:
