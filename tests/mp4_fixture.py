@@ -33,9 +33,24 @@ def _runs(values):
 def write_av_mp4(path, *, sps, pps, video_samples, keyframes, width, height, timescale=15360, delta=512,
                  ctts=None, video_media_time=0, audio_rate=48000, audio_channels=2, audio_pcm=None,
                  audio_chunk=1024, video_chunk=5, moov_first=False, co64=False, movie_timescale=1000,
-                 audio_empty_edit=0):
+                 audio_empty_edit=0, version1=False, stz2=False):
     """video_samples: list of lists of NAL byte strings (no start codes / lengths).  audio_pcm: int16 array
-    [n, channels] or None.  Returns a dict describing what was written (sample byte strings per track)."""
+    [n, channels] or None.  version1: 64-bit mvhd / tkhd / mdhd / elst; stz2: the video sizes as a compact (16-bit)
+    `stz2` box.  Returns a dict describing what was written (sample byte strings per track)."""
+    def hdr_times(ts, dur):            # creation, modification, timescale, duration of mvhd / mdhd
+        return struct.pack(">QQIQ", 0, 0, ts, dur) if version1 else struct.pack(">IIII", 0, 0, ts, dur)
+
+    def tk_times(track_id, dur):       # creation, modification, track id, reserved, duration of tkhd
+        return struct.pack(">QQIIQ", 0, 0, track_id, 0, dur) if version1 else struct.pack(">IIIII", 0, 0, track_id, 0, dur)
+
+    def elst(entries):                 # [(segment duration, media time)]
+        if version1:
+            body = b"".join(struct.pack(">QqI", d, mt, 0x10000) for d, mt in entries)
+        else:
+            body = b"".join(struct.pack(">IiI", d, mt, 0x10000) for d, mt in entries)
+        return full(b"elst", 1 if version1 else 0, 0, struct.pack(">I", len(entries)) + body)
+
+    ver = 1 if version1 else 0
     vs = [b"".join(struct.pack(">I", len(n)) + n for n in nals) for nals in video_samples]
     n_v = len(vs)
     a_bytes = b""
@@ -81,17 +96,20 @@ def write_av_mp4(path, *, sps, pps, video_samples, keyframes, width, height, tim
             ent += struct.pack(">III", first, v, 1)
             first += c
         stbl += full(b"stsc", 0, 0, struct.pack(">I", len(r)) + ent)
-        stbl += full(b"stsz", 0, 0, struct.pack(">II", 0, n_v) + b"".join(struct.pack(">I", len(s)) for s in vs))
+        if stz2 and max(len(s) for s in vs) < 65536:
+            stbl += full(b"stz2", 0, 0, struct.pack(">3xBI", 16, n_v) + b"".join(struct.pack(">H", len(s)) for s in vs))
+        else:
+            stbl += full(b"stsz", 0, 0, struct.pack(">II", 0, n_v) + b"".join(struct.pack(">I", len(s)) for s in vs))
         if co64:
             stbl += full(b"co64", 0, 0, struct.pack(">I", len(v_off)) + struct.pack(">%dQ" % len(v_off), *v_off))
         else:
             stbl += full(b"stco", 0, 0, struct.pack(">I", len(v_off)) + struct.pack(">%dI" % len(v_off), *v_off))
         dinf = box(b"dinf", full(b"dref", 0, 0, struct.pack(">I", 1) + full(b"url ", 0, 1, b"")))
         minf = box(b"minf", full(b"vmhd", 0, 1, bytes(8)) + dinf + box(b"stbl", stbl))
-        mdia = box(b"mdia", full(b"mdhd", 0, 0, struct.pack(">IIIIHH", 0, 0, timescale, v_media, 0x55C4, 0)) +
+        mdia = box(b"mdia", full(b"mdhd", ver, 0, hdr_times(timescale, v_media) + struct.pack(">HH", 0x55C4, 0)) +
                    full(b"hdlr", 0, 0, struct.pack(">I4s12x", 0, b"vide") + b"FixtureVideo\x00") + minf)
-        edts = box(b"edts", full(b"elst", 0, 0, struct.pack(">IIiI", 1, v_movie, video_media_time, 0x10000)))
-        tkhd = full(b"tkhd", 0, 3, struct.pack(">IIIII", 0, 0, 1, 0, v_movie) + bytes(8) +
+        edts = box(b"edts", elst([(v_movie, video_media_time)]))
+        tkhd = full(b"tkhd", ver, 3, tk_times(1, v_movie) + bytes(8) +
                     struct.pack(">hhhH", 0, 0, 0, 0) + MATRIX + struct.pack(">II", width << 16, height << 16))
         traks = box(b"trak", tkhd + edts + mdia)
         movie_dur = v_movie
@@ -113,20 +131,14 @@ def write_av_mp4(path, *, sps, pps, video_samples, keyframes, width, height, tim
             else:
                 stbl += full(b"stco", 0, 0, struct.pack(">I", len(a_off)) + struct.pack(">%dI" % len(a_off), *a_off))
             minf = box(b"minf", full(b"smhd", 0, 0, bytes(4)) + dinf + box(b"stbl", stbl))
-            mdia = box(b"mdia", full(b"mdhd", 0, 0, struct.pack(">IIIIHH", 0, 0, audio_rate, n_a, 0x55C4, 0)) +
+            mdia = box(b"mdia", full(b"mdhd", ver, 0, hdr_times(audio_rate, n_a) + struct.pack(">HH", 0x55C4, 0)) +
                        full(b"hdlr", 0, 0, struct.pack(">I4s12x", 0, b"soun") + b"FixtureAudio\x00") + minf)
-            ent = b""
-            n_e = 1
-            if audio_empty_edit:
-                ent += struct.pack(">IiI", audio_empty_edit, -1, 0x10000)
-                n_e = 2
-            ent += struct.pack(">IiI", a_movie, 0, 0x10000)
-            edts = box(b"edts", full(b"elst", 0, 0, struct.pack(">I", n_e) + ent))
-            tkhd = full(b"tkhd", 0, 3, struct.pack(">IIIII", 0, 0, 2, 0, a_movie + audio_empty_edit) + bytes(8) +
+            edts = box(b"edts", elst(([(audio_empty_edit, -1)] if audio_empty_edit else []) + [(a_movie, 0)]))
+            tkhd = full(b"tkhd", ver, 3, tk_times(2, a_movie + audio_empty_edit) + bytes(8) +
                         struct.pack(">hhhH", 0, 1, 0x0100, 0) + MATRIX + struct.pack(">II", 0, 0))
             traks += box(b"trak", tkhd + edts + mdia)
             movie_dur = max(movie_dur, a_movie + audio_empty_edit)
-        mvhd = full(b"mvhd", 0, 0, struct.pack(">IIIIIH", 0, 0, movie_timescale, movie_dur, 0x10000, 0x0100) +
+        mvhd = full(b"mvhd", ver, 0, hdr_times(movie_timescale, movie_dur) + struct.pack(">IH", 0x10000, 0x0100) +
                     bytes(10) + MATRIX + bytes(24) + struct.pack(">I", 3))
         return box(b"moov", mvhd + traks + box(b"udta", box(b"name", b"fixture")))
 

@@ -127,8 +127,9 @@ def _pcm_samples(w, h, n, gop):
     return wr._sps[4:], wr._pps[4:], samples, keys, luma
 
 
-@pytest.mark.parametrize("moov_first,co64", [(False, False), (True, True)])
-def test_cut_keeps_every_track_byte_identical(tmp_path, moov_first, co64):
+@pytest.mark.parametrize("moov_first,co64,version1,stz2", [(False, False, False, False), (True, True, False, False),
+                                                          (False, True, True, True)])
+def test_cut_keeps_every_track_byte_identical(tmp_path, moov_first, co64, version1, stz2):
     """AUD+SEI+slice samples, a ctts box with an edit list, and a PCM audio trak: the cut carries both tracks, sample
     bytes and sample descriptions verbatim, and libavcodec decodes it to the expected pictures."""
     from oracle import scene_oracle
@@ -141,7 +142,7 @@ def test_cut_keeps_every_track_byte_identical(tmp_path, moov_first, co64):
     delta = 512
     meta = write_av_mp4(src, sps=sps, pps=pps, video_samples=samples, keyframes=keys, width=w, height=h,
                         timescale=fps * delta, delta=delta, ctts=[delta] * n, video_media_time=delta, audio_pcm=pcm,
-                        audio_rate=rate, moov_first=moov_first, co64=co64)
+                        audio_rate=rate, moov_first=moov_first, co64=co64, version1=version1, stz2=stz2)
     assert abs(probe_duration(src) - n / fps) < 1e-3
     assert abs(probe_duration(src) - _cv_duration(src)) < 1e-3
     movie = isobmff.read_movie(src)
