@@ -131,9 +131,10 @@ __device__ __forceinline__ int nbits_of(int v) { return 32 - __clz(v < 0 ? -v : 
 
 // Walks the entropy code of one block.  EMIT = false: returns its length in bits.  EMIT = true: writes the bits at
 // bit position `pos` of `buf` (big-endian 32-bit words) and returns the position after the block.
+// zz[k * stride]: coefficient k of the block (the row's coefficients are stored k-major, see jpeg_row_kernel).
 template <bool EMIT>
-__device__ __forceinline__ uint32_t walk_block(const int16_t *zz, int pred, const uint32_t *dc_tab, const uint32_t *ac_tab,
-                                               uint32_t *buf, uint32_t pos) {
+__device__ __forceinline__ uint32_t walk_block(const int16_t *zz, int stride, int pred, const uint32_t *dc_tab,
+                                               const uint32_t *ac_tab, uint32_t *buf, uint32_t pos) {
     uint32_t widx = pos >> 5, acc = 0;
     int fill = (int)(pos & 31u);
     uint32_t total = 0;
@@ -165,7 +166,7 @@ __device__ __forceinline__ uint32_t walk_block(const int16_t *zz, int pred, cons
     int run = 0;
 #pragma unroll 1
     for (int k = 1; k < 64; k++) {
-        const int v = zz[k];
+        const int v = zz[k * stride];
         if (v == 0) {
             run++;
             continue;
@@ -224,8 +225,12 @@ __global__ void __launch_bounds__(JT) jpeg_row_kernel(const __grid_constant__ Jp
     extern __shared__ __align__(16) uint8_t sm[];
     const int row = blockIdx.x, f = blockIdx.y;
     const int nb = a.mw * 6;                             // 8x8 blocks of this MCU row, in scan order
-    int16_t *coef = reinterpret_cast<int16_t *>(sm);                                   // [nb][64]
-    uint32_t *bitbuf = reinterpret_cast<uint32_t *>(sm + (size_t)nb * 128);            // [cap_words]
+    // coefficients K-MAJOR: coef[k * nbp + b].  Threads walk the same k of neighbouring blocks, so a block-major layout
+    // (128 bytes between lanes) put all 32 lanes on one bank: 93 % of the kernel's shared wavefronts were conflicts
+    // (profiles/r02_ncu_jpeg.csv, first build); k-major they are adjacent halfwords.
+    const int nbp = (nb + 1) & ~1;
+    int16_t *coef = reinterpret_cast<int16_t *>(sm);                                   // [64][nbp]
+    uint32_t *bitbuf = reinterpret_cast<uint32_t *>(sm + (size_t)nbp * 128);           // [cap_words]
     uint32_t *tabs = bitbuf + a.cap_words;                                             // [4][256]
     __shared__ uint32_t warp_sums[JT / 32];
     for (int i = threadIdx.x; i < 4 * 256; i += JT) tabs[i] = (&c_huff[0][0])[i];
@@ -277,7 +282,7 @@ __global__ void __launch_bounds__(JT) jpeg_row_kernel(const __grid_constant__ Jp
 #pragma unroll
         for (int i = 0; i < 8; i++) fdct_1d<8, false>(d + i);
         const uint16_t *qd = a.qdiv[chroma];
-        int16_t *o = coef + (size_t)b * 64;
+        int16_t *o = coef + b;
 #pragma unroll
         for (int kz = 0; kz < 64; kz++) {
             constexpr uint8_t zig[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
@@ -286,7 +291,7 @@ __global__ void __launch_bounds__(JT) jpeg_row_kernel(const __grid_constant__ Jp
             const int t = d[zig[kz]];
             const unsigned qv = qd[kz];
             const unsigned mag = ((unsigned)(t < 0 ? -t : t) + (qv >> 1)) / qv;
-            o[kz] = (int16_t)(t < 0 ? -(int)mag : (int)mag);
+            o[kz * nbp] = (int16_t)(t < 0 ? -(int)mag : (int)mag);
         }
     }
     __syncthreads();
@@ -296,14 +301,14 @@ __global__ void __launch_bounds__(JT) jpeg_row_kernel(const __grid_constant__ Jp
     const int b0 = min(nb, (int)threadIdx.x * per), b1 = min(nb, b0 + per);
     auto pred_of = [&](int b) -> int {                   // DC predictor of block b: previous block of its component
         const int m = b / 6, k = b - 6 * m;
-        if (k >= 1 && k <= 3) return coef[(size_t)(b - 1) * 64];
+        if (k >= 1 && k <= 3) return coef[b - 1];
         if (m == 0) return 0;                            // restart at the beginning of every MCU row
-        return coef[(size_t)(b - (k == 0 ? 3 : 6)) * 64];
+        return coef[b - (k == 0 ? 3 : 6)];
     };
     uint32_t mine = 0;
     for (int b = b0; b < b1; b++) {
         const int chroma = (b % 6) >= 4;
-        mine += walk_block<false>(coef + (size_t)b * 64, pred_of(b), tabs + (chroma ? 512 : 0), tabs + (chroma ? 768 : 256),
+        mine += walk_block<false>(coef + b, nbp, pred_of(b), tabs + (chroma ? 512 : 0), tabs + (chroma ? 768 : 256),
                                   nullptr, 0);
     }
     uint32_t total_bits;
@@ -320,7 +325,7 @@ __global__ void __launch_bounds__(JT) jpeg_row_kernel(const __grid_constant__ Jp
     // ---- phase 3: emit
     for (int b = b0; b < b1; b++) {
         const int chroma = (b % 6) >= 4;
-        pos = walk_block<true>(coef + (size_t)b * 64, pred_of(b), tabs + (chroma ? 512 : 0), tabs + (chroma ? 768 : 256),
+        pos = walk_block<true>(coef + b, nbp, pred_of(b), tabs + (chroma ? 512 : 0), tabs + (chroma ? 768 : 256),
                                bitbuf, pos);
     }
     __syncthreads();
@@ -355,18 +360,22 @@ __global__ void __launch_bounds__(JT) jpeg_row_kernel(const __grid_constant__ Jp
     if (threadIdx.x == 0) a.row_bytes[row_index] = out_bytes;
 }
 
-// offsets[f] = first byte of picture f in the packed output, offsets[n] = total (exclusive scan, one block)
+// offsets[f] = first byte of picture f in the packed output, offsets[n] = total (exclusive scan, one block);
+// row_off[f][r] = first byte of MCU row r inside its picture
 __global__ void jpeg_offsets_kernel(const uint32_t *row_bytes, int n_frames, int mh, uint32_t header_len,
-                                    unsigned long long *offsets, unsigned long long out_cap, int *status) {
+                                    unsigned long long *offsets, uint32_t *row_off, unsigned long long out_cap, int *status) {
     __shared__ unsigned long long chunk_sum[1024];
     const int t = threadIdx.x, nt = blockDim.x;
     const int per = (n_frames + nt - 1) / nt;
     const int f0 = min(n_frames, t * per), f1 = min(n_frames, f0 + per);
     unsigned long long s = 0;
     for (int f = f0; f < f1; f++) {
-        unsigned long long sz = header_len + 2ull * (mh - 1) + 2ull;      // RSTn between rows, EOI
-        for (int r = 0; r < mh; r++) sz += row_bytes[(size_t)f * mh + r];
-        s += sz;
+        uint32_t at = header_len;
+        for (int r = 0; r < mh; r++) {
+            row_off[(size_t)f * mh + r] = at;
+            at += row_bytes[(size_t)f * mh + r] + 2u;                    // + RSTn (or EOI after the last row)
+        }
+        s += at;
     }
     chunk_sum[t] = s;
     __syncthreads();
@@ -384,32 +393,29 @@ __global__ void jpeg_offsets_kernel(const uint32_t *row_bytes, int n_frames, int
     unsigned long long run = chunk_sum[t];
     for (int f = f0; f < f1; f++) {
         offsets[f] = run;
-        unsigned long long sz = header_len + 2ull * (mh - 1) + 2ull;
-        for (int r = 0; r < mh; r++) sz += row_bytes[(size_t)f * mh + r];
-        run += sz;
+        const size_t last = (size_t)f * mh + mh - 1;
+        run += row_off[last] + row_bytes[last] + 2u;
     }
 }
 
-__global__ void __launch_bounds__(256) jpeg_assemble_kernel(const uint8_t *header, uint32_t header_len, const uint8_t *scratch,
-                                                            const uint32_t *row_bytes, int mh, int row_cap,
-                                                            const unsigned long long *offsets, unsigned long long out_cap,
-                                                            const int *status, uint8_t *out) {
-    const int f = blockIdx.x;
-    if (*status != 0) return;
+// one block per (MCU row or header, picture): header / row bytes and the marker that follows the row
+__global__ void __launch_bounds__(128) jpeg_assemble_kernel(const uint8_t *header, uint32_t header_len, const uint8_t *scratch,
+                                                            const uint32_t *row_bytes, const uint32_t *row_off, int mh,
+                                                            int row_cap, const unsigned long long *offsets,
+                                                            unsigned long long out_cap, const int *status, uint8_t *out) {
+    const int f = blockIdx.y, r = (int)blockIdx.x - 1;
+    if (*status != 0 || offsets[f + 1] > out_cap) return;
     uint8_t *o = out + offsets[f];
-    if (offsets[f + 1] > out_cap) return;
-    for (uint32_t i = threadIdx.x; i < header_len; i += blockDim.x) o[i] = header[i];
-    unsigned long long at = header_len;
-    for (int r = 0; r < mh; r++) {
-        const uint32_t n = row_bytes[(size_t)f * mh + r];
-        const uint8_t *s = scratch + ((size_t)f * mh + r) * (size_t)row_cap;
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) o[at + i] = s[i];
-        at += n;
-        if (threadIdx.x == 0) {
-            o[at] = 0xFF;
-            o[at + 1] = (uint8_t)(r + 1 < mh ? 0xD0 + (r & 7) : 0xD9);     // RSTm after every row but the last, then EOI
-        }
-        at += 2;
+    if (r < 0) {
+        for (uint32_t i = threadIdx.x; i < header_len; i += blockDim.x) o[i] = header[i];
+        return;
+    }
+    const uint32_t n = row_bytes[(size_t)f * mh + r], at = row_off[(size_t)f * mh + r];
+    const uint8_t *s = scratch + ((size_t)f * mh + r) * (size_t)row_cap;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) o[at + i] = s[i];
+    if (threadIdx.x == 0) {
+        o[at + n] = 0xFF;
+        o[at + n + 1] = (uint8_t)(r + 1 < mh ? 0xD0 + (r & 7) : 0xD9);     // RSTm after every row but the last, then EOI
     }
 }
 
@@ -424,7 +430,7 @@ struct vt_jpeg_plan {
     std::vector<uint8_t> header;
     uint8_t *header_dev = nullptr;
     uint8_t *scratch = nullptr;
-    uint32_t *row_bytes = nullptr;
+    uint32_t *row_bytes = nullptr, *row_off = nullptr;
     int scratch_frames = 0;
 };
 
@@ -469,7 +475,7 @@ extern "C" int vt_jpeg_plan_create(int w, int h, int quality, int expand_range, 
     // bit buffer of an MCU row: as many bytes as the row has samples (a 1:1 "compression" is the refusal point)
     p->cap_words = (p->mw * 16 * 16 * 3 / 2 + 3) / 4;
     p->row_cap = p->cap_words * 4 + p->cap_words;         // + 25 % for stuffed zero bytes
-    p->smem = (size_t)p->mw * 6 * 128 + (size_t)p->cap_words * 4 + 4 * 256 * 4;
+    p->smem = (size_t)((p->mw * 6 + 1) & ~1) * 128 + (size_t)p->cap_words * 4 + 4 * 256 * 4;
     if (p->smem > 220 * 1024) {
         delete p;
         vt::set_error("vt_jpeg_plan_create: %d-pixel-wide pictures need %zu bytes of shared memory per MCU row", w, p->smem);
@@ -523,6 +529,7 @@ extern "C" void vt_jpeg_plan_destroy(vt_jpeg_plan *p) {
     if (p->header_dev) cudaFree(p->header_dev);
     if (p->scratch) cudaFree(p->scratch);
     if (p->row_bytes) cudaFree(p->row_bytes);
+    if (p->row_off) cudaFree(p->row_off);
     delete p;
 }
 
@@ -549,11 +556,13 @@ extern "C" int vt_jpeg_encode_yuv420p(vt_jpeg_plan *p, const uint8_t *src_dev, s
         VT_CUDA(cudaStreamSynchronize(st));
         if (p->scratch) cudaFree(p->scratch);
         if (p->row_bytes) cudaFree(p->row_bytes);
+        if (p->row_off) cudaFree(p->row_off);
         p->scratch = nullptr;
-        p->row_bytes = nullptr;
+        p->row_bytes = p->row_off = nullptr;
         p->scratch_frames = 0;
         VT_CUDA(cudaMalloc((void **)&p->scratch, (size_t)n_frames * p->mh * p->row_cap));
         VT_CUDA(cudaMalloc((void **)&p->row_bytes, (size_t)n_frames * p->mh * sizeof(uint32_t)));
+        VT_CUDA(cudaMalloc((void **)&p->row_off, (size_t)n_frames * p->mh * sizeof(uint32_t)));
         p->scratch_frames = n_frames;
     }
     VT_CUDA(cudaMemsetAsync(status_dev, 0, sizeof(int32_t), st));
@@ -573,10 +582,12 @@ extern "C" int vt_jpeg_encode_yuv420p(vt_jpeg_plan *p, const uint8_t *src_dev, s
     VT_LAUNCHED("jpeg_row_kernel");
     const int nt = n_frames >= 1024 ? 1024 : ((n_frames + 31) / 32) * 32;
     vt::jpeg_offsets_kernel<<<1, nt, 0, st>>>(p->row_bytes, n_frames, p->mh, (uint32_t)p->header.size(),
-                                              (unsigned long long *)offsets_dev, (unsigned long long)out_cap, status_dev);
+                                              (unsigned long long *)offsets_dev, p->row_off, (unsigned long long)out_cap,
+                                              status_dev);
     VT_LAUNCHED("jpeg_offsets_kernel");
-    vt::jpeg_assemble_kernel<<<(unsigned)n_frames, 256, 0, st>>>(p->header_dev, (uint32_t)p->header.size(), p->scratch,
-                                                                 p->row_bytes, p->mh, p->row_cap,
+    vt::jpeg_assemble_kernel<<<dim3((unsigned)p->mh + 1, (unsigned)n_frames), 128, 0, st>>>(
+                                                                 p->header_dev, (uint32_t)p->header.size(), p->scratch,
+                                                                 p->row_bytes, p->row_off, p->mh, p->row_cap,
                                                                  (const unsigned long long *)offsets_dev,
                                                                  (unsigned long long)out_cap, status_dev, out_dev);
     VT_LAUNCHED("jpeg_assemble_kernel");
