@@ -194,3 +194,49 @@ def write_fragmented_mp4(path, *, n_frag=4, per_frag=25, timescale=12800, delta=
     with open(path, "wb") as f:
         f.write(data)
     return total / timescale
+
+
+def write_fragmented_av(path, *, sps, pps, video_samples, keyframes, width, height, timescale=30000, delta=1000,
+                        per_fragment=12, base_is_moof=True, with_tfdt=True):
+    """A fragmented MP4 (`moov` with empty tables + `mvex`, then `moof` + `mdat` per fragment) that carries real H.264
+    samples: per-sample sizes and flags in `trun`, `tfdt`, default-base-is-moof or an explicit base_data_offset."""
+    vs = [b"".join(struct.pack(">I", len(n)) + n for n in nals) for nals in video_samples]
+    avcc = struct.pack(">BBBBBB", 1, sps[1], sps[2], sps[3], 0xFF, 0xE1) + struct.pack(">H", len(sps)) + sps + \
+        struct.pack(">BH", 1, len(pps)) + pps
+    avc1 = struct.pack(">6xH", 1) + bytes(16) + struct.pack(">HH", width, height) + \
+        struct.pack(">IIIH", 0x00480000, 0x00480000, 0, 1) + bytes(32) + struct.pack(">Hh", 0x18, -1) + box(b"avcC", avcc)
+    stbl = full(b"stsd", 0, 0, struct.pack(">I", 1) + box(b"avc1", avc1)) + full(b"stts", 0, 0, struct.pack(">I", 0)) + \
+        full(b"stsc", 0, 0, struct.pack(">I", 0)) + full(b"stsz", 0, 0, struct.pack(">II", 0, 0)) + \
+        full(b"stco", 0, 0, struct.pack(">I", 0))
+    dinf = box(b"dinf", full(b"dref", 0, 0, struct.pack(">I", 1) + full(b"url ", 0, 1, b"")))
+    minf = box(b"minf", full(b"vmhd", 0, 1, bytes(8)) + dinf + box(b"stbl", stbl))
+    mdia = box(b"mdia", full(b"mdhd", 0, 0, struct.pack(">IIIIHH", 0, 0, timescale, 0, 0x55C4, 0)) +
+               full(b"hdlr", 0, 0, struct.pack(">I4s12x", 0, b"vide") + b"V\x00") + minf)
+    tkhd = full(b"tkhd", 0, 3, struct.pack(">IIIII", 0, 0, 1, 0, 0) + bytes(8) + struct.pack(">hhhH", 0, 0, 0, 0) +
+                MATRIX + struct.pack(">II", width << 16, height << 16))
+    mvex = full(b"trex", 0, 0, struct.pack(">IIIII", 1, 1, delta, 0, 0x00010000))
+    mvhd = full(b"mvhd", 0, 0, struct.pack(">IIIIIH", 0, 0, 1000, 0, 0x10000, 0x0100) + bytes(10) + MATRIX +
+                bytes(24) + struct.pack(">I", 2))
+    data = box(b"ftyp", b"iso5" + struct.pack(">I", 0x200) + b"iso5iso6mp41") + \
+        box(b"moov", mvhd + box(b"trak", tkhd + mdia) + box(b"mvex", mvex))
+    n = len(vs)
+    seq = 0
+    for f0 in range(0, n, per_fragment):
+        f1 = min(n, f0 + per_fragment)
+        seq += 1
+        rows = b"".join(struct.pack(">II", len(vs[i]), 0x02000000 if keyframes[i] else 0x01010000) for i in range(f0, f1))
+
+        def moof_bytes(data_offset, base):
+            flags = 0x020000 if base_is_moof else 0x000001
+            tfhd = full(b"tfhd", 0, flags, struct.pack(">I", 1) + (b"" if base_is_moof else struct.pack(">Q", base)))
+            tfdt = full(b"tfdt", 1, 0, struct.pack(">Q", f0 * delta)) if with_tfdt else b""
+            trun = full(b"trun", 0, 0x000601, struct.pack(">Ii", f1 - f0, data_offset) + rows)   # sizes + flags per sample
+            return box(b"moof", full(b"mfhd", 0, 0, struct.pack(">I", seq)) + box(b"traf", tfhd + tfdt + trun))
+
+        moof_len = len(moof_bytes(0, 0))
+        here = len(data)
+        moof = moof_bytes(moof_len + 8, here) if base_is_moof else moof_bytes(0, here + moof_len + 8)
+        data += moof + box(b"mdat", b"".join(vs[f0:f1]))
+    with open(path, "wb") as f:
+        f.write(data)
+    return {"video_samples": vs}

@@ -16,7 +16,7 @@ import struct
 import numpy as np
 import pytest
 
-from mp4_fixture import write_av_mp4, write_fragmented_mp4
+from mp4_fixture import write_av_mp4, write_fragmented_av, write_fragmented_mp4
 from video_transformer_b200 import container, isobmff, synth, video_segmenter
 from video_transformer_b200.video_utils import probe_duration
 
@@ -266,8 +266,44 @@ def test_fragmented_mp4_duration(tmp_path, with_mehd):
     p = tmp_path / "frag.mp4"
     exp = write_fragmented_mp4(p, with_mehd=with_mehd)
     assert abs(probe_duration(p) - exp) < 1e-3
+    movie = isobmff.read_movie(p)
+    assert movie.fragmented and movie.tracks[0].n == 100 and int(movie.tracks[0].deltas.sum()) == 100 * 512
+
+
+@pytest.mark.parametrize("base_is_moof,with_tfdt", [(True, True), (False, False)])
+def test_fragmented_source_is_cut_like_any_other(tmp_path, base_is_moof, with_tfdt):
+    """moof/traf/tfhd/tfdt/trun are indexed into ordinary sample tables: the cut of a fragmented file is a plain faststart
+    MP4 with the same sample bytes, which libavcodec decodes to the expected pictures."""
+    from oracle import scene_oracle
+    w, h, n, gop, fps = 128, 96, 60, 10, 30
+    sps, pps, samples, keys, luma = _pcm_samples(w, h, n, gop)
+    src = tmp_path / "frag.mp4"
+    meta = write_fragmented_av(src, sps=sps, pps=pps, video_samples=samples, keyframes=keys, width=w, height=h,
+                               base_is_moof=base_is_moof, with_tfdt=with_tfdt)
+    assert abs(probe_duration(src) - n / fps) < 1e-3
+    assert len(_cv_frames(src)) == n                      # libavformat agrees that this is a fragmented file with n pictures
+    idx = container.probe(src)
+    assert idx.n_frames == n and idx.keyframe.tolist() == keys and idx.extra["decodable"]
+    video_segmenter.configure(frame_buffers=False)
     out = tmp_path / "cut.mp4"
-    assert video_segmenter.extract_segment(p, 0.0, 1.0, out) is False and not out.exists()
+    start, end = 0.7, 1.6
+    assert video_segmenter.extract_segment(src, start, end, out) is True
+    first, last = scene_oracle.frames_for_window(start, end, n, fps, 1, np.nonzero(keys)[0], True)
+    cut = isobmff.read_movie(out)
+    assert not cut.fragmented and cut.tracks[0].n == last - first
+    data = out.read_bytes()
+    v = cut.tracks[0]
+    assert [data[int(o):int(o) + int(z)] for o, z in zip(v.offsets, v.sizes)] == meta["video_samples"][first:last]
+    cap = cv2.VideoCapture(str(out), cv2.CAP_FFMPEG)
+    cap.set(cv2.CAP_PROP_CONVERT_RGB, 0)
+    k = first
+    while True:
+        ok, fr = cap.read()
+        if not ok:
+            break
+        assert np.array_equal(np.asarray(fr).reshape(-1)[: w * h].reshape(h, w), luma[k]), k
+        k += 1
+    assert k == last
 
 
 def test_keyframe_at_or_before_on_foreign_file(tmp_path):

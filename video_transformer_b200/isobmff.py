@@ -13,7 +13,7 @@ Selection rule (derived from the command line above): s
 d = round(end - start, 3); the reference track (first video track) keeps the samples whose presentation time is in
 [s, s + d), extended back to the last sync sample at or before the first of them; every other track keeps the
 samples that overlap the reference track's kept time span.  The movie box is written before the media data
-(`+faststart`).  Fragmented files (`moof`) are probed for their duration but not cut.
+(`+faststart`).  Fragmented sources (`moof`/`traf`/`trun`) are indexed like any other; the output is never fragmented.
 """
 from __future__ import annotations
 
@@ -394,6 +394,125 @@ def _fragments_duration(path: Path, tops, moov: bytes, movie: Movie) -> float:
     return best
 
 
+def _append_fragments(path: Path, tops, moov: bytes, movie: Movie) -> None:
+    """Index the samples of a fragmented file (moof/traf/tfhd/tfdt/trun) into the tracks' tables, so that a
+    fragmented source is cut like any other (the output is an ordinary, non-fragmented faststart MP4)."""
+    trex = {}
+    mvex = find_box(moov, 0, len(moov), b"mvex")
+    if mvex:
+        for k, s, e in iter_boxes(moov, mvex[0], mvex[1]):
+            if k == b"trex" and e - s >= 24:
+                tid, _desc, ddur, dsize, dflags = struct.unpack_from(">IIIII", moov, s + 4)
+                trex[tid] = (ddur, dsize, dflags)
+    by_id = {t.track_id: t for t in movie.tracks}
+    acc = {tid: {"sizes": [], "offsets": [], "deltas": [], "cts": [], "sync": [], "dts": [], "next_dts": None, "has_cts": False}
+           for tid in by_id}
+    with open(path, "rb") as f:
+        for kind, b0, p0, b1 in tops:
+            if kind != b"moof":
+                continue
+            f.seek(p0)
+            moof = f.read(b1 - p0)
+            prev_end = None                                   # end of the previous traf's data (legacy base rule)
+            for k, s, e in iter_boxes(moof, 0, len(moof)):
+                if k != b"traf":
+                    continue
+                tfhd = find_box(moof, s, e, b"tfhd")
+                if not tfhd:
+                    continue
+                fl = struct.unpack_from(">I", moof, tfhd[0])[0] & 0xFFFFFF
+                tid = struct.unpack_from(">I", moof, tfhd[0] + 4)[0]
+                a = acc.get(tid)
+                if a is None:
+                    continue
+                p = tfhd[0] + 8
+                base = None
+                if fl & 0x1:
+                    base = struct.unpack_from(">Q", moof, p)[0]
+                    p += 8
+                if fl & 0x2:
+                    p += 4
+                ddur, dsize, dflags = trex.get(tid, (0, 0, 0))
+                if fl & 0x8:
+                    ddur = struct.unpack_from(">I", moof, p)[0]
+                    p += 4
+                if fl & 0x10:
+                    dsize = struct.unpack_from(">I", moof, p)[0]
+                    p += 4
+                if fl & 0x20:
+                    dflags = struct.unpack_from(">I", moof, p)[0]
+                    p += 4
+                if base is None:
+                    base = b0 if (fl & 0x020000 or prev_end is None) else prev_end
+                tfdt = find_box(moof, s, e, b"tfdt")
+                if tfdt:
+                    v = moof[tfdt[0]]
+                    a["next_dts"] = struct.unpack_from(">Q" if v == 1 else ">I", moof, tfdt[0] + 4)[0]
+                elif a["next_dts"] is None:
+                    a["next_dts"] = 0
+                run_pos = base
+                for k2, s2, e2 in iter_boxes(moof, s, e):
+                    if k2 != b"trun":
+                        continue
+                    tv = moof[s2]
+                    tf = struct.unpack_from(">I", moof, s2)[0] & 0xFFFFFF
+                    cnt = struct.unpack_from(">I", moof, s2 + 4)[0]
+                    q = s2 + 8
+                    if tf & 0x1:
+                        run_pos = base + struct.unpack_from(">i", moof, q)[0]
+                        q += 4
+                    first_flags = None
+                    if tf & 0x4:
+                        first_flags = struct.unpack_from(">I", moof, q)[0]
+                        q += 4
+                    ncol = bool(tf & 0x100) + bool(tf & 0x200) + bool(tf & 0x400) + bool(tf & 0x800)
+                    tab = _be(moof, ">u4", cnt * ncol, q).reshape(cnt, ncol).astype(np.int64) if ncol else None
+                    col = 0
+                    if tf & 0x100:
+                        dur = tab[:, col]; col += 1
+                    else:
+                        dur = np.full(cnt, ddur, np.int64)
+                    if tf & 0x200:
+                        size = tab[:, col]; col += 1
+                    else:
+                        size = np.full(cnt, dsize, np.int64)
+                    if tf & 0x400:
+                        flags = tab[:, col]; col += 1
+                    else:
+                        flags = np.full(cnt, dflags, np.int64)
+                        if first_flags is not None and cnt:
+                            flags[0] = first_flags
+                    if tf & 0x800:
+                        cts = tab[:, col].astype(np.uint32).view(np.int32).astype(np.int64) if tv else tab[:, col]
+                        a["has_cts"] = True
+                    else:
+                        cts = np.zeros(cnt, np.int64)
+                    offs = run_pos + np.concatenate(([0], np.cumsum(size)[:-1])) if cnt else np.zeros(0, np.int64)
+                    dts = a["next_dts"] + np.concatenate(([0], np.cumsum(dur)[:-1])) if cnt else np.zeros(0, np.int64)
+                    a["sizes"].append(size); a["offsets"].append(offs); a["deltas"].append(dur); a["cts"].append(cts)
+                    a["sync"].append((flags & 0x00010000) == 0); a["dts"].append(dts)
+                    run_pos += int(size.sum())
+                    a["next_dts"] += int(dur.sum())
+                prev_end = run_pos
+    for tid, a in acc.items():
+        if not a["sizes"]:
+            continue
+        t = by_id[tid]
+        cat = lambda key, dt: np.concatenate(a[key]).astype(dt)          # noqa: E731
+        t.sizes = np.concatenate((t.sizes, cat("sizes", np.uint64)))
+        t.offsets = np.concatenate((t.offsets, cat("offsets", np.uint64)))
+        base_dts = int(t.dts[-1] + t.deltas[-1]) if t.dts.size else 0
+        frag_dts = cat("dts", np.int64)
+        t.dts = np.concatenate((t.dts, frag_dts + (base_dts if frag_dts.size and frag_dts[0] == 0 and t.dts.size else 0)))
+        t.deltas = np.concatenate((t.deltas, cat("deltas", np.int64)))
+        new_cts = cat("cts", np.int64)
+        if a["has_cts"] or t.cts_off is not None:
+            old = t.cts_off if t.cts_off is not None else np.zeros(t.sync.size, np.int64)
+            t.cts_off = np.concatenate((old, new_cts))
+        t.sync = np.concatenate((t.sync, cat("sync", bool)))
+        t.has_stss = t.has_stss or not bool(t.sync.all())
+
+
 def read_movie(path: str | Path) -> Movie:
     """Parse the movie box of an ISO-BMFF file.  Raises BmffError when there is none."""
     path = Path(path)
@@ -426,8 +545,10 @@ def read_movie(path: str | Path) -> Movie:
             if t is not None:
                 movie.tracks.append(t)
     movie.fragmented = any(kind == b"moof" for kind, *_ in tops)
-    if movie.fragmented and not movie.duration:
-        movie.fragment_duration_s = _fragments_duration(path, tops, moov, movie)
+    if movie.fragmented:
+        if not movie.duration:
+            movie.fragment_duration_s = _fragments_duration(path, tops, moov, movie)
+        _append_fragments(path, tops, moov, movie)
     return movie
 
 
@@ -497,8 +618,6 @@ def cut_movie(movie: Movie, start: float, end: float, dst: str | Path, *, stream
                              IDR is re-expressed by that IDR's sample).
     Returns None when the window selects nothing; raises BmffError/OSError on malformed input.
     """
-    if movie.fragmented and not any(t.n for t in movie.tracks):
-        raise BmffError("fragmented MP4 (moof): stream copy not supported")
     ref = movie.video_track() or next((t for t in movie.tracks if t.n), None)
     if ref is None:
         return None
