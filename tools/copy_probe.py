@@ -70,3 +70,34 @@ for name, fn in (("sendfile", sendfile), ("copy_file_range", cfr), ("pread_pwrit
         out[name + "_error"] = repr(e)
 os.unlink(src); os.unlink(dst)
 print(json.dumps(out, indent=1))
+
+# ---- several threads copying disjoint ranges of ONE output file (is the write path serialised per file?) ----
+import threading
+with open(src, "wb") as f:
+    f.write(os.urandom(1 << 20) * (SIZE >> 20))
+res2 = {}
+for nt in (1, 2, 4):
+    for mode in ("cold", "warm"):
+        if mode == "cold" and os.path.exists(dst):
+            os.unlink(dst)
+        fi = os.open(src, os.O_RDONLY)
+        fo = os.open(dst, os.O_RDWR | os.O_CREAT, 0o644)
+        step = SIZE // nt
+
+        def work(i):
+            lo, hi = i * step, (i + 1) * step if i + 1 < nt else SIZE
+            done = lo
+            while done < hi:
+                done += os.copy_file_range(fi, fo, hi - done, done, done)
+
+        ts = [threading.Thread(target=work, args=(i,)) for i in range(nt)]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        dt = time.perf_counter() - t0
+        os.close(fi); os.close(fo)
+        res2["copy_file_range_%dthreads_%s_gbs" % (nt, mode)] = SIZE / dt / 1e9
+os.unlink(src); os.unlink(dst)
+print(json.dumps(res2, indent=1))
