@@ -240,3 +240,63 @@ def write_fragmented_av(path, *, sps, pps, video_samples, keyframes, width, heig
     with open(path, "wb") as f:
         f.write(data)
     return {"video_samples": vs}
+
+
+# ---- a minimal Matroska writer (EBML) for tests: one AVC video track and one Opus audio track ---------------------------
+def _ebml(eid, payload):
+    n = len(payload)
+    for width in range(1, 9):
+        if n < (1 << (7 * width)) - 1:
+            size = ((1 << (7 * width)) | n).to_bytes(width, "big")
+            break
+    return eid + size + payload
+
+
+def _u(eid, value, width=None):
+    width = width or max(1, (value.bit_length() + 7) // 8)
+    return _ebml(eid, value.to_bytes(width, "big"))
+
+
+def write_mkv(path, *, sps, pps, video_samples, keyframes, width, height, fps=30, opus_packets=None, opus_ms=20,
+              frames_per_cluster=10):
+    """video_samples: lists of NAL byte strings (stored length-prefixed, CodecPrivate = avcC, as V_MPEG4/ISO/AVC);
+    opus_packets: list of byte strings, one per opus_ms milliseconds (A_OPUS with an OpusHead CodecPrivate).  SimpleBlocks,
+    1 ms timestamps, Duration filled in.  Returns the sample byte strings per track."""
+    vs = [b"".join(struct.pack(">I", len(n)) + n for n in nals) for nals in video_samples]
+    avcc = struct.pack(">BBBBBB", 1, sps[1], sps[2], sps[3], 0xFF, 0xE1) + struct.pack(">H", len(sps)) + sps + \
+        struct.pack(">BH", 1, len(pps)) + pps
+    head = _ebml(b"\x1a\x45\xdf\xa3", _u(b"\x42\x86", 1) + _u(b"\x42\xf7", 1) + _u(b"\x42\xf2", 4) + _u(b"\x42\xf3", 8) +
+                 _ebml(b"\x42\x82", b"matroska") + _u(b"\x42\x87", 4) + _u(b"\x42\x85", 2))
+    n = len(vs)
+    dur_ms = n * 1000.0 / fps
+    info = _ebml(b"\x15\x49\xa9\x66", _u(b"\x2a\xd7\xb1", 1000000) + _ebml(b"\x44\x89", struct.pack(">d", dur_ms)) +
+                 _ebml(b"\x4d\x80", b"fixture") + _ebml(b"\x57\x41", b"fixture"))
+    vtrack = _ebml(b"\xae", _u(b"\xd7", 1) + _u(b"\x73\xc5", 1) + _u(b"\x83", 1) + _ebml(b"\x86", b"V_MPEG4/ISO/AVC") +
+                   _ebml(b"\x63\xa2", avcc) + _u(b"\x23\xe3\x83", int(1e9 / fps)) +
+                   _ebml(b"\xe0", _u(b"\xb0", width) + _u(b"\xba", height)))
+    tracks = vtrack
+    opus_head = b""
+    if opus_packets:
+        opus_head = b"OpusHead" + bytes([1, 2]) + struct.pack("<HIh", 312, 48000, 0) + bytes([0])
+        tracks += _ebml(b"\xae", _u(b"\xd7", 2) + _u(b"\x73\xc5", 2) + _u(b"\x83", 2) + _ebml(b"\x86", b"A_OPUS") +
+                        _ebml(b"\x63\xa2", opus_head) +
+                        _ebml(b"\xe1", _ebml(b"\xb5", struct.pack(">f", 48000.0)) + _u(b"\x9f", 2)))
+    tracks = _ebml(b"\x16\x54\xae\x6b", tracks)
+    events = [(int(round(i * 1000.0 / fps)), 1, i) for i in range(n)]
+    events += [(i * opus_ms, 2, i) for i in range(len(opus_packets or []))]
+    events.sort()
+    clusters = b""
+    cur, cur_ts, in_cluster = b"", None, 0
+    for ts, trk, i in events:
+        if cur_ts is None or (trk == 1 and keyframes[i] and in_cluster >= frames_per_cluster) or ts - cur_ts > 30000:
+            if cur_ts is not None:
+                clusters += _ebml(b"\x1f\x43\xb6\x75", _u(b"\xe7", cur_ts) + cur)
+            cur, cur_ts, in_cluster = b"", ts, 0
+        payload = vs[i] if trk == 1 else opus_packets[i]
+        flags = 0x80 if (trk == 2 or keyframes[i]) else 0
+        cur += _ebml(b"\xa3", bytes([0x80 | trk]) + struct.pack(">h", ts - cur_ts) + bytes([flags]) + payload)
+        in_cluster += trk == 1
+    clusters += _ebml(b"\x1f\x43\xb6\x75", _u(b"\xe7", cur_ts) + cur)
+    with open(path, "wb") as f:
+        f.write(head + _ebml(b"\x18\x53\x80\x67", info + tracks + clusters))
+    return {"video_samples": vs, "opus_packets": list(opus_packets or []), "opus_head": opus_head}

@@ -16,7 +16,7 @@ import struct
 import numpy as np
 import pytest
 
-from mp4_fixture import write_av_mp4, write_fragmented_av, write_fragmented_mp4
+from mp4_fixture import write_av_mp4, write_fragmented_av, write_fragmented_mp4, write_mkv
 from video_transformer_b200 import container, isobmff, synth, video_segmenter
 from video_transformer_b200.video_utils import probe_duration
 
@@ -333,3 +333,67 @@ def test_truncated_and_garbage_inputs_are_refused(tmp_path):
     junk.write_bytes(b"\x00\x00\x00\x18ftypisom" + bytes(range(200)))
     assert probe_duration(junk) == 0.0
     assert video_segmenter.extract_segment(junk, 0.0, 1.0, tmp_path / "o2.mp4") is False
+
+
+@pytest.mark.parametrize("name,fourcc", [("m.mkv", "VP90"), ("n.mkv", "mp4v"), ("o.webm", "VP90")])
+def test_matroska_source_is_stream_copied_into_mp4(tmp_path, name, fourcc):
+    """`ffmpeg -ss S -i IN.webm -t D -c copy OUT.mp4` re-wraps Matroska streams: VP9 and MPEG-4 tracks written by
+    libavformat's matroska muxer are indexed, cut at a keyframe and decode to exactly the source's pictures."""
+    from oracle import scene_oracle
+    src = tmp_path / name
+    n, fps = 90, 25
+    _cv_write(src, fourcc, n=n, fps=float(fps))
+    idx = container.probe(src)
+    assert idx is not None and idx.n_frames == n and (idx.fps_num, idx.fps_den) == (fps, 1)
+    assert idx.extra["container"] == "matroska" and not idx.extra["decodable"]
+    keys = np.nonzero(idx.keyframe)[0]
+    out = tmp_path / "seg" / "segment_0000.mp4"
+    start, end = 1.3, 2.9
+    assert video_segmenter.extract_segment(src, start, end, out) is True
+    first, last = scene_oracle.frames_for_window(start, end, n, fps, 1, keys, True)
+    side = json.loads(out.with_suffix(".json").read_text())
+    assert (side["first_picture"], side["last_picture"]) == (first, last) and side["frames"] is None
+    ref, got = _cv_frames(src), _cv_frames(out)
+    assert len(got) == last - first
+    for i, fr in enumerate(got):
+        assert np.array_equal(fr, ref[first + i]), i
+    assert abs(probe_duration(out) - (last - first) / fps) < 2e-3
+
+
+def test_matroska_avc_and_opus_tracks_become_avc1_and_opus(tmp_path):
+    """A hand-written MKV (AVC video with AUD+SEI+slice samples, Opus audio): both tracks arrive in the MP4 with their
+    sample bytes unchanged, avcC verbatim, OpusHead re-expressed as dOps (big endian), and libavcodec decodes the video."""
+    from oracle import scene_oracle
+    w, h, n, gop, fps = 128, 96, 60, 10, 30
+    sps, pps, samples, keys, luma = _pcm_samples(w, h, n, gop)
+    packets = [bytes([0xFC, k & 0xFF]) + bytes((k * 7 + j) & 0xFF for j in range(40 + k % 5)) for k in range(100)]   # 2 s
+    src = tmp_path / "av.mkv"
+    meta = write_mkv(src, sps=sps, pps=pps, video_samples=samples, keyframes=keys, width=w, height=h, fps=fps,
+                     opus_packets=packets)
+    assert abs(probe_duration(src) - 2.0) < 1e-3
+    assert len(_cv_frames(src)) == n                     # libavformat reads the fixture as 60 pictures
+    video_segmenter.configure(frame_buffers=False)
+    out = tmp_path / "cut.mp4"
+    assert video_segmenter.extract_segment(src, 0.7, 1.6, out) is True
+    first, last = scene_oracle.frames_for_window(0.7, 1.6, n, fps, 1, np.nonzero(keys)[0], True)
+    cut = isobmff.read_movie(out)
+    assert [t.codec for t in cut.tracks] == [b"avc1", b"Opus"]
+    v, a = cut.tracks
+    data = out.read_bytes()
+    assert [data[int(o):int(o) + int(z)] for o, z in zip(v.offsets, v.sizes)] == meta["video_samples"][first:last]
+    t_lo, t_hi = round(first * 1000 / fps) / 1000, round(last * 1000 / fps) / 1000
+    want = [p for k, p in enumerate(packets) if (k * 20 + 20) / 1000 > t_lo and k * 20 / 1000 < t_hi]
+    assert [data[int(o):int(o) + int(z)] for o, z in zip(a.offsets, a.sizes)] == want
+    dops = a.stsd[a.stsd.index(b"dOps") + 4:]
+    assert dops[:2] == bytes([0, 2]) and struct.unpack_from(">HIh", dops, 2) == (312, 48000, 0) and dops[10] == 0
+    assert b"avcC" in v.stsd and meta["video_samples"][0][4:6] != b""      # avcC carried
+    cap = cv2.VideoCapture(str(out), cv2.CAP_FFMPEG)
+    cap.set(cv2.CAP_PROP_CONVERT_RGB, 0)
+    k = first
+    while True:
+        ok, fr = cap.read()
+        if not ok:
+            break
+        assert np.array_equal(np.asarray(fr).reshape(-1)[: w * h].reshape(h, w), luma[k]), k
+        k += 1
+    assert k == last

@@ -306,8 +306,9 @@ def probe_h264(path: Path) -> StreamIndex | None:
 
 
 def probe(path: Path) -> StreamIndex | None:
-    """Index a media file.  Returns None when the file is not a container this layer can cut (ISO-BMFF with a video
-    track, or a raw Annex-B H.264 stream); `container_duration` still knows Matroska/WebM and AVI."""
+    """Index a media file.  Returns None when the file is not a container this layer can cut (ISO-BMFF or
+    Matroska/WebM with a video track that has an MP4 mapping, or a raw Annex-B H.264 stream); `container_duration`
+    still knows AVI."""
     path = Path(path)
     if not path.is_file() or path.stat().st_size < 16:
         return None
@@ -317,6 +318,17 @@ def probe(path: Path) -> StreamIndex | None:
         return probe_mp4(path)
     if head[:4] == b"\x00\x00\x00\x01" or head[:3] == b"\x00\x00\x01":
         return probe_h264(path)
+    if head[:4] == b"\x1a\x45\xdf\xa3":
+        from . import matroska
+        try:
+            movie = matroska.read_movie(path)
+        except (isobmff.BmffError, struct.error, OSError, IndexError, ValueError):
+            return None
+        idx = index_from_movie(movie)
+        if idx is not None:
+            idx.duration = matroska.duration_seconds(path) or idx.duration
+            idx.extra["container"] = "matroska"
+        return idx
     return None
 
 
