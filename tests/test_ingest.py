@@ -251,3 +251,43 @@ def test_frames_land_directly_in_the_file_and_landing_files_are_recycled(cuda, t
         video_segmenter.configure(target_height=720, batch_frames=32, scene_threshold=0.10, sample_every=1)
         landing.release_all()
         shutil.rmtree(out_dir, ignore_errors=True)
+
+
+def test_pixel_pass_reads_a_matroska_source(cuda, oracle_c, tmp_path):
+    """The decode front end indexes slice NALs by file offset, so a PCM-intra AVC track inside Matroska goes through the
+    same GPU pass as one inside MP4: same frame buffers, same SADs."""
+    import struct
+    import sys
+    sys.path.insert(0, str(__import__("pathlib").Path(__file__).parent))
+    from mp4_fixture import write_mkv
+    w, h, n, gop = 320, 240, 40, 8
+    wr = synth.H264PcmWriter(w, h, 30, 1)
+    samples, keys = [], []
+    for k in range(n):
+        if k % gop == 0:
+            samples.append([wr.idr(*synth.testsrc_frame(w, h, k, k // gop), with_params=False)[4:]])
+            keys.append(True)
+        else:
+            samples.append([wr.skip()[4:]])
+            keys.append(False)
+    mkv = tmp_path / "clip.mkv"
+    write_mkv(mkv, sps=wr._sps[4:], pps=wr._pps[4:], video_samples=samples, keyframes=keys, width=w, height=h, fps=30)
+    mp4 = tmp_path / "clip.mp4"
+    sys.path.insert(0, str(tmp_path))
+    from mp4_fixture import write_av_mp4
+    write_av_mp4(mp4, sps=wr._sps[4:], pps=wr._pps[4:], video_samples=samples, keyframes=keys, width=w, height=h,
+                 timescale=30000, delta=1000)
+    saved = video_segmenter.configure()
+    try:
+        video_segmenter.configure(target_height=120, batch_frames=8, scene_threshold=0.05)
+        outs = []
+        for src in (mkv, mp4):
+            out = tmp_path / (src.suffix[1:]) / "segment_0000.mp4"
+            assert video_segmenter.extract_segment(src, 0.3, 1.2, out) is True
+            side = json.loads(out.with_suffix(".json").read_text())
+            outs.append((side, np.fromfile(out.with_suffix(".frames"), np.uint8)))
+        assert outs[0][0]["frames"] == outs[1][0]["frames"] > 0
+        assert outs[0][0]["sad"] == outs[1][0]["sad"] and outs[0][0]["cuts"] == outs[1][0]["cuts"]
+        assert np.array_equal(outs[0][1], outs[1][1])
+    finally:
+        video_segmenter.configure(**saved)
