@@ -33,7 +33,7 @@ def _runs(values):
 def write_av_mp4(path, *, sps, pps, video_samples, keyframes, width, height, timescale=15360, delta=512,
                  ctts=None, video_media_time=0, audio_rate=48000, audio_channels=2, audio_pcm=None,
                  audio_chunk=1024, video_chunk=5, moov_first=False, co64=False, movie_timescale=1000,
-                 audio_empty_edit=0, version1=False, stz2=False):
+                 audio_empty_edit=0, version1=False, stz2=False, audio_codec=b"sowt"):
     """video_samples: list of lists of NAL byte strings (no start codes / lengths).  audio_pcm: int16 array
     [n, channels] or None.  version1: 64-bit mvhd / tkhd / mdhd / elst; stz2: the video sizes as a compact (16-bit)
     `stz2` box.  Returns a dict describing what was written (sample byte strings per track)."""
@@ -117,7 +117,7 @@ def write_av_mp4(path, *, sps, pps, video_samples, keyframes, width, height, tim
             a_movie = n_a * movie_timescale // audio_rate
             sowt = struct.pack(">6xH", 1) + struct.pack(">HHIHHHHI", 0, 0, 0, audio_channels, 16, 0, 0,
                                                         audio_rate << 16)
-            stbl = full(b"stsd", 0, 0, struct.pack(">I", 1) + box(b"sowt", sowt))
+            stbl = full(b"stsd", 0, 0, struct.pack(">I", 1) + box(audio_codec, sowt))
             stbl += full(b"stts", 0, 0, struct.pack(">III", 1, n_a, 1))
             r = _runs([b - a for a, b in a_chunks])
             ent, first = b"", 1

@@ -261,6 +261,29 @@ def test_audio_that_starts_late_keeps_its_offset(tmp_path):
     assert a.n == int(0.75 * rate)                         # and runs to the end of the video span
 
 
+def test_transform_coded_audio_keeps_its_preroll_behind_the_edit_list(tmp_path):
+    """An `mp4a` track (the payload is irrelevant to a stream copy) gets one extra sample before the first audible one,
+    and the edit list starts the presentation after it."""
+    w, h, n, gop = 128, 96, 60, 15
+    sps, pps, samples, keys, _ = _pcm_samples(w, h, n, gop)
+    rate = 8000
+    pcm = (np.arange(2 * rate) % 199).astype(np.int16)[:, None]
+    src = tmp_path / "aac.mp4"
+    meta = write_av_mp4(src, sps=sps, pps=pps, video_samples=samples, keyframes=keys, width=w, height=h, timescale=30000,
+                        delta=1000, audio_pcm=pcm, audio_rate=rate, audio_channels=1, audio_codec=b"mp4a")
+    video_segmenter.configure(frame_buffers=False)
+    out = tmp_path / "cut.mp4"
+    assert video_segmenter.extract_segment(src, 0.5, 1.5, out) is True
+    cut = isobmff.read_movie(out)
+    v, a = cut.tracks
+    assert a.codec == b"mp4a" and a.n == rate + 1                     # one pre-roll sample before t = 0.5 s
+    empty, mt = a.edit_shift(cut.timescale)
+    assert empty == 0.0 and mt == 1                                    # ... which the edit list skips
+    data = out.read_bytes()
+    first = data[int(a.offsets[0]):int(a.offsets[0]) + 2]
+    assert first == meta["audio_bytes"][(rate // 2 - 1) * 2:(rate // 2) * 2]
+
+
 @pytest.mark.parametrize("with_mehd", [True, False])
 def test_fragmented_mp4_duration(tmp_path, with_mehd):
     p = tmp_path / "frag.mp4"
@@ -382,8 +405,10 @@ def test_matroska_avc_and_opus_tracks_become_avc1_and_opus(tmp_path):
     data = out.read_bytes()
     assert [data[int(o):int(o) + int(z)] for o, z in zip(v.offsets, v.sizes)] == meta["video_samples"][first:last]
     t_lo, t_hi = round(first * 1000 / fps) / 1000, round(last * 1000 / fps) / 1000
-    want = [p for k, p in enumerate(packets) if (k * 20 + 20) / 1000 > t_lo and k * 20 / 1000 < t_hi]
+    hit = [k for k in range(len(packets)) if (k * 20 + 20) / 1000 > t_lo and k * 20 / 1000 < t_hi]
+    want = packets[max(0, hit[0] - 4):hit[-1] + 1]                      # 80 ms of Opus pre-roll, hidden by the edit list
     assert [data[int(o):int(o) + int(z)] for o, z in zip(a.offsets, a.sizes)] == want
+    assert a.edit_shift(cut.timescale)[1] >= 60                        # media time skips the pre-roll packets
     dops = a.stsd[a.stsd.index(b"dOps") + 4:]
     assert dops[:2] == bytes([0, 2]) and struct.unpack_from(">HIh", dops, 2) == (312, 48000, 0) and dops[10] == 0
     assert b"avcC" in v.stsd and meta["video_samples"][0][4:6] != b""      # avcC carried

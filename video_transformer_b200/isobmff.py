@@ -24,6 +24,8 @@ from pathlib import Path
 
 import numpy as np
 
+AUDIO_PREROLL_SAMPLES = {b"mp4a": 1, b"Opus": 4, b".mp3": 1, b"ac-3": 1, b"ec-3": 1}
+
 CONTAINER_BOXES = (b"moov", b"trak", b"edts", b"mdia", b"minf", b"dinf", b"stbl", b"mvex", b"moof", b"traf")
 
 
@@ -655,6 +657,10 @@ def cut_movie(movie: Movie, start: float, end: float, dst: str | Path, *, stream
                 k = np.nonzero(t.sync[:a + 1])[0]
                 if k.size:
                     a = int(k[-1])
+            else:
+                # transform-coded audio needs the packets just before the first audible one to decode it correctly
+                # (AAC: one frame of overlap; Opus: 80 ms): keep them in the file, the edit list below skips them
+                a = max(0, a - AUDIO_PREROLL_SAMPLES.get(t.codec, 0))
         sizes = t.sizes[a:b].copy()
         override = None
         if t is ref and first_sample is not None:
