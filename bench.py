@@ -570,32 +570,45 @@ def _run_ours(args, K, Wm, rank, world, local, cores, dev, store, L, barrier, wo
         ceil_gbs = reps * chunk / (time.perf_counter() - tc) / 1e9
     del d_src, h_dst
     barrier()
-    # ---- concurrent file-write ceiling of the box: every rank stream-copies UNIT-sized byte ranges of the clip at once
-    # (the MP4 half of extract_segment is a file -> file copy of the unit's samples; the synthetic bitstream is
-    # uncompressed, ~115 KB per picture, so this path carries far more bytes than a real H.264 stream would) ---------
+    # ---- concurrent file-write ceiling of the box: every rank copies UNIT-sized byte ranges of the clip at once, the
+    # way the product does (the MP4 half of extract_segment is a file -> file copy of the unit's samples: plain stores
+    # into a recycled mapping of the output, landing.acquire_mapped), and with copy_file_range for comparison.  The
+    # synthetic bitstream is uncompressed, ~115 KB per picture, so this path carries far more bytes than a real H.264
+    # stream would ---------
+    import mmap as _mmap
     unit_bytes = int(idx.nal_offsets[min(UNIT_PICTURES, n_clip - 1)] - idx.nal_offsets[0])
     probe_out = os.path.join(my_dir, "write_probe.bin")
+    src_map = np.memmap(raw_path, dtype=np.uint8, mode="r")
     fi = os.open(raw_path, os.O_RDONLY)
     fo = os.open(probe_out, os.O_RDWR | os.O_CREAT, 0o644)
+    os.ftruncate(fo, unit_bytes)
+    probe_mm = _mmap.mmap(fo, unit_bytes)
+    dst_map = np.frombuffer(probe_mm, dtype=np.uint8)
 
     def copy_once():
+        dst_map[:] = src_map[:unit_bytes]
+
+    def copy_in_kernel():
         done = 0
         while done < unit_bytes:
             done += os.copy_file_range(fi, fo, unit_bytes - done, done, done)
 
-    try:
+    copy_once()
+    barrier()
+    tw = time.perf_counter()
+    for _ in range(3):
         copy_once()
-        if world > 1:
-            dist.barrier()
+    write_gbs = 3 * unit_bytes / (time.perf_counter() - tw) / 1e9
+    try:
+        copy_in_kernel()
+        barrier()
         tw = time.perf_counter()
         for _ in range(3):
-            copy_once()
-        write_gbs = 3 * unit_bytes / (time.perf_counter() - tw) / 1e9
+            copy_in_kernel()
+        kernel_copy_gbs = 3 * unit_bytes / (time.perf_counter() - tw) / 1e9
     except (OSError, AttributeError):
-        write_gbs = 0.0
+        kernel_copy_gbs = 0.0
     os.close(fi)
-    os.close(fo)
-    os.unlink(probe_out)
     bytes_per_picture_bs = unit_bytes / UNIT_PICTURES
     barrier()
     # ---- the same three transfers AT ONCE, in the workload's byte mix: per picture the path moves frame_bytes of D2H,
@@ -608,21 +621,18 @@ def _run_ours(args, K, Wm, rank, world, local, cores, dev, store, L, barrier, wo
     d_in = torch.empty(h2d_n, dtype=torch.uint8, device=dev)
     h_in = torch.empty(h2d_n, dtype=torch.uint8, pin_memory=True)
     s_a, s_b = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    fi = os.open(raw_path, os.O_RDONLY)
-    fo = os.open(probe_out, os.O_RDWR | os.O_CREAT, 0o644)
     reps = 24
     stop = threading.Event()
 
     def copier():
         off = 0
+        n_mix = min(h2d_n, unit_bytes)
         for _ in range(reps):
-            done = 0
-            while done < h2d_n and not stop.is_set():
-                try:
-                    done += os.copy_file_range(fi, fo, h2d_n - done, (off + done) % max(1, unit_bytes - h2d_n), done)
-                except (OSError, AttributeError):
-                    return
-            off += h2d_n
+            if stop.is_set():
+                return
+            lo = off % max(1, unit_bytes - n_mix)
+            dst_map[:n_mix] = src_map[lo:lo + n_mix]
+            off += n_mix
 
     for i in range(2):
         with torch.cuda.stream(s_a):
@@ -643,7 +653,8 @@ def _run_ours(args, K, Wm, rank, world, local, cores, dev, store, L, barrier, wo
     s_b.synchronize()
     stop.set()
     th.join()
-    os.close(fi)
+    del dst_map, src_map
+    probe_mm.close()
     os.close(fo)
     os.unlink(probe_out)
     del d_src, h_dst, d_in, h_in
@@ -723,7 +734,7 @@ def _run_ours(args, K, Wm, rank, world, local, cores, dev, store, L, barrier, wo
         dsink_fps = n_ds / (time.perf_counter() - t0)
 
     stats = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    per_rank = torch.tensor([float(my_units), busy, ceil_gbs, float(e2e_d2h), float(e2e_h2d), write_gbs, mixed_gbs], dtype=torch.float64,
+    per_rank = torch.tensor([float(my_units), busy, ceil_gbs, float(e2e_d2h), float(e2e_h2d), write_gbs, mixed_gbs, kernel_copy_gbs], dtype=torch.float64,
                             device=dev)
     all_rank = [torch.zeros_like(per_rank) for _ in range(world)]
     if world > 1:
@@ -744,12 +755,14 @@ def _run_ours(args, K, Wm, rank, world, local, cores, dev, store, L, barrier, wo
     step_pictures = R * F
     value = world * K * step_pictures / (dev_ms_max * 1e-3)
     e2e_pictures = total_units * UNIT_PICTURES
+    from video_transformer_b200 import landing as _landing
+    landing_stats = _landing.stats()
     e2e_value = e2e_pictures / (e2e_ms_max * 1e-3)
     segs_per_s = value / (720.0 * FPS)                   # shipped plan for 7200 s: 10 segments of 720 s
     ranks = [{"rank": r, "units": int(t[0]), "busy_s": float(t[1]),
               "d2h_gbs": float(t[3]) / float(t[1]) / 1e9 if float(t[1]) > 0 else 0.0,
               "d2h_ceiling_gbs": float(t[2]), "file_copy_ceiling_gbs": float(t[5]),
-              "d2h_in_mix_gbs": float(t[6])} for r, t in enumerate(all_rank)]
+              "d2h_in_mix_gbs": float(t[6]), "copy_file_range_gbs": float(t[7])} for r, t in enumerate(all_rank)]
     ceiling_fps = sum(r["d2h_ceiling_gbs"] for r in ranks) * 1e9 / (fb + 1032)
     write_fps = sum(r["file_copy_ceiling_gbs"] for r in ranks) * 1e9 / bytes_per_picture_bs
     mixed_fps = sum(r["d2h_in_mix_gbs"] for r in ranks) * 1e9 / (fb + 1032)
@@ -767,6 +780,7 @@ def _run_ours(args, K, Wm, rank, world, local, cores, dev, store, L, barrier, wo
                 "through": "video_segmenter.extract_segment (host MP4 in, faststart MP4 + .frames + .json on /dev/shm out)",
                 "pictures": e2e_pictures, "seconds": e2e_ms_max * 1e-3, "unit_pictures": UNIT_PICTURES,
                 "landing": landing_mode,
+                "mp4_write": "recycled mapping" if landing_stats.get("mapped_files") else "copy_file_range",
                 "last_call_ms": {k: round(v * 1e3, 2) for k, v in timings.items()}},
         "e2e_cold": {"value": UNIT_PICTURES / cold_s, "unit": UNIT,
                      "note": "first call of the process: index, plans, pinned staging, and a new landing file "
@@ -780,9 +794,10 @@ def _run_ours(args, K, Wm, rank, world, local, cores, dev, store, L, barrier, wo
                         "mixed_d2h_gbs_per_rank": [r["d2h_in_mix_gbs"] for r in ranks],
                         "mixed_frames_per_s": mixed_fps, "e2e_of_mixed": e2e_value / mixed_fps if mixed_fps else None,
                         "note": "measured right after the timed arm, all ranks at once: (a) 44 MB chunks device -> pinned "
-                                "host (a picture costs frame_bytes + 1032 B of D2H); (b) copy_file_range of one unit's "
-                                "samples on /dev/shm (the stream-copy half of the call; the synthetic bitstream is "
-                                "uncompressed PCM).  The lower of the two bounds the plugin call on this box.  (c) "
+                                "host (a picture costs frame_bytes + 1032 B of D2H); (b) one unit's samples copied "
+                                "into an existing mapping of a /dev/shm file (the stream-copy half of the call, "
+                                "landing.acquire_mapped; per_rank.copy_file_range_gbs is the in-kernel copy beside it; "
+                                "the synthetic bitstream is uncompressed PCM).  The lower of the two bounds the plugin call on this box.  (c) "
                                 "`mixed`: D2H + H2D + file copy at once in the workload's byte mix (per picture: frame "
                                 "bytes out, bitstream bytes in, bitstream bytes copied) -- the D2H rate that survives is "
                                 "what this path could reach with no kernels and no host code in the way."},

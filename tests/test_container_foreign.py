@@ -11,6 +11,7 @@ MJPEG); (ii) MP4s from the test-side writer tests/mp4_fixture.py with AUD+SEI+sl
 and a second (PCM `sowt`) audio trak.
 """
 import json
+from pathlib import Path
 import struct
 
 import numpy as np
@@ -422,3 +423,40 @@ def test_matroska_avc_and_opus_tracks_become_avc1_and_opus(tmp_path):
         assert np.array_equal(np.asarray(fr).reshape(-1)[: w * h].reshape(h, w), luma[k]), k
         k += 1
     assert k == last
+
+
+def test_mapped_and_in_kernel_copies_write_the_same_file(tmp_path):
+    """The segment MP4 written through the recycled mapping (RAM-backed output directory) is byte-identical to the one
+    copy_file_range writes, including a re-cut into recycled pages and a first-sample replacement."""
+    import shutil
+    import tempfile
+    from video_transformer_b200 import landing
+    if not landing.on_memory_fs("/dev/shm"):
+        pytest.skip("no RAM-backed file system here")
+    w, h, n, gop, fps = 96, 80, 90, 10, 30
+    sps, pps, samples, keys, _ = _pcm_samples(w, h, n, gop)
+    rate = 48000
+    t = np.arange(n * rate // fps)
+    pcm = np.stack([(t % 311).astype(np.int16), (t % 1000).astype(np.int16)], 1)
+    src = tmp_path / "src.mp4"
+    write_av_mp4(src, sps=sps, pps=pps, video_samples=samples, keyframes=keys, width=w, height=h, timescale=fps * 512,
+                 delta=512, audio_pcm=pcm, audio_rate=rate)
+    movie = isobmff.read_movie(src)
+    shm = tempfile.mkdtemp(prefix="vt_test_", dir="/dev/shm")
+    try:
+        for k, (start, end, copy) in enumerate([(0.5, 2.0, True), (1.0, 2.6, True), (0.7, 1.9, False)]):
+            plain = tmp_path / ("plain_%d.mp4" % k)
+            fast = Path(shm) / "seg.mp4"
+            kw = {}
+            if not copy:
+                vt = movie.video_track()
+                kw["first_sample"] = src.read_bytes()[int(vt.offsets[20]):int(vt.offsets[20]) + int(vt.sizes[20])]
+            r0 = isobmff.cut_movie(movie, start, end, plain, stream_copy=copy, **kw)
+            if fast.exists():
+                fast.unlink()                   # the consumer deleted the previous segment: its pages are reused
+            r1 = isobmff.cut_movie(movie, start, end, fast, stream_copy=copy, mapped=True, **kw)
+            assert r0 == r1 and fast.read_bytes() == plain.read_bytes()
+            assert landing.stats()["mapped_files"] == 1
+    finally:
+        landing.release_all()
+        shutil.rmtree(shm, ignore_errors=True)

@@ -56,3 +56,46 @@ def test_stale_arena_names_are_swept(tmp_path):
     landing._sweep_stale(arena)
     assert not dead.exists() and mine.exists() and other.exists()
     assert frames.read_bytes() == b"x"                           # the artefact survives, only the extra name went
+
+
+def _shm_dir():
+    import tempfile
+    if not os.path.isdir("/dev/shm") or not landing.on_memory_fs("/dev/shm"):
+        import pytest
+        pytest.skip("no RAM-backed file system here")
+    return tempfile.mkdtemp(prefix="vt_test_", dir="/dev/shm")
+
+
+def test_mapped_output_is_refused_off_ram(tmp_path):
+    if landing.on_memory_fs(tmp_path):
+        import pytest
+        pytest.skip("tmp_path is RAM-backed here")
+    assert landing.acquire_mapped(tmp_path / "a.mp4", 4096) is None
+    assert not (tmp_path / "a.mp4").exists()
+
+
+def test_mapped_output_recycles_pages_and_sizes_the_file_exactly():
+    import shutil
+    d = _shm_dir()
+    try:
+        from pathlib import Path
+        a = landing.acquire_mapped(Path(d) / "a.mp4", 1_000_003)
+        assert a is not None and not a.recycled and a.array.size == 1_000_003
+        a.array[:] = 7
+        assert os.path.getsize(a.path) == 1_000_003 and a.path.read_bytes() == b"\x07" * 1_000_003
+        b = landing.acquire_mapped(Path(d) / "b.mp4", 900_000)             # a.mp4 still exists: a second arena file
+        assert b is not None and not b.recycled and b.slot is not a.slot
+        os.unlink(a.path)                                                  # the consumer is done with a.mp4
+        c = landing.acquire_mapped(Path(d) / "c.mp4", 1_100_000)           # a little larger: still fits the capacity
+        assert c is not None and c.recycled and c.slot is a.slot
+        c.array[:] = 9
+        assert os.path.getsize(c.path) == 1_100_000 and c.path.read_bytes() == b"\x09" * 1_100_000
+        b.array[:] = 1
+        assert b.path.read_bytes() == b"\x01" * 900_000                    # the other file is untouched by the reuse
+        # replacing an existing name frees its arena file for the same call
+        c2 = landing.acquire_mapped(c.path, 1_050_000)
+        assert c2 is not None and c2.recycled and c2.slot is c.slot and os.path.getsize(c2.path) == 1_050_000
+        assert landing.stats()["mapped_files"] == 2
+    finally:
+        landing.release_all()
+        shutil.rmtree(d, ignore_errors=True)

@@ -606,7 +606,7 @@ def _patch_duration(payload: bytes, at_v0: int, at_v1: int, value: int) -> bytes
 def cut_movie(movie: Movie, start: float, end: float, dst: str | Path, *, stream_copy: bool = True,
               accurate_presentation: bool = False, selection: tuple | None = None,
               first_sample: bytes | None = None, chunk_seconds: float = 0.5,
-              chunk_bytes: int = 4 << 20) -> CutResult | None:
+              chunk_bytes: int = 4 << 20, mapped: bool = False) -> CutResult | None:
     """Write the samples of [start, end) of every track of `movie` into a new faststart MP4 at `dst`.
 
     stream_copy            : extend the reference track back to its last sync sample (what `-c copy` does).
@@ -696,7 +696,7 @@ def cut_movie(movie: Movie, start: float, end: float, dst: str | Path, *, stream
                       "chunk_time": np.asarray(chunk_time, np.float64)})
     if not plans:
         return None
-    total_bytes = write_plans(dst, plans, mts, movie.ftyp, movie.path)
+    total_bytes = write_plans(dst, plans, mts, movie.ftyp, movie.path, mapped=mapped)
     return CutResult(first, last, first_acc, len(plans), total_bytes, t_present)
 
 
@@ -765,10 +765,12 @@ def plan_memory_track(t: Track, samples: list, deltas, sync=None, chunk_seconds:
             "chunk_count": cc, "chunk_bytes": cb, "chunk_time": rel[cf], "mem": samples, "all_sync": bool(sync.all())}
 
 
-def write_plans(dst: str | Path, plans: list, mts: int, ftyp: bytes = b"", src_path: Path | None = None) -> int:
+def write_plans(dst: str | Path, plans: list, mts: int, ftyp: bytes = b"", src_path: Path | None = None,
+                mapped: bool = False) -> int:
     """Write the planned tracks into a faststart MP4: ftyp, moov, mdat with the tracks' chunks interleaved by time.
     Sample bytes come from src_path (plans made from a parsed file) or from memory (plan_memory_track).  Returns the
-    media bytes written."""
+    media bytes written.  mapped=True writes through landing.acquire_mapped (a recycled mapping of the output, RAM-
+    backed file systems only) and falls back to the in-kernel copy when that is not available."""
     for p in plans:
         if p["pres_ticks"] is None:
             p["pres_ticks"] = (p["media_dur"] * mts + p["t"].timescale - 1) // p["t"].timescale
@@ -887,6 +889,26 @@ def write_plans(dst: str | Path, plans: list, mts: int, ftyp: bytes = b"", src_p
     if need_src and src_path is None:
         raise BmffError("plans refer to a source file but none was given")
     src_size = os.path.getsize(src_path) if need_src else 0
+    head = ftyp + moov + struct.pack(">I4sQ", 1, b"mdat", 16 + total_bytes)
+    if mapped:
+        for lo, ln in zip(src_lo, src_len):
+            if lo >= 0 and lo + ln > src_size:
+                raise BmffError("sample data past the end of the file (truncated source)")
+        from . import landing
+        out = landing.acquire_mapped(dst, len(head) + int(sum(src_len)))
+        if out is not None:
+            try:
+                view = _source_view(src_path) if need_src else None
+                a = out.array
+                a[:len(head)] = np.frombuffer(head, np.uint8)
+                pos = len(head)
+                for i, (lo, ln) in enumerate(zip(src_lo, src_len)):
+                    a[pos:pos + ln] = np.frombuffer(over_at[i], np.uint8) if lo < 0 else view[lo:lo + ln]
+                    pos += ln
+            except BaseException:
+                out.abort()
+                raise
+            return total_bytes
     # An existing output is overwritten IN PLACE and trimmed at the end: rewriting pages a file already owns is faster
     # than allocating fresh ones (tmpfs on the GPU box: 5.1 vs 3.8 GB/s, tools/copy_probe.py), which matters when a
     # segment is re-cut (retries, `ffmpeg -y` semantics).
@@ -894,7 +916,6 @@ def write_plans(dst: str | Path, plans: list, mts: int, ftyp: bytes = b"", src_p
     try:
         out_fd = os.open(dst, os.O_RDWR | os.O_CREAT, 0o644)
         try:
-            head = ftyp + moov + struct.pack(">I4sQ", 1, b"mdat", 16 + total_bytes)
             pos = _write_all(out_fd, head, 0)
             for i, (lo, ln) in enumerate(zip(src_lo, src_len)):
                 if lo < 0:
@@ -911,6 +932,21 @@ def write_plans(dst: str | Path, plans: list, mts: int, ftyp: bytes = b"", src_p
         if in_fd >= 0:
             os.close(in_fd)
     return total_bytes
+
+
+_SOURCE_VIEWS: dict = {}
+
+
+def _source_view(path: Path) -> np.ndarray:
+    """Read-only mapping of a source file, kept for the segments that follow (two files at most)."""
+    st = os.stat(path)
+    key = (str(path), st.st_size, st.st_mtime_ns, st.st_ino)
+    v = _SOURCE_VIEWS.get(key)
+    if v is None:
+        while len(_SOURCE_VIEWS) >= 2:
+            _SOURCE_VIEWS.pop(next(iter(_SOURCE_VIEWS)))
+        v = _SOURCE_VIEWS[key] = np.memmap(path, dtype=np.uint8, mode="r")
+    return v
 
 
 def _write_all(fd: int, data: bytes, offset: int) -> int:

@@ -40,13 +40,16 @@ _arena_of_device: dict = {}      # st_dev -> arena directory: hard links work an
 class _Slot:
     """One registered file mapping."""
 
-    def __init__(self, path: Path, nbytes: int):
+    def __init__(self, path: Path, nbytes: int, register: bool = True):
         self.path, self.nbytes = path, nbytes
         self.fd = os.open(path, os.O_RDWR | os.O_CREAT | os.O_EXCL, 0o644)
         try:
-            rc = _libc.posix_fallocate(self.fd, 0, nbytes)
-            if rc != 0:
-                raise OSError(rc, "posix_fallocate(%d bytes) failed" % nbytes)
+            if register:
+                rc = _libc.posix_fallocate(self.fd, 0, nbytes)
+                if rc != 0:
+                    raise OSError(rc, "posix_fallocate(%d bytes) failed" % nbytes)
+            else:
+                os.ftruncate(self.fd, nbytes)     # pages arrive as they are first written
             self.mm = mmap.mmap(self.fd, nbytes, flags=mmap.MAP_SHARED, prot=mmap.PROT_READ | mmap.PROT_WRITE)
         except Exception:
             os.close(self.fd)
@@ -54,8 +57,9 @@ class _Slot:
             raise
         self.array = np.frombuffer(self.mm, dtype=np.uint8)
         self.base = self.array.ctypes.data
-        self.registered = lib().vt_host_register(ctypes.c_void_p(self.base), nbytes) == 0
-        self.tensor = torch.from_numpy(self.array)
+        self.plain = not register
+        self.registered = register and lib().vt_host_register(ctypes.c_void_p(self.base), nbytes) == 0
+        self.tensor = torch.from_numpy(self.array) if register else None
         self.stamp = 0
 
     def free(self) -> bool:
@@ -166,30 +170,16 @@ def acquire(path: str | Path, nbytes: int, direct: bool | None = None) -> Landin
         if path.exists() or path.is_symlink():
             path.unlink()                       # a replaced artefact frees its arena file for the search below
         if direct:
-            try:
-                dev_id = os.stat(path.parent).st_dev
-            except OSError:
-                dev_id = None
-            arena = _arena_of_device.get(dev_id)
-            if arena is None or not arena.is_dir():
-                arena = path.parent / ARENA_DIR
-                _arena_of_device[dev_id] = arena
-                _sweep_stale(arena)
+            arena = _arena_for(path.parent)
             slot = None
             for s in _slots:
-                if s.nbytes == nbytes and s.path.parent == arena and s.free():
+                if s.nbytes == nbytes and not s.plain and s.path.parent == arena and s.free():
                     slot = s
                     break
             recycled = slot is not None
             if slot is None:
                 # over the cap: release the oldest files, free ones first (busy ones keep their `.frames` name)
-                used = sum(s.nbytes for s in _slots)
-                for s in sorted(_slots, key=lambda s: (not s.free(), s.stamp)):
-                    if used + nbytes <= _arena_cap():
-                        break
-                    s.destroy()
-                    _slots.remove(s)
-                    used -= s.nbytes
+                _make_room(nbytes, False, _arena_cap())
                 try:
                     arena.mkdir(exist_ok=True)
                     _seq += 1
@@ -214,6 +204,125 @@ def acquire(path: str | Path, nbytes: int, direct: bool | None = None) -> Landin
             if direct is True and os.environ.get("VT_LANDING") == "direct-only":
                 raise OSError("cannot register a mapping of %s" % path)
         return Landing(path, nbytes, None, False)
+
+
+def _make_room(nbytes: int, plain: bool, cap: int) -> None:
+    """Release the oldest arena files of one kind until nbytes more fit under cap (free ones first)."""
+    mine = [s for s in _slots if s.plain == plain]
+    used = sum(s.nbytes for s in mine)
+    for s in sorted(mine, key=lambda s: (not s.free(), s.stamp)):
+        if used + nbytes <= cap:
+            break
+        s.destroy()
+        _slots.remove(s)
+        used -= s.nbytes
+
+
+def _arena_for(parent: Path) -> Path:
+    try:
+        dev_id = os.stat(parent).st_dev
+    except OSError:
+        dev_id = None
+    arena = _arena_of_device.get(dev_id)
+    if arena is None or not arena.is_dir():
+        arena = parent / ARENA_DIR
+        _arena_of_device[dev_id] = arena
+        _sweep_stale(arena)
+    return arena
+
+
+_MEMORY_FS_MAGIC = {0x01021994, 0x858458F6}     # tmpfs, ramfs (statfs f_type)
+
+
+def on_memory_fs(path: Path) -> bool:
+    """True when `path` lives on a RAM-backed file system (statfs f_type; /proc/self/mounts as the second opinion)."""
+    buf = ctypes.create_string_buffer(256)
+    try:
+        if _libc.statfs(os.fsencode(str(path)), buf) == 0:
+            if ctypes.c_long.from_buffer(buf).value & 0xFFFFFFFF in _MEMORY_FS_MAGIC:
+                return True
+    except (OSError, AttributeError):
+        pass
+    try:
+        best, kind = "", ""
+        real = os.path.realpath(path)
+        with open("/proc/self/mounts") as f:
+            for line in f:
+                parts = line.split()
+                if len(parts) >= 3 and (real == parts[1] or real.startswith(parts[1].rstrip("/") + "/")) \
+                        and len(parts[1]) >= len(best):
+                    best, kind = parts[1], parts[2]
+        return kind in ("tmpfs", "ramfs")
+    except OSError:
+        return False
+
+
+class MappedFile:
+    """An output file (a segment's MP4) written through a long-lived shared mapping: `array[:nbytes]` IS the file."""
+
+    def __init__(self, path: Path, nbytes: int, slot: _Slot, recycled: bool):
+        self.path, self.nbytes, self.slot, self.recycled = path, nbytes, slot, recycled
+        self.array = slot.array[:nbytes]
+
+    def abort(self) -> None:
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+
+
+def _mapped_cap() -> int:
+    return int(float(os.environ.get("VT_MP4_ARENA_CAP_GB", "8")) * (1 << 30))
+
+
+def acquire_mapped(path: str | Path, nbytes: int) -> MappedFile | None:
+    """`path` as a file of exactly nbytes whose content is written by plain stores into a recycled mapping.
+
+    The stream copy of a segment (K4) is a 100-400 MB file-to-file copy.  Through write()/copy_file_range() every
+    call allocates the output's pages anew (3.6-5 GB/s on the B200 box's tmpfs, one thread, and the rate does not
+    scale with threads); into a mapping whose pages already exist it is a memcpy (7-8 GB/s per thread).  The same
+    recycling as the `.frames` landing makes the pages exist: the MP4 name is a hard link to an arena file, and once
+    the consumer deletes the name the next segment is copied into the same pages.  The mapping covers the slot's
+    capacity; the FILE is ftruncate()d to the exact size each time, so only the tail pages churn between segments of
+    slightly different sizes.  Returns None when the file system is not RAM-backed (dirty shared mappings of disk files
+    buy nothing) or the arena cannot be set up -- the caller then uses the in-kernel copy."""
+    global _seq
+    path = Path(path)
+    if nbytes <= 0 or os.environ.get("VT_MP4_ARENA", "1") == "0":
+        return None
+    path.parent.mkdir(parents=True, exist_ok=True)
+    if not on_memory_fs(path.parent):
+        return None
+    with _lock:
+        if path.exists() or path.is_symlink():
+            path.unlink()
+        arena = _arena_for(path.parent)
+        slot = None
+        for s in _slots:
+            if s.plain and s.path.parent == arena and nbytes <= s.nbytes <= 2 * nbytes + (64 << 20) and s.free() \
+                    and (slot is None or s.nbytes < slot.nbytes):
+                slot = s
+        recycled = slot is not None
+        try:
+            if slot is None:
+                cap = -(-(nbytes + nbytes // 8) // (16 << 20)) * (16 << 20)
+                _make_room(cap, True, _mapped_cap())
+                arena.mkdir(exist_ok=True)
+                _seq += 1
+                slot = _Slot(arena / ("landing_%d_%d.bin" % (os.getpid(), _seq)), cap, register=False)
+            os.ftruncate(slot.fd, nbytes)
+            os.link(slot.path, path)
+        except OSError:
+            if slot is not None:
+                slot.destroy()
+                if recycled:
+                    _slots.remove(slot)
+            return None
+        _seq += 1
+        slot.stamp = _seq
+        if not recycled:
+            _slots.append(slot)
+        return MappedFile(path, nbytes, slot, recycled)
 
 
 def _sweep_stale(arena: Path) -> None:
@@ -244,7 +353,7 @@ def _sweep_stale(arena: Path) -> None:
 def stats() -> dict:
     with _lock:
         return {"files": len(_slots), "bytes": sum(s.nbytes for s in _slots),
-                "free": sum(1 for s in _slots if s.free())}
+                "free": sum(1 for s in _slots if s.free()), "mapped_files": sum(1 for s in _slots if s.plain)}
 
 
 def release_all() -> None:

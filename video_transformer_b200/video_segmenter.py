@@ -75,6 +75,9 @@ _OPTIONS = {
     # this many seconds (a score-only GPU pass over the two windows finds the cuts).  0 keeps the reference's times, so
     # plans and manifests stay value-identical by default.
     "snap_tolerance_s": 0.0,
+    # write the segment's MP4 through a recycled mapping when the output directory is RAM-backed (landing.acquire_mapped);
+    # anywhere else, or when False, the bytes move with copy_file_range
+    "mapped_output": True,
 }
 
 
@@ -262,6 +265,7 @@ def _cut(src: Path, start: float, end: float, dst: Path, stream_copy: bool) -> b
                 first = k if k is not None else first
                 kwargs = {"stream_copy": True, "accurate_presentation": True, "selection": (first, last, first_acc)}
         # the stream copy (file -> file, inside the kernel) runs beside the GPU pass
+        kwargs["mapped"] = bool(_OPTIONS["mapped_output"])
         copier = _Background(isobmff.cut_movie, movie, start, end, dst, **kwargs)
     LAST_TIMINGS["index"] = time.perf_counter() - t_begin
     try:
