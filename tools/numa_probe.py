@@ -1,109 +1,98 @@
-#!/usr/bin/env python
-"""Where do the D2H landing buffers live?  Prints the GPU <-> NUMA topology of the box and, under torchrun, the
-concurrent per-rank D2H / H2D copy rate with the rank's threads (a) left where the launcher put them, (b) bound to
-the cores of the GPU's own NUMA node, (c) bound to a remote node.  Pinned pages are placed first-touch, so the
-binding that is in force when the buffer is allocated decides which socket's memory the PCIe writes land in.
+"""Where do the 8 GPUs' D2H copies lose bandwidth?  Prints what the box exposes about NUMA / affinity and measures the
+D2H rate of every GPU into pinned buffers first-touched under different CPU affinities, alone and all at once.
 
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/numa_probe.py
+    gpurun --gpus 8 -- python tools/numa_probe.py
 """
-import glob, os, subprocess, sys, time
+import glob
+import os
+import subprocess
+import time
 
 import torch
-import torch.distributed as dist
 
 
-def cpulist(s):
-    out = []
-    for part in s.strip().split(","):
-        if not part:
-            continue
-        a, _, b = part.partition("-")
-        out += list(range(int(a), int(b or a) + 1))
-    return out
-
-
-def nodes():
-    d = {}
-    for p in sorted(glob.glob("/sys/devices/system/node/node[0-9]*")):
-        d[int(p.rsplit("node", 1)[1])] = cpulist(open(p + "/cpulist").read())
-    return d
-
-
-def gpu_node(i):
-    pr = torch.cuda.get_device_properties(i)
-    bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+def sh(cmd):
     try:
-        return bdf, int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
-    except OSError as e:
-        return bdf, "?(%s)" % e
-
-
-def rate(dev, label, world):
-    n = 44 * 1024 * 1024
-    d = [torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(2)]
-    h = [torch.empty(n, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
-    for x in h:
-        x.zero_()
-    s = torch.cuda.Stream()
-    res = []
-    for direction in ("d2h", "h2d"):
-        with torch.cuda.stream(s):
-            for i in range(8):
-                (h[i % 2].copy_(d[i % 2], non_blocking=True) if direction == "d2h" else d[i % 2].copy_(h[i % 2], non_blocking=True))
-            s.synchronize()
-            if world > 1:
-                dist.barrier()
-            t0 = time.perf_counter()
-            reps = 96
-            for i in range(reps):
-                (h[i % 2].copy_(d[i % 2], non_blocking=True) if direction == "d2h" else d[i % 2].copy_(h[i % 2], non_blocking=True))
-            s.synchronize()
-            dt = time.perf_counter() - t0
-        res.append(reps * n / dt / 1e9)
-    print("rank %d %-28s d2h %.1f GB/s  h2d %.1f GB/s  (cpus now: %d)" % (
-        int(os.environ.get("RANK", 0)), label, res[0], res[1], len(os.sched_getaffinity(0))), flush=True)
+        return subprocess.run(cmd, shell=True, capture_output=True, text=True, timeout=30).stdout.strip()
+    except Exception as e:  # noqa: BLE001
+        return "ERR %r" % e
 
 
 def main():
-    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    if world > 1:
-        dist.init_process_group("gloo")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    nd = nodes()
-    if rank == 0:
-        print("cpu_count", os.cpu_count(), "affinity", len(os.sched_getaffinity(0)), "nodes", {k: len(v) for k, v in nd.items()})
-        for k, v in nd.items():
-            print(" node", k, "cpus", v[:4], "...", v[-2:])
-            try:
-                print("   ", open("/sys/devices/system/node/node%d/meminfo" % k).read().splitlines()[0])
-            except OSError:
-                pass
-        for i in range(torch.cuda.device_count()):
-            print(" gpu", i, gpu_node(i))
+    print("cpus allowed:", len(os.sched_getaffinity(0)), sorted(os.sched_getaffinity(0))[:8], "...")
+    print(sh("lscpu | grep -i -E 'numa|socket|model name|^CPU\\(s\\)'"))
+    print(sh("nvidia-smi topo -m"))
+    for p in sorted(glob.glob("/sys/devices/system/node/node*/cpulist")):
+        print(p, open(p).read().strip())
+    print(sh("cat /proc/self/status | grep -i -E 'cpus_allowed_list|mems_allowed_list'"))
+    n = torch.cuda.device_count()
+    nodes = {}
+    for p in sorted(glob.glob("/sys/devices/system/node/node*/cpulist")):
+        cpus = set()
+        for part in open(p).read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        nodes[os.path.basename(os.path.dirname(p))] = cpus
+    all_cpus = os.sched_getaffinity(0)
+    if not nodes:
+        half = sorted(all_cpus)
+        nodes = {"lowhalf": set(half[:len(half) // 2]), "highhalf": set(half[len(half) // 2:])}
+    chunk = 256 << 20
+    bufs = {}
+    for name, cpus in nodes.items():
+        use = cpus & all_cpus
+        if not use:
+            continue
         try:
-            print(subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=30).stdout)
-        except Exception as e:
-            print("topo failed", e)
-    full = os.sched_getaffinity(0)
-    bdf, node = gpu_node(local)
-    rate(dev, "launcher affinity", world)
-    if isinstance(node, int) and node in nd and len(nd) > 1:
-        own = set(nd[node]) & full
-        other = set(c for k, v in nd.items() if k != node for c in v) & full
-        if own:
-            os.sched_setaffinity(0, own)
-            rate(dev, "bound to own node %d" % node, world)
-        if other:
-            os.sched_setaffinity(0, other)
-            rate(dev, "bound to remote node", world)
-        os.sched_setaffinity(0, full)
-    else:
-        print("rank", rank, "gpu node", node, "- single node box or unknown, nothing to bind")
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+            os.sched_setaffinity(0, use)
+        except OSError as e:
+            print("setaffinity failed", e)
+        for g in range(n):
+            torch.cuda.set_device(g)
+            h = torch.empty(chunk, dtype=torch.uint8, pin_memory=True)
+            h.fill_(1)
+            bufs[(name, g)] = h
+    os.sched_setaffinity(0, all_cpus)
+    dsrc = [torch.ones(chunk, dtype=torch.uint8, device="cuda:%d" % g) for g in range(n)]
+    streams = [torch.cuda.Stream("cuda:%d" % g) for g in range(n)]
+
+    def run(gs, name, reps=8):
+        for g in gs:
+            with torch.cuda.stream(streams[g]):
+                bufs[(name[g] if isinstance(name, dict) else name, g)].copy_(dsrc[g], non_blocking=True)
+        for g in gs:
+            streams[g].synchronize()
+        t0 = time.perf_counter()
+        done = {}
+        for _ in range(reps):
+            for g in gs:
+                with torch.cuda.stream(streams[g]):
+                    bufs[(name[g] if isinstance(name, dict) else name, g)].copy_(dsrc[g], non_blocking=True)
+        for g in gs:
+            streams[g].synchronize()
+            done[g] = reps * chunk / (time.perf_counter() - t0) / 1e9
+        return done
+
+    names = [k for k in nodes if (k, 0) in bufs]
+    for name in names:
+        print("alone, buffers touched on", name, {g: round(run([g], name)[g], 1) for g in range(n)})
+    for name in names:
+        r = run(list(range(n)), name)
+        print("all at once, buffers touched on", name, {g: round(v, 1) for g, v in r.items()}, "sum", round(sum(r.values()), 1))
+    if len(names) >= 2 and n >= 2:
+        for flip in (False, True):
+            m = {g: names[(g * 2 // n) ^ flip] if len(names) == 2 else names[g % len(names)] for g in range(n)}
+            r = run(list(range(n)), m)
+            print("all at once, split", m, {g: round(v, 1) for g, v in r.items()}, "sum", round(sum(r.values()), 1))
+    for k in (2, 4):
+        if n >= k:
+            r = run(list(range(k)), names[0])
+            print("first %d at once" % k, {g: round(v, 1) for g, v in r.items()})
+            r = run(list(range(n - k, n)), names[0])
+            print("last %d at once" % k, {g: round(v, 1) for g, v in r.items()})
 
 
 if __name__ == "__main__":
