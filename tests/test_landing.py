@@ -80,17 +80,21 @@ def test_mapped_output_recycles_pages_and_sizes_the_file_exactly():
     try:
         from pathlib import Path
         a = landing.acquire_mapped(Path(d) / "a.mp4", 1_000_003)
-        assert a is not None and not a.recycled and a.array.size == 1_000_003
-        a.array[:] = 7
+        # a NEW arena file is filled through its descriptor (no mapping yet), then mapped for the segments after it
+        assert a is not None and not a.recycled and a.array is None
+        os.pwrite(a.fd, b"\x07" * 1_000_003, 0)
+        a.populate()
         assert os.path.getsize(a.path) == 1_000_003 and a.path.read_bytes() == b"\x07" * 1_000_003
         b = landing.acquire_mapped(Path(d) / "b.mp4", 900_000)             # a.mp4 still exists: a second arena file
         assert b is not None and not b.recycled and b.slot is not a.slot
+        os.pwrite(b.fd, b"\x01" * 900_000, 0)
+        b.populate()
         os.unlink(a.path)                                                  # the consumer is done with a.mp4
         c = landing.acquire_mapped(Path(d) / "c.mp4", 1_100_000)           # a little larger: still fits the capacity
         assert c is not None and c.recycled and c.slot is a.slot
+        assert c.array is not None and c.array.size == 1_100_000
         c.array[:] = 9
         assert os.path.getsize(c.path) == 1_100_000 and c.path.read_bytes() == b"\x09" * 1_100_000
-        b.array[:] = 1
         assert b.path.read_bytes() == b"\x01" * 900_000                    # the other file is untouched by the reuse
         # replacing an existing name frees its arena file for the same call
         c2 = landing.acquire_mapped(c.path, 1_050_000)

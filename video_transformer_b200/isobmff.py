@@ -890,42 +890,55 @@ def write_plans(dst: str | Path, plans: list, mts: int, ftyp: bytes = b"", src_p
         raise BmffError("plans refer to a source file but none was given")
     src_size = os.path.getsize(src_path) if need_src else 0
     head = ftyp + moov + struct.pack(">I4sQ", 1, b"mdat", 16 + total_bytes)
+
+    def emit(out_fd: int) -> int:
+        pos = _write_all(out_fd, head, 0)
+        for i, (lo, ln) in enumerate(zip(src_lo, src_len)):
+            if lo < 0:
+                pos = _write_all(out_fd, over_at[i], pos)
+                continue
+            if lo + ln > src_size:
+                raise BmffError("sample data past the end of the file (truncated source)")
+            _copy_range(in_fd, out_fd, lo, pos, ln)
+            pos += ln
+        return pos
+
+    out = None
     if mapped:
         for lo, ln in zip(src_lo, src_len):
             if lo >= 0 and lo + ln > src_size:
                 raise BmffError("sample data past the end of the file (truncated source)")
         from . import landing
         out = landing.acquire_mapped(dst, len(head) + int(sum(src_len)))
-        if out is not None:
+    if out is not None and out.array is not None:         # recycled pages: plain stores
+        try:
+            view = _source_view(src_path) if need_src else None
+            a = out.array
+            a[:len(head)] = np.frombuffer(head, np.uint8)
+            pos = len(head)
+            for i, (lo, ln) in enumerate(zip(src_lo, src_len)):
+                a[pos:pos + ln] = np.frombuffer(over_at[i], np.uint8) if lo < 0 else view[lo:lo + ln]
+                pos += ln
+        except BaseException:
+            out.abort()
+            raise
+        return total_bytes
+    in_fd = os.open(src_path, os.O_RDONLY) if need_src else -1
+    try:
+        if out is not None:                                # a new arena file: in-kernel copy, then a warm mapping
             try:
-                view = _source_view(src_path) if need_src else None
-                a = out.array
-                a[:len(head)] = np.frombuffer(head, np.uint8)
-                pos = len(head)
-                for i, (lo, ln) in enumerate(zip(src_lo, src_len)):
-                    a[pos:pos + ln] = np.frombuffer(over_at[i], np.uint8) if lo < 0 else view[lo:lo + ln]
-                    pos += ln
+                emit(out.fd)
             except BaseException:
                 out.abort()
                 raise
+            out.populate()
             return total_bytes
-    # An existing output is overwritten IN PLACE and trimmed at the end: rewriting pages a file already owns is faster
-    # than allocating fresh ones (tmpfs on the GPU box: 5.1 vs 3.8 GB/s, tools/copy_probe.py), which matters when a
-    # segment is re-cut (retries, `ffmpeg -y` semantics).
-    in_fd = os.open(src_path, os.O_RDONLY) if need_src else -1
-    try:
+        # An existing output is overwritten IN PLACE and trimmed at the end: rewriting pages a file already owns is
+        # faster than allocating fresh ones (tmpfs on the GPU box: 5.1 vs 3.8 GB/s, tools/copy_probe.py), which
+        # matters when a segment is re-cut (retries, `ffmpeg -y` semantics).
         out_fd = os.open(dst, os.O_RDWR | os.O_CREAT, 0o644)
         try:
-            pos = _write_all(out_fd, head, 0)
-            for i, (lo, ln) in enumerate(zip(src_lo, src_len)):
-                if lo < 0:
-                    pos = _write_all(out_fd, over_at[i], pos)
-                    continue
-                if lo + ln > src_size:
-                    raise BmffError("sample data past the end of the file (truncated source)")
-                _copy_range(in_fd, out_fd, lo, pos, ln)
-                pos += ln
-            os.ftruncate(out_fd, pos)
+            os.ftruncate(out_fd, emit(out_fd))
         finally:
             os.close(out_fd)
     finally:

@@ -48,16 +48,20 @@ class _Slot:
                 rc = _libc.posix_fallocate(self.fd, 0, nbytes)
                 if rc != 0:
                     raise OSError(rc, "posix_fallocate(%d bytes) failed" % nbytes)
-            else:
-                os.ftruncate(self.fd, nbytes)     # pages arrive as they are first written
-            self.mm = mmap.mmap(self.fd, nbytes, flags=mmap.MAP_SHARED, prot=mmap.PROT_READ | mmap.PROT_WRITE)
+                self.mm = mmap.mmap(self.fd, nbytes, flags=mmap.MAP_SHARED, prot=mmap.PROT_READ | mmap.PROT_WRITE)
         except Exception:
             os.close(self.fd)
             os.unlink(path)
             raise
+        self.plain = not register
+        if self.plain:                 # an MP4 arena file: first filled through its descriptor, mapped afterwards
+            self.mm = self.array = self.tensor = None
+            self.base = 0
+            self.registered = False
+            self.stamp = 0
+            return
         self.array = np.frombuffer(self.mm, dtype=np.uint8)
         self.base = self.array.ctypes.data
-        self.plain = not register
         self.registered = register and lib().vt_host_register(ctypes.c_void_p(self.base), nbytes) == 0
         self.tensor = torch.from_numpy(self.array) if register else None
         self.stamp = 0
@@ -78,7 +82,8 @@ class _Slot:
         self.tensor = None
         self.array = None
         try:
-            self.mm.close()
+            if self.mm is not None:
+                self.mm.close()
         except (BufferError, ValueError):
             pass
         try:
@@ -258,11 +263,35 @@ def on_memory_fs(path: Path) -> bool:
 
 
 class MappedFile:
-    """An output file (a segment's MP4) written through a long-lived shared mapping: `array[:nbytes]` IS the file."""
+    """An output file (a segment's MP4) in the arena.  Recycled: `array[:nbytes]` IS the file (a long-lived shared
+    mapping whose pages exist).  New: `array` is None -- fill the file through `fd` (the in-kernel copy allocates
+    pages several times faster than first-touch faults through a mapping: 175 vs 279 ms for 220 MB in this container),
+    then call populate() so that the NEXT segment finds a warm mapping."""
 
     def __init__(self, path: Path, nbytes: int, slot: _Slot, recycled: bool):
         self.path, self.nbytes, self.slot, self.recycled = path, nbytes, slot, recycled
-        self.array = slot.array[:nbytes]
+        self.fd = slot.fd
+        self.array = slot.array[:nbytes] if slot.array is not None else None
+
+    def populate(self) -> None:
+        """Map the (filled) file over the slot's capacity and pre-fault the pages it has."""
+        s = self.slot
+        if s.mm is not None:
+            return
+        with _lock:
+            try:
+                os.ftruncate(s.fd, s.nbytes)
+                s.mm = mmap.mmap(s.fd, s.nbytes, flags=mmap.MAP_SHARED, prot=mmap.PROT_READ | mmap.PROT_WRITE)
+                os.ftruncate(s.fd, self.nbytes)
+                s.array = np.frombuffer(s.mm, dtype=np.uint8)
+            except (OSError, ValueError):
+                s.mm = s.array = None
+                os.ftruncate(s.fd, self.nbytes)
+                return
+        try:
+            s.mm.madvise(getattr(mmap, "MADV_POPULATE_WRITE", 23), 0, self.nbytes & ~(mmap.PAGESIZE - 1))
+        except (OSError, ValueError, AttributeError):
+            pass                                    # older kernels: the first recycled copy takes the faults instead
 
     def abort(self) -> None:
         try:
@@ -299,7 +328,8 @@ def acquire_mapped(path: str | Path, nbytes: int) -> MappedFile | None:
         arena = _arena_for(path.parent)
         slot = None
         for s in _slots:
-            if s.plain and s.path.parent == arena and nbytes <= s.nbytes <= 2 * nbytes + (64 << 20) and s.free() \
+            if s.plain and s.array is not None and s.path.parent == arena \
+                    and nbytes <= s.nbytes <= 2 * nbytes + (64 << 20) and s.free() \
                     and (slot is None or s.nbytes < slot.nbytes):
                 slot = s
         recycled = slot is not None
