@@ -551,24 +551,44 @@ def _run_ours(args, K, Wm, rank, world, local, cores, dev, store, L, barrier, wo
     clocks_e2e = sampler2.stop() if rank == 0 else None
     barrier()
 
-    # ---- concurrent D2H ceiling, measured in the same run: every rank copies 44 MB chunks into pinned memory at once --
+    # ---- concurrent D2H ceiling, measured in the same run: every rank copies 44 MB chunks into pinned memory for the
+    # same WINDOW of wall time (a fixed number of copies per rank would let the ranks on fast links finish first and
+    # the slow ones then measure an emptier box: at N=8 that overstated the slow links by a third) ---------------------
     chunk = 44 << 20
+    PROBE_S = 0.6
     d_src = torch.empty(chunk, dtype=torch.uint8, device=dev)
     h_dst = [torch.empty(chunk, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
     s_copy = torch.cuda.Stream(dev)
-    with torch.cuda.stream(s_copy):
-        for i in range(4):
-            h_dst[i % 2].copy_(d_src, non_blocking=True)
+
+    def d2h_window(seconds, each=None):
+        """Copy chunks device -> pinned host, two in flight, until `seconds` have passed; `each(i)` runs per copy.
+        Returns GB/s over the copies known complete at the last synchronisation inside the window."""
+        from collections import deque
+        with torch.cuda.stream(s_copy):
+            for i in range(2):
+                h_dst[i].copy_(d_src, non_blocking=True)
         s_copy.synchronize()
-        if world > 1:
-            dist.barrier()
-        tc = time.perf_counter()
-        reps = 24
-        for i in range(reps):
-            h_dst[i % 2].copy_(d_src, non_blocking=True)
+        barrier()
+        pending = deque()
+        n = done = 0
+        t0 = t_done = time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            with torch.cuda.stream(s_copy):
+                h_dst[n % 2].copy_(d_src, non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(s_copy)
+            if each is not None:
+                each(n)
+            pending.append(e)
+            n += 1
+            if len(pending) >= 2:
+                pending.popleft().synchronize()
+                done += 1
+                t_done = time.perf_counter()
         s_copy.synchronize()
-        ceil_gbs = reps * chunk / (time.perf_counter() - tc) / 1e9
-    del d_src, h_dst
+        return done * chunk / max(t_done - t0, 1e-9) / 1e9
+
+    ceil_gbs = d2h_window(PROBE_S)
     barrier()
     # ---- concurrent file-write ceiling of the box: every rank copies UNIT-sized byte ranges of the clip at once, the
     # way the product does (the MP4 half of extract_segment is a file -> file copy of the unit's samples: plain stores
@@ -593,19 +613,19 @@ def _run_ours(args, K, Wm, rank, world, local, cores, dev, store, L, barrier, wo
         while done < unit_bytes:
             done += os.copy_file_range(fi, fo, unit_bytes - done, done, done)
 
-    copy_once()
-    barrier()
-    tw = time.perf_counter()
-    for _ in range(3):
-        copy_once()
-    write_gbs = 3 * unit_bytes / (time.perf_counter() - tw) / 1e9
-    try:
-        copy_in_kernel()
+    def copy_window(fn, seconds):
+        fn()
         barrier()
         tw = time.perf_counter()
-        for _ in range(3):
-            copy_in_kernel()
-        kernel_copy_gbs = 3 * unit_bytes / (time.perf_counter() - tw) / 1e9
+        k = 0
+        while time.perf_counter() - tw < seconds:
+            fn()
+            k += 1
+        return k * unit_bytes / (time.perf_counter() - tw) / 1e9
+
+    write_gbs = copy_window(copy_once, 0.4)
+    try:
+        kernel_copy_gbs = copy_window(copy_in_kernel, 0.4)
     except (OSError, AttributeError):
         kernel_copy_gbs = 0.0
     os.close(fi)
@@ -616,40 +636,32 @@ def _run_ours(args, K, Wm, rank, world, local, cores, dev, store, L, barrier, wo
     # This is the platform's ceiling for THIS byte mix, with no kernels and no Python in the way.
     mix_ratio = bytes_per_picture_bs / float(fb + 1032)
     h2d_n = max(1 << 16, int(chunk * mix_ratio) & ~4095)
-    d_src = torch.empty(chunk, dtype=torch.uint8, device=dev)
-    h_dst = [torch.empty(chunk, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
     d_in = torch.empty(h2d_n, dtype=torch.uint8, device=dev)
     h_in = torch.empty(h2d_n, dtype=torch.uint8, pin_memory=True)
-    s_a, s_b = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    reps = 24
+    s_b = torch.cuda.Stream(dev)
     stop = threading.Event()
+    copied = [0]                                         # D2H chunks issued so far: the file copy keeps pace with them
 
     def copier():
-        off = 0
+        off = k = 0
         n_mix = min(h2d_n, unit_bytes)
-        for _ in range(reps):
-            if stop.is_set():
-                return
+        while not stop.is_set():
+            if k >= copied[0]:
+                time.sleep(0.0002)
+                continue
             lo = off % max(1, unit_bytes - n_mix)
             dst_map[:n_mix] = src_map[lo:lo + n_mix]
             off += n_mix
+            k += 1
 
-    for i in range(2):
-        with torch.cuda.stream(s_a):
-            h_dst[i].copy_(d_src, non_blocking=True)
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    th = threading.Thread(target=copier)
-    tm = time.perf_counter()
-    th.start()
-    for i in range(reps):
-        with torch.cuda.stream(s_a):
-            h_dst[i % 2].copy_(d_src, non_blocking=True)
+    def each(i):
         with torch.cuda.stream(s_b):
             d_in.copy_(h_in, non_blocking=True)
-    s_a.synchronize()
-    mixed_gbs = reps * chunk / (time.perf_counter() - tm) / 1e9
+        copied[0] = i + 1
+
+    th = threading.Thread(target=copier)
+    th.start()
+    mixed_gbs = d2h_window(PROBE_S, each)
     s_b.synchronize()
     stop.set()
     th.join()
@@ -657,7 +669,7 @@ def _run_ours(args, K, Wm, rank, world, local, cores, dev, store, L, barrier, wo
     probe_mm.close()
     os.close(fo)
     os.unlink(probe_out)
-    del d_src, h_dst, d_in, h_in
+    del d_src, h_dst, d_in, h_in, s_copy
     barrier()
 
     # ---- boundaries: shards pulled dynamically by all ranks, merged on rank 0, vs ONE single-GPU pass ---------------
@@ -793,7 +805,7 @@ def _run_ours(args, K, Wm, rank, world, local, cores, dev, store, L, barrier, wo
                         "e2e_of_ceiling": e2e_value / binding if binding else None,
                         "mixed_d2h_gbs_per_rank": [r["d2h_in_mix_gbs"] for r in ranks],
                         "mixed_frames_per_s": mixed_fps, "e2e_of_mixed": e2e_value / mixed_fps if mixed_fps else None,
-                        "note": "measured right after the timed arm, all ranks at once: (a) 44 MB chunks device -> pinned "
+                        "note": "measured right after the timed arm, all ranks at once over the same 0.6 s window: (a) 44 MB chunks device -> pinned "
                                 "host (a picture costs frame_bytes + 1032 B of D2H); (b) one unit's samples copied "
                                 "into an existing mapping of a /dev/shm file (the stream-copy half of the call, "
                                 "landing.acquire_mapped; per_rank.copy_file_range_gbs is the in-kernel copy beside it; "
