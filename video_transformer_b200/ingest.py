@@ -18,6 +18,7 @@ PyTorch only owns memory, streams and events here.
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import c_void_p
 from dataclasses import dataclass, field
 
@@ -150,7 +151,6 @@ class SegmentIngestor:
         self.slots = []
         self._pool_key = (str(self.dev), B, self.rows, self.pitch, self.frame_bytes, self.bs_cap, self.opts.sample_every > 1)
         pooled = _SLOT_POOL.get(self._pool_key) or []
-        import os
         self.n_slots = int(os.environ.get("VT_INGEST_SLOTS", "3"))   # batch i+1 is staged by a helper thread while i computes, i-1 copies out
         self.stage_thread = os.environ.get("VT_INGEST_THREAD", "1") == "1"
         for _ in range(self.n_slots):
@@ -194,7 +194,6 @@ class SegmentIngestor:
         VT_INGEST_DIRECT_H2D=0; files over VT_INGEST_DIRECT_MAX_GB (default 16) and file systems whose mappings cannot be
         pinned keep the staging path."""
         import mmap
-        import os
         if os.environ.get("VT_INGEST_DIRECT_H2D", "1") != "1" or self.dev.type != "cuda":
             return
         try:
@@ -304,6 +303,8 @@ class SegmentIngestor:
         if not (0 <= first < last <= n_total):
             raise ValueError("picture range [%d,%d) outside the stream (%d pictures)" % (first, last, n_total))
         L = lib()
+        import time as _time
+        host_t = [_time.perf_counter()]
         # lead-in: the score of picture `first` needs mafd of picture first-1, i.e. SAD(first-1, first-2), so
         # decoding starts at the keyframe that picture first-2 depends on ("decode 2 extra
         # lead-in frames per shard" instead of communicating)
@@ -367,9 +368,19 @@ class SegmentIngestor:
             from concurrent.futures import ThreadPoolExecutor
             self._pool = ThreadPoolExecutor(max_workers=1)
         staged = self._pool.submit(stage, 0) if (batches and self.stage_thread) else None
+        trace = [] if os.environ.get("VT_INGEST_TRACE") == "1" else None   # tools/trace_unit.py: per-batch stream timeline
+
+        def mark(stream):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            return e
+
+        host_t.append(_time.perf_counter())
         for i, (b0, b1) in enumerate(batches):
             slot = self.slots[i % self.n_slots]
             nb = b1 - b0
+            if i == 1:
+                host_t.append(_time.perf_counter())
             if self.stage_thread:
                 pay, nbytes = staged.result()
                 drain(slot)                  # host may only reuse pinned/device buffers whose copies completed
@@ -379,6 +390,8 @@ class SegmentIngestor:
                 drain(slot)
                 pay, nbytes = self._stage_bitstream(slot, b0, b1)
             with torch.cuda.stream(self.s_in):
+                if trace is not None:
+                    trace.append([mark(self.s_in)])
                 if nbytes:
                     if self._src_map is not None:
                         check(L.vt_copy_to_device_async(c_void_p(slot["bs_dev"].data_ptr()),
@@ -388,8 +401,12 @@ class SegmentIngestor:
                         slot["bs_dev"][:nbytes].copy_(slot["bs_host"][:nbytes], non_blocking=True)
                     self.h2d_bytes += nbytes
                 slot["ev_in"].record(self.s_in)
+                if trace is not None:
+                    trace[-1].append(mark(self.s_in))
             with torch.cuda.stream(self.s_cmp):
                 self.s_cmp.wait_event(slot["ev_in"])
+                if trace is not None:
+                    trace[-1].append(mark(self.s_cmp))
                 st = c_void_p(self.s_cmp.cuda_stream)
                 surf = slot["surf"]
                 prev_p = c_void_p(prev_surface.data_ptr()) if prev_surface is not None else None
@@ -441,9 +458,13 @@ class SegmentIngestor:
                     elif b1 > max(b0, first):
                         device_sink(slot["out"][max(b0, first) - b0:nb], max(b0, first))
                 slot["ev_cmp"].record(self.s_cmp)
+                if trace is not None:
+                    trace[-1].append(mark(self.s_cmp))
                 prev_surface = surf[nb - 1]
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(slot["ev_cmp"])
+                if trace is not None:
+                    trace[-1].append(mark(self.s_out))
                 lo = max(b0, first)
                 slot["land"] = None
                 cnt = row0 = 0
@@ -468,17 +489,25 @@ class SegmentIngestor:
                 slot["hist_host"][:nb].copy_(slot["hist"][:nb], non_blocking=True)
                 self.d2h_bytes += nb * (8 + 1024)
                 slot["ev_out"].record(self.s_out)
+                if trace is not None:
+                    trace[-1].append(mark(self.s_out))
             # drain() synchronises this slot's ev_out before the host issues batch i+2 into the same buffers,
             # which orders every device-side reuse (bitstream, surfaces, output) after the copies that read them
             slot["pending"] = (b0, b1)
             if land_staged and i >= 1:
                 drain(self.slots[(i - 1) % self.n_slots])    # hand batch i-1 to the writer while batch i runs
+        host_t.append(_time.perf_counter())
         for slot in sorted(self.slots, key=lambda sl: sl["pending"][0] if sl["pending"] else -1):
             drain(slot)                      # oldest batch first: the sink sees pictures in order
         for slot in self.slots:
             drain(slot)                      # writer futures of the last batches
         cur.wait_stream(self.s_cmp)
         cur.wait_stream(self.s_out)
+        host_t.append(_time.perf_counter())
+        self.last_host_ms = [round((t - host_t[0]) * 1e3, 3) for t in host_t]   # enter, loop, batch 1, drain, drained
+        if trace:
+            t0 = trace[0][0]
+            self.last_trace = [[t0.elapsed_time(e) for e in row] for row in trace]   # ms: h2d, cmp, d2h start/end
         if r0 == 0:
             sad_all[0] = 0                   # picture 0 has no predecessor
         scores = scene.scene_scores(sad_all, self.w, self.h)

@@ -266,7 +266,7 @@ def _cut(src: Path, start: float, end: float, dst: Path, stream_copy: bool) -> b
                 kwargs = {"stream_copy": True, "accurate_presentation": True, "selection": (first, last, first_acc)}
         # the stream copy (file -> file, inside the kernel) runs beside the GPU pass
         kwargs["mapped"] = bool(_OPTIONS["mapped_output"])
-        copier = _Background(isobmff.cut_movie, movie, start, end, dst, **kwargs)
+        copier = _Background(isobmff.cut_movie, movie, start, end, dst, delay=_copy_delay(), **kwargs)
     LAST_TIMINGS["index"] = time.perf_counter() - t_begin
     try:
         if _OPTIONS["frame_buffers"]:
@@ -293,10 +293,21 @@ def _cut(src: Path, start: float, end: float, dst: Path, stream_copy: bool) -> b
     return res is not None and res is not False
 
 
+def _copy_delay() -> float:
+    """Seconds the stream-copy thread waits before it starts.  Its first milliseconds are Python (sample tables, moov)
+    and hold the GIL exactly while the calling thread enqueues the first batches of the GPU pass: measured with
+    tools/trace_unit.py, the first H2D of a call started 1.4 ms late.  The copy needs 20-30 ms of a 50 ms pass, so it
+    can afford to start after the pipeline is primed."""
+    import os
+    if not _OPTIONS["frame_buffers"]:
+        return 0.0
+    return float(os.environ.get("VT_COPY_DELAY_MS", "3")) * 1e-3
+
+
 class _Background:
     """Runs one call on a helper thread; result() re-raises its exception."""
 
-    def __init__(self, fn, *args, **kwargs):
+    def __init__(self, fn, *args, delay: float = 0.0, **kwargs):
         import threading
         self._out = None
         self._exc = None
@@ -305,6 +316,8 @@ class _Background:
 
         def body():
             import time
+            if delay > 0:
+                time.sleep(delay)
             t0 = time.perf_counter()
             try:
                 self._out = fn(*args, **kwargs)
