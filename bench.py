@@ -891,6 +891,9 @@ def _run_config3(args, rank, world, local, dev, barrier, workdir, torch, dist, v
     rep = batch.ingest_batch_dynamic(vids, os.path.join(workdir, "temp"), rank=rank, world=world, on_done=consume)
     torch.cuda.synchronize(dev)
     last_call = {k: round(v * 1e3, 2) for k, v in video_segmenter.LAST_TIMINGS.items()}
+    eng_last = video_segmenter._ENGINE_CACHE.get("engine")
+    if eng_last is not None:
+        last_call["engine_setup"] = eng_last[1].setup_ms
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     cnt = torch.tensor([float(rep.pictures), float(rep.segments_done), float(len(rep.processed)), float(len(rep.failed))],
                        dtype=torch.float64, device=dev)

@@ -291,3 +291,28 @@ def test_pixel_pass_reads_a_matroska_source(cuda, oracle_c, tmp_path):
         assert np.array_equal(outs[0][1], outs[1][1])
     finally:
         video_segmenter.configure(**saved)
+
+
+def test_direct_and_staged_copy_in_deliver_the_same_pass(cuda, tmp_path, monkeypatch):
+    """The bitstream reaches the device either straight from a page-locked mapping of the source file (files of
+    VT_INGEST_DIRECT_MIN_MB and more) or through the pinned staging buffers (small files): same frames, same SADs."""
+    from video_transformer_b200 import ingest
+    w, h, n = 320, 240, 75
+    src, _meta = _clip(tmp_path, w, h, n, gop=10, cuts=[31], mp4=True)
+    idx = container.probe(src)
+    got = {}
+    for mode, min_mb in (("staged", "128"), ("direct", "0")):
+        monkeypatch.setenv("VT_INGEST_DIRECT_MIN_MB", min_mb)
+        eng = ingest.SegmentIngestor(idx, ingest.IngestOptions(target_height=120, batch_frames=16))
+        assert (eng._src_map is not None) == (mode == "direct"), mode
+        frames = np.zeros((n - 12, eng.frame_bytes), np.uint8)
+
+        def sink(chunk, first_picture, frames=frames):
+            frames[first_picture - 12:first_picture - 12 + chunk.shape[0]] = chunk.numpy()
+
+        res = eng.run(12, n, sink=sink)
+        got[mode] = (frames, res.sad.copy(), res.hist.copy(), res.cuts.copy())
+        eng.release()
+    for a, b in zip(got["staged"], got["direct"]):
+        assert np.array_equal(a, b)
+    assert got["direct"][0].any()

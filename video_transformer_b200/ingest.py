@@ -85,6 +85,8 @@ class SegmentIngestor:
     """Decode/score/scale engine for one indexed file on one GPU."""
 
     def __init__(self, index: StreamIndex, opts: IngestOptions | None = None, host_bytes: np.ndarray | None = None):
+        import time as _time
+        t_setup = [_time.perf_counter()]
         self.idx = index
         self.opts = opts or IngestOptions()
         self.dev = torch.device(self.opts.device)
@@ -112,6 +114,7 @@ class SegmentIngestor:
         else:
             check(L.vt_h264_pcm_layout(self.host.ctypes.data, self.host.size, offs.ctypes.data, sizes.ctypes.data, n,
                                        self.payload.ctypes.data))
+        t_setup.append(_time.perf_counter())
         self.offs, self.sizes = offs, sizes
         self.keyframes = np.nonzero(index.keyframe)[0].astype(np.int64)
         self.w, self.h = index.width, index.height
@@ -142,6 +145,7 @@ class SegmentIngestor:
         self.frame_bytes = self.out_w * self.out_h + 2 * ((self.out_w + 1) // 2) * ((self.out_h + 1) // 2)
         if self.rgb_plan is not None:
             self.frame_bytes = self.out_w * self.out_h * 3
+        t_setup.append(_time.perf_counter())
         B = self.opts.batch_frames
         self.B = B
         max_nal = int(sizes.max()) if n else 0
@@ -176,8 +180,13 @@ class SegmentIngestor:
                 "ev_in": torch.cuda.Event(), "ev_cmp": torch.cuda.Event(), "ev_out": torch.cuda.Event(),
                 "used": False, "pending": None, "kept": None, "land": None, "wfut": None,
             })
+        t_setup.append(_time.perf_counter())
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
+        t_setup.append(_time.perf_counter())
         self._register_source()
+        t_setup.append(_time.perf_counter())
+        self.setup_ms = dict(zip(("layout", "plans", "slots", "streams", "register_source"),
+                                 (round((b - a) * 1e3, 3) for a, b in zip(t_setup, t_setup[1:]))))
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self._pool = None
@@ -192,13 +201,16 @@ class SegmentIngestor:
         """Map the bitstream file privately and page-lock the mapping, so that the copy-in stream reads the page cache
         directly and the staging memcpy (one more pass over the host's memory per batch) disappears.  Off with
         VT_INGEST_DIRECT_H2D=0; files over VT_INGEST_DIRECT_MAX_GB (default 16) and file systems whose mappings cannot be
-        pinned keep the staging path."""
+        pinned keep the staging path -- and so do files under VT_INGEST_DIRECT_MIN_MB (default 128): page-locking costs
+        1-4 GB/s up front on this box (33 ms for a 34 MB clip, four times that clip's whole GPU pass), the staging copy
+        8 GB/s on a helper thread beside the GPU, so pinning only pays for files that are cut into many segments."""
         import mmap
         if os.environ.get("VT_INGEST_DIRECT_H2D", "1") != "1" or self.dev.type != "cuda":
             return
         try:
             size = os.path.getsize(self.idx.path)
-            if size == 0 or size > float(os.environ.get("VT_INGEST_DIRECT_MAX_GB", "16")) * (1 << 30):
+            if size == 0 or size > float(os.environ.get("VT_INGEST_DIRECT_MAX_GB", "16")) * (1 << 30) \
+                    or size < float(os.environ.get("VT_INGEST_DIRECT_MIN_MB", "128")) * (1 << 20):
                 return
             fd = os.open(self.idx.path, os.O_RDONLY)
             try:
