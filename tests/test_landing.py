@@ -103,3 +103,62 @@ def test_mapped_output_recycles_pages_and_sizes_the_file_exactly():
     finally:
         landing.release_all()
         shutil.rmtree(d, ignore_errors=True)
+
+
+def test_arena_never_evicts_outputs_that_still_exist(monkeypatch):
+    """At the cap only FREE arena files are released; while every file is an output somebody still holds, new outputs
+    are written the plain way instead of churning mappings."""
+    import shutil
+    from pathlib import Path
+    d = _shm_dir()
+    try:
+        monkeypatch.setenv("VT_MP4_ARENA_CAP_GB", str(50 / 1024))          # 50 MB: three 16 MB granules fit, four do not
+        outs = []
+        for k in range(3):
+            m = landing.acquire_mapped(Path(d) / ("seg_%d.mp4" % k), 10 << 20)
+            assert m is not None
+            os.pwrite(m.fd, bytes([k + 1]) * (10 << 20), 0)
+            m.populate()
+            outs.append(m)
+        assert landing.acquire_mapped(Path(d) / "seg_3.mp4", 10 << 20) is None      # all three files are still held
+        assert all(o.path.read_bytes() == bytes([k + 1]) * (10 << 20) for k, o in enumerate(outs))
+        os.unlink(outs[0].path)                                                      # the consumer lets one go
+        m = landing.acquire_mapped(Path(d) / "seg_3.mp4", 10 << 20)
+        assert m is not None and m.recycled and m.slot is outs[0].slot
+        os.unlink(m.path)
+        os.unlink(outs[1].path)
+        big = landing.acquire_mapped(Path(d) / "big.mp4", 17 << 20)                  # needs 32 MB: both free files go
+        assert big is not None and not big.recycled and landing.stats()["mapped_files"] == 2
+        assert outs[2].path.read_bytes() == bytes([3]) * (10 << 20)
+    finally:
+        landing.release_all()
+        shutil.rmtree(d, ignore_errors=True)
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_registered_arena_falls_back_to_the_staged_writer_at_its_cap(cuda, monkeypatch):
+    """A consumer that keeps every `.frames` must not make each new segment pay for un-registering an old file and
+    registering a new one: at the cap, with nothing free, the landing is the staged writer."""
+    import shutil
+    from pathlib import Path
+    d = _shm_dir()
+    try:
+        monkeypatch.setenv("VT_LANDING_CAP_GB", str(3 / 1024))
+        a = landing.acquire(Path(d) / "a.frames", 2 << 20)
+        if not a.direct:
+            pytest.skip("mappings of this file system cannot be registered")
+        a.finish()
+        b = landing.acquire(Path(d) / "b.frames", 2 << 20)                  # a.frames still exists, 2 + 2 > 3 MB
+        assert not b.direct
+        b.abort()
+        assert os.path.getsize(a.path) == 2 << 20
+        os.unlink(a.path)
+        c = landing.acquire(Path(d) / "c.frames", 2 << 20)
+        assert c.direct and c.recycled and c.slot is a.slot
+        c.finish()
+    finally:
+        landing.release_all()
+        shutil.rmtree(d, ignore_errors=True)

@@ -171,56 +171,71 @@ def acquire(path: str | Path, nbytes: int, direct: bool | None = None) -> Landin
         raise ValueError("landing size must be positive")
     if direct is None:
         direct = os.environ.get("VT_LANDING", "direct") != "staged"
+    slot = None
+    room = False
     with _lock:
         if path.exists() or path.is_symlink():
             path.unlink()                       # a replaced artefact frees its arena file for the search below
         if direct:
             arena = _arena_for(path.parent)
-            slot = None
             for s in _slots:
                 if s.nbytes == nbytes and not s.plain and s.path.parent == arena and s.free():
                     slot = s
                     break
-            recycled = slot is not None
-            if slot is None:
-                # over the cap: release the oldest files, free ones first (busy ones keep their `.frames` name)
-                _make_room(nbytes, False, _arena_cap())
-                try:
-                    arena.mkdir(exist_ok=True)
-                    _seq += 1
-                    slot = _Slot(arena / ("landing_%d_%d.bin" % (os.getpid(), _seq)), nbytes)
-                    if not slot.registered:
-                        slot.destroy()
-                        slot = None
-                except OSError:
-                    slot = None
             if slot is not None:
                 try:
                     os.link(slot.path, path)
                 except OSError:
                     slot.destroy()
+                    _slots.remove(slot)
                     slot = None
                 else:
                     _seq += 1
                     slot.stamp = _seq
-                    if not recycled:
-                        _slots.append(slot)
-                    return Landing(path, nbytes, slot, recycled)
-            if direct is True and os.environ.get("VT_LANDING") == "direct-only":
-                raise OSError("cannot register a mapping of %s" % path)
-        return Landing(path, nbytes, None, False)
+                    return Landing(path, nbytes, slot, True)
+            # Nothing to recycle.  A new registered file is worth its price (allocate + page-lock, ~3 GB/s) only while
+            # the arena has room: FREE files are released to make it, files whose `.frames` name still exists are not
+            # -- a consumer that keeps every output would otherwise make each segment pay for a registration AND an
+            # un-registration (64 kept 415 MB clips: 1.1 s per clip), where the staged writer costs 0.1 s.
+            room = _make_room(nbytes, False, _arena_cap())
+            _seq += 1
+            name = arena / ("landing_%d_%d.bin" % (os.getpid(), _seq))
+    if direct and room:                         # the slow part runs outside the lock (the MP4 writer takes it too)
+        try:
+            arena.mkdir(exist_ok=True)
+            slot = _Slot(name, nbytes)
+            if not slot.registered:
+                slot.destroy()
+                slot = None
+            else:
+                os.link(slot.path, path)
+        except OSError:
+            if slot is not None:
+                slot.destroy()
+            slot = None
+        if slot is not None:
+            with _lock:
+                _seq += 1
+                slot.stamp = _seq
+                _slots.append(slot)
+            return Landing(path, nbytes, slot, False)
+    if direct is True and os.environ.get("VT_LANDING") == "direct-only":
+        raise OSError("cannot register a mapping of %s" % path)
+    return Landing(path, nbytes, None, False)
 
 
-def _make_room(nbytes: int, plain: bool, cap: int) -> None:
-    """Release the oldest arena files of one kind until nbytes more fit under cap (free ones first)."""
+def _make_room(nbytes: int, plain: bool, cap: int) -> bool:
+    """Release the oldest FREE arena files of one kind until nbytes more fit under cap; False if they still do not
+    (the rest are outputs somebody still holds: they stay as they are)."""
     mine = [s for s in _slots if s.plain == plain]
     used = sum(s.nbytes for s in mine)
-    for s in sorted(mine, key=lambda s: (not s.free(), s.stamp)):
+    for s in sorted((s for s in mine if s.free()), key=lambda s: s.stamp):
         if used + nbytes <= cap:
             break
         s.destroy()
         _slots.remove(s)
         used -= s.nbytes
+    return used + nbytes <= cap
 
 
 def _arena_for(parent: Path) -> Path:
@@ -336,7 +351,8 @@ def acquire_mapped(path: str | Path, nbytes: int) -> MappedFile | None:
         try:
             if slot is None:
                 cap = -(-(nbytes + nbytes // 8) // (16 << 20)) * (16 << 20)
-                _make_room(cap, True, _mapped_cap())
+                if not _make_room(cap, True, _mapped_cap()):
+                    return None                 # every arena file is an output somebody still holds: plain copy
                 arena.mkdir(exist_ok=True)
                 _seq += 1
                 slot = _Slot(arena / ("landing_%d_%d.bin" % (os.getpid(), _seq)), cap, register=False)
