@@ -294,7 +294,7 @@ class SegmentIngestor:
         se = self.opts.sample_every
         return last - first if se == 1 else len(range(-(-first // se) * se, last, se))
 
-    def run(self, first: int, last: int, sink=None, device_sink=None, landing=None) -> IngestResult:
+    def run(self, first: int, last: int, sink=None, device_sink=None, landing=None, on_primed=None) -> IngestResult:
         """Process pictures [first, last).  Output frames go to sink(chunk_host_tensor, first_picture).
 
         landing (landing.Landing), if given, is the `.frames` file of the segment: with a registered mapping the copy
@@ -306,12 +306,20 @@ class SegmentIngestor:
         it is called with the compute stream current, right after the kernels that produce the chunk were enqueued,
         so whatever it enqueues on the current stream is ordered after them and before the buffers are reused; the
         frames are then not copied to the host at all (scores still are).  This is the hand-off for a consumer that
-        lives on the GPU (the model's own input pipeline): the D2H copy is what bounds the host-buffer path."""
-        n_total = self.idx.n_frames
-        with torch.cuda.device(self.dev):
-            return self._run(first, last, sink, device_sink, landing, n_total)
+        lives on the GPU (the model's own input pipeline): the D2H copy is what bounds the host-buffer path.
 
-    def _run(self, first, last, sink, device_sink, landing, n_total) -> IngestResult:
+        on_primed(), if given, is called once the pipeline is full (one batch enqueued per slot) or the pass has nothing
+        more to enqueue: the moment from which this thread mostly sleeps on events and other Python threads of the
+        caller (the stream copy) can have the interpreter without delaying the GPU."""
+        n_total = self.idx.n_frames
+        try:
+            with torch.cuda.device(self.dev):
+                return self._run(first, last, sink, device_sink, landing, n_total, on_primed)
+        finally:
+            if on_primed is not None:
+                on_primed()
+
+    def _run(self, first, last, sink, device_sink, landing, n_total, on_primed=None) -> IngestResult:
         if not (0 <= first < last <= n_total):
             raise ValueError("picture range [%d,%d) outside the stream (%d pictures)" % (first, last, n_total))
         L = lib()
@@ -506,6 +514,8 @@ class SegmentIngestor:
             # drain() synchronises this slot's ev_out before the host issues batch i+2 into the same buffers,
             # which orders every device-side reuse (bitstream, surfaces, output) after the copies that read them
             slot["pending"] = (b0, b1)
+            if on_primed is not None and i == self.n_slots - 1:
+                on_primed()
             if land_staged and i >= 1:
                 drain(self.slots[(i - 1) % self.n_slots])    # hand batch i-1 to the writer while batch i runs
         host_t.append(_time.perf_counter())

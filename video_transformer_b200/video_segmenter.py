@@ -238,6 +238,7 @@ def _cut(src: Path, start: float, end: float, dst: Path, stream_copy: bool) -> b
                 return False                 # a mid-GOP start needs an encoder unless pictures merely repeat the IDR
             samples[0] = data[int(idx.nal_offsets[k]):int(idx.nal_offsets[k]) + int(idx.nal_sizes[k])]
             keys[0] = True
+        gate = None
         container.write_mp4(dst, sps=sps, pps=pps, samples=samples, width=idx.width, height=idx.height,
                             fps_num=idx.fps_num, fps_den=idx.fps_den, keyframes=keys)
         copier = None
@@ -266,7 +267,8 @@ def _cut(src: Path, start: float, end: float, dst: Path, stream_copy: bool) -> b
                 kwargs = {"stream_copy": True, "accurate_presentation": True, "selection": (first, last, first_acc)}
         # the stream copy (file -> file, inside the kernel) runs beside the GPU pass
         kwargs["mapped"] = bool(_OPTIONS["mapped_output"])
-        copier = _Background(isobmff.cut_movie, movie, start, end, dst, delay=_copy_delay(), **kwargs)
+        gate = _copy_gate()
+        copier = _Background(isobmff.cut_movie, movie, start, end, dst, gate=gate, **kwargs)
     LAST_TIMINGS["index"] = time.perf_counter() - t_begin
     try:
         if _OPTIONS["frame_buffers"]:
@@ -278,12 +280,14 @@ def _cut(src: Path, start: float, end: float, dst: Path, stream_copy: bool) -> b
                 reason = ("H.264 stream uses coding tools outside the PCM-intra subset K0 decodes; NVDEC is not "
                           "available on this host")
             if reason is None:
-                _ingest_to_files(idx, first, last, dst, snapped)
+                _ingest_to_files(idx, first, last, dst, snapped, gate.set if gate is not None else None)
             else:                               # the stream copy needs no decode: the cut stands, the pixel pass is skipped
                 _write_sidecar(dst, idx, first, last, None, reason)
                 log.info("event=segment_pixel_pass_skipped reason=%s", reason)
     finally:
         t_pix = time.perf_counter()
+        if gate is not None:
+            gate.set()
         res = copier.result() if copier is not None else True
         LAST_TIMINGS["pixel_pass"] = t_pix - t_begin - LAST_TIMINGS["index"]
         LAST_TIMINGS["wait_for_stream_copy"] = time.perf_counter() - t_pix
@@ -293,21 +297,23 @@ def _cut(src: Path, start: float, end: float, dst: Path, stream_copy: bool) -> b
     return res is not None and res is not False
 
 
-def _copy_delay() -> float:
-    """Seconds the stream-copy thread waits before it starts.  Its first milliseconds are Python (sample tables, moov)
-    and hold the GIL exactly while the calling thread enqueues the first batches of the GPU pass: measured with
-    tools/trace_unit.py, the first H2D of a call started 1.4 ms late.  The copy needs 20-30 ms of a 50 ms pass, so it
-    can afford to start after the pipeline is primed."""
+def _copy_gate():
+    """Event the stream-copy thread waits for before it starts (None: start at once).  Its first milliseconds are Python
+    (sample tables, moov) and hold the GIL exactly while the calling thread enqueues the first batches of the GPU pass:
+    measured with tools/trace_unit.py, the first H2D of a call started 1.4-2.6 ms late and the D2H engine idled that
+    long.  The ingest sets the event once its pipeline is full (SegmentIngestor.run(on_primed=...)); from then on the
+    calling thread sleeps on CUDA events most of the time."""
     import os
-    if not _OPTIONS["frame_buffers"]:
-        return 0.0
-    return float(os.environ.get("VT_COPY_DELAY_MS", "3")) * 1e-3
+    import threading
+    if not _OPTIONS["frame_buffers"] or os.environ.get("VT_COPY_GATE", "1") == "0":
+        return None
+    return threading.Event()
 
 
 class _Background:
     """Runs one call on a helper thread; result() re-raises its exception."""
 
-    def __init__(self, fn, *args, delay: float = 0.0, **kwargs):
+    def __init__(self, fn, *args, gate=None, **kwargs):
         import threading
         self._out = None
         self._exc = None
@@ -316,8 +322,8 @@ class _Background:
 
         def body():
             import time
-            if delay > 0:
-                time.sleep(delay)
+            if gate is not None:
+                gate.wait(0.05)                 # never longer than 50 ms: the copy must not depend on the pixel pass
             t0 = time.perf_counter()
             try:
                 self._out = fn(*args, **kwargs)
@@ -393,7 +399,7 @@ def _snap_window(idx, times: np.ndarray, start: float, end: float, tol: float):
     return out
 
 
-def _ingest_to_files(idx, first: int, last: int, dst: Path, snapped=None) -> None:
+def _ingest_to_files(idx, first: int, last: int, dst: Path, snapped=None, on_primed=None) -> None:
     """GPU pass for pictures [first,last): writes <dst>.frames and <dst>.json.  Raises on any failure."""
     import time
     from . import landing
@@ -406,7 +412,7 @@ def _ingest_to_files(idx, first: int, last: int, dst: Path, snapped=None) -> Non
     LAST_TIMINGS["engine"] = t1 - t0
     LAST_TIMINGS["landing_acquire"] = t2 - t1
     try:
-        res = eng.run(first, last, landing=land)
+        res = eng.run(first, last, landing=land, on_primed=on_primed)
         land.finish(res.stats["landed_frames"] * eng.frame_bytes)
         LAST_TIMINGS["gpu_pass"] = time.perf_counter() - t2
     except BaseException:
