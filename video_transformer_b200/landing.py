@@ -226,7 +226,9 @@ def acquire(path: str | Path, nbytes: int, direct: bool | None = None) -> Landin
 
 def _make_room(nbytes: int, plain: bool, cap: int) -> bool:
     """Release the oldest FREE arena files of one kind until nbytes more fit under cap; False if they still do not
-    (the rest are outputs somebody still holds: they stay as they are)."""
+    (the rest are outputs somebody still holds: they stay as they are).  One file larger than the whole cap is allowed
+    when it would be the only one: a 720 s segment of 720p frames is 30 GB, and recycling that file is worth far more
+    than any number of small ones."""
     mine = [s for s in _slots if s.plain == plain]
     used = sum(s.nbytes for s in mine)
     for s in sorted((s for s in mine if s.free()), key=lambda s: s.stamp):
@@ -235,7 +237,7 @@ def _make_room(nbytes: int, plain: bool, cap: int) -> bool:
         s.destroy()
         _slots.remove(s)
         used -= s.nbytes
-    return used + nbytes <= cap
+    return used + nbytes <= cap or used == 0
 
 
 def _arena_for(parent: Path) -> Path:
