@@ -256,8 +256,23 @@ def _arena_for(parent: Path) -> Path:
 _MEMORY_FS_MAGIC = {0x01021994, 0x858458F6}     # tmpfs, ramfs (statfs f_type)
 
 
+_memory_fs_of_device: dict = {}
+
+
 def on_memory_fs(path: Path) -> bool:
-    """True when `path` lives on a RAM-backed file system (statfs f_type; /proc/self/mounts as the second opinion)."""
+    """True when `path` lives on a RAM-backed file system (statfs f_type; /proc/self/mounts as the second opinion).
+    The answer is kept per st_dev."""
+    try:
+        dev_id = os.stat(path).st_dev
+    except OSError:
+        return False
+    hit = _memory_fs_of_device.get(dev_id)
+    if hit is None:
+        hit = _memory_fs_of_device[dev_id] = _probe_memory_fs(path)
+    return hit
+
+
+def _probe_memory_fs(path: Path) -> bool:
     buf = ctypes.create_string_buffer(256)
     try:
         if _libc.statfs(os.fsencode(str(path)), buf) == 0:
