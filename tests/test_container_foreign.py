@@ -460,3 +460,97 @@ def test_mapped_and_in_kernel_copies_write_the_same_file(tmp_path):
     finally:
         landing.release_all()
         shutil.rmtree(shm, ignore_errors=True)
+
+
+def test_uncompressed_audio_with_millions_of_frames_is_handled_in_groups(tmp_path, monkeypatch):
+    """A PCM track has one sample per audio frame (two hours at 48 kHz: 345 million).  Large uniform tracks are read as
+    groups of frames inside their chunks; the cut still carries a true per-frame table (fixed-size stsz, one stts run),
+    byte-identical audio, and starts its presentation on the same frame as the per-sample path."""
+    w, h, n, gop, fps = 96, 80, 120, 12, 30
+    sps, pps, samples, keys, _ = _pcm_samples(w, h, n, gop)
+    rate = 48000
+    t = np.arange(n * rate // fps)
+    pcm = np.stack([(t % 32749).astype(np.int16), (-(t % 1021)).astype(np.int16)], 1)
+    src = tmp_path / "src.mp4"
+    meta = write_av_mp4(src, sps=sps, pps=pps, video_samples=samples, keyframes=keys, width=w, height=h,
+                        timescale=fps * 512, delta=512, audio_pcm=pcm, audio_rate=rate, audio_chunk=1500)
+    bpf = meta["bytes_per_audio_frame"]
+    exact = isobmff.read_movie(src)
+    assert exact.tracks[1].unit is None and exact.tracks[1].n == t.size
+    monkeypatch.setattr(isobmff, "UNIFORM_MIN_SAMPLES", 1000)
+    monkeypatch.setattr(isobmff, "UNIFORM_GROUP", 256)
+    grouped = isobmff.read_movie(src)
+    a = grouped.tracks[1]
+    assert a.unit == (bpf, 1) and a.n == -(-1500 // 256) * (t.size // 1500) and int(a.sizes.sum()) == t.size * bpf
+    assert int(a.deltas.sum()) == t.size and a.sync.all() and a.cts_off is None
+    data = src.read_bytes()
+    assert b"".join(data[int(o):int(o) + int(z)] for o, z in zip(a.offsets, a.sizes)) == meta["audio_bytes"]
+    assert abs(grouped.duration_seconds() - exact.duration_seconds()) < 1e-9
+    start, end = 1.25, 3.0
+    out_g, out_e = tmp_path / "grouped.mp4", tmp_path / "exact.mp4"
+    r_g = isobmff.cut_movie(grouped, start, end, out_g)
+    r_e = isobmff.cut_movie(exact, start, end, out_e)
+    assert (r_g.first, r_g.last) == (r_e.first, r_e.last)
+    monkeypatch.undo()                                    # read both outputs sample by sample
+    cut_g, cut_e = isobmff.read_movie(out_g), isobmff.read_movie(out_e)
+    ag, ae = cut_g.tracks[1], cut_e.tracks[1]
+    assert ag.stsd == ae.stsd == exact.tracks[1].stsd and ag.unit is None
+    assert (ag.sizes == bpf).all() and (ag.deltas == 1).all()
+    # the grouped cut holds whole groups: a few more frames on either side, the same frames in between
+    t_lo, t_hi = r_e.first / fps, r_e.last / fps
+    a0, a1 = int(np.floor(t_lo * rate + 1e-9)), int(np.ceil(t_hi * rate - 1e-9))
+    assert ae.n == a1 - a0
+    g_lo = (a0 // 1500) * 1500 + ((a0 % 1500) // 256) * 256
+    g_hi = min(((a1 - 1) // 1500) * 1500 + (((a1 - 1) % 1500) // 256 + 1) * 256, ((a1 - 1) // 1500 + 1) * 1500)
+    assert ag.n == g_hi - g_lo and g_lo <= a0 and g_hi >= a1
+    dg = out_g.read_bytes()
+    offs, sizes = ag.offsets.astype(np.int64), ag.sizes.astype(np.int64)
+    brk = np.nonzero(offs[1:] != offs[:-1] + sizes[:-1])[0] + 1
+    got = b"".join(dg[offs[s_]:offs[e_ - 1] + sizes[e_ - 1]]
+                   for s_, e_ in zip(np.concatenate(([0], brk)), np.concatenate((brk, [offs.size]))))
+    assert got == meta["audio_bytes"][g_lo * bpf:g_hi * bpf]
+    # presentation: both edit lists start the audio on the same source frame (the video's first picture)
+    assert ag.edit_shift(cut_g.timescale)[1] + g_lo == ae.edit_shift(cut_e.timescale)[1] + a0
+    assert abs(probe_duration(out_g) - probe_duration(out_e)) < 2e-3
+    cap = cv2.VideoCapture(str(out_g), cv2.CAP_FFMPEG)
+    k = 0
+    while cap.read()[0]:
+        k += 1
+    assert k == r_g.last - r_g.first
+
+
+def test_corrupt_run_lengths_do_not_allocate_the_world(tmp_path):
+    """A flipped byte in a stts/ctts/stsc run length (0xCE000000 samples ...) must not expand into gigabytes: tables are
+    expanded up to the track's sample count only, and a sample count beyond the limit is refused."""
+    import time
+    import torch  # noqa: F401  (imported lazily by the cut path: keep its seconds out of the timings below)
+    w, h, n, gop = 64, 48, 40, 8
+    sps, pps, samples, keys, _ = _pcm_samples(w, h, n, gop)
+    src = tmp_path / "src.mp4"
+    write_av_mp4(src, sps=sps, pps=pps, video_samples=samples, keyframes=keys, width=w, height=h, timescale=30 * 512,
+                 delta=512, ctts=[512] * n, video_media_time=512)
+    good = src.read_bytes()
+    video_segmenter.configure(frame_buffers=False)
+    video_segmenter.extract_segment(src, 0.2, 1.0, tmp_path / "warm.mp4")
+    for tag in (b"stts", b"ctts", b"stsc"):
+        at = good.find(tag)
+        assert at > 0
+        bad = bytearray(good)
+        first_count = at + 4 + 4 + 4 + (4 if tag == b"stsc" else 0)       # version/flags, entry count, [first_chunk]
+        bad[first_count] = 0xCE
+        f = tmp_path / ("bad_%s.mp4" % tag.decode())
+        f.write_bytes(bytes(bad))
+        t0 = time.perf_counter()
+        assert isinstance(probe_duration(f), float)
+        video_segmenter.configure(frame_buffers=False)
+        assert video_segmenter.extract_segment(f, 0.2, 1.0, tmp_path / "o.mp4") in (True, False)
+        assert time.perf_counter() - t0 < 2.0, tag
+    at = good.find(b"stsz")
+    bad = bytearray(good)
+    bad[at + 8:at + 16] = struct.pack(">II", 4, 0xFFFFFFF0)                # fixed size, four billion samples
+    f = tmp_path / "bad_stsz.mp4"
+    f.write_bytes(bytes(bad))
+    t0 = time.perf_counter()
+    assert isinstance(probe_duration(f), float)
+    assert video_segmenter.extract_segment(f, 0.2, 1.0, tmp_path / "o2.mp4") is False
+    assert time.perf_counter() - t0 < 2.0

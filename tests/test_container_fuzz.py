@@ -1,0 +1,63 @@
+"""Mutated inputs: the reference's probe_duration returns 0.0 on every failure (src/utils/video_utils.py:28-38) and its
+extract_segment never raises (src/utils/video_segmenter.py:93-115) -- ffprobe/ffmpeg exit with an error and the wrapper
+turns that into 0.0 / False.  The container layer here parses downloaded files itself, so the same must hold for files
+that are truncated, bit-flipped or carry absurd counts: no exception escapes, and no call takes seconds (run lengths
+and sample counts come from the file)."""
+import struct
+import time
+
+import numpy as np
+import pytest
+
+from mp4_fixture import write_av_mp4, write_fragmented_av, write_mkv
+from test_container_foreign import _pcm_samples
+from video_transformer_b200 import video_segmenter
+from video_transformer_b200.video_utils import probe_duration
+
+
+def _sources(tmp_path):
+    w, h, n, gop, fps = 64, 48, 40, 8, 30
+    sps, pps, samples, keys, _ = _pcm_samples(w, h, n, gop)
+    t = np.arange(n * 48000 // fps)
+    pcm = np.stack([(t % 311).astype(np.int16), (t % 1000).astype(np.int16)], 1)
+    plain = tmp_path / "plain.mp4"
+    write_av_mp4(plain, sps=sps, pps=pps, video_samples=samples, keyframes=keys, width=w, height=h, timescale=fps * 512,
+                 delta=512, audio_pcm=pcm, audio_rate=48000, ctts=[512] * n, video_media_time=512, moov_first=True)
+    frag = tmp_path / "frag.mp4"
+    write_fragmented_av(frag, sps=sps, pps=pps, video_samples=samples, keyframes=keys, width=w, height=h)
+    mkv = tmp_path / "src.mkv"
+    write_mkv(mkv, sps=sps, pps=pps, video_samples=samples, keyframes=keys, width=w, height=h, fps=fps,
+              opus_packets=[bytes([i % 251]) * 40 for i in range(70)])
+    return plain, frag, mkv
+
+
+@pytest.mark.parametrize("which", [0, 1, 2])
+def test_mutated_files_never_raise_and_never_stall(tmp_path, which):
+    import torch  # noqa: F401  (lazily imported by the cut path; keep it out of the per-call timings)
+    src = _sources(tmp_path)[which]
+    good = src.read_bytes()
+    head = min(len(good), 4096)                           # where the metadata of these files lives
+    rng = np.random.default_rng(1234 + which)
+    video_segmenter.configure(frame_buffers=False)
+    assert probe_duration(src) > 1.0 and video_segmenter.extract_segment(src, 0.2, 1.0, tmp_path / "ok.mp4") is True
+    f = tmp_path / ("mutant" + src.suffix)
+    for it in range(150):
+        b = bytearray(good)
+        mode = it % 4
+        if mode == 0:                                     # flipped bytes in the metadata
+            for _ in range(int(rng.integers(1, 6))):
+                b[int(rng.integers(0, head))] = int(rng.integers(0, 256))
+        elif mode == 1:                                   # truncated download
+            b = b[:int(rng.integers(8, len(b)))]
+        elif mode == 2:                                   # an absurd 32-bit count or size
+            p = int(rng.integers(0, head - 4))
+            b[p:p + 4] = struct.pack(">I", int(rng.choice([0, 1, 0x7FFFFFFF, 0xFFFFFFFF, 0x80000000, 0xCE000000])))
+        else:                                             # noise anywhere
+            for _ in range(int(rng.integers(1, 20))):
+                b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        f.write_bytes(bytes(b))
+        t0 = time.perf_counter()
+        d = probe_duration(f)
+        ok = video_segmenter.extract_segment(f, 0.2, 1.0, tmp_path / "out.mp4")
+        assert isinstance(d, float) and d >= 0.0 and ok in (True, False), (which, it)
+        assert time.perf_counter() - t0 < 2.0, (which, it, mode)

@@ -123,6 +123,8 @@ class Track:
     has_stss: bool
     edits: list                     # [(segment_duration (movie ts), media_time, rate_16_16)]
     entry_payload: tuple = (0, 0)   # (start, end) of the first sample entry's payload inside `stsd`
+    unit: tuple | None = None       # (bytes, duration) of ONE sample when the arrays above describe GROUPS of equal
+                                    # samples (uniform tracks with millions of samples, e.g. PCM audio: see _parse_track)
 
     @property
     def n(self) -> int:
@@ -189,6 +191,20 @@ def _be(buf, dtype, count, offset):
     return np.frombuffer(buf, dtype, count, offset)
 
 
+MAX_TRACK_SAMPLES = 1 << 25      # per-sample tables beyond this are refused (a corrupt count must not allocate gigabytes)
+UNIFORM_MIN_SAMPLES = 1 << 21    # uniform tracks (one size, one duration, every sample sync) larger than this are grouped
+UNIFORM_GROUP = 1024             # ... into runs of at most this many samples inside a chunk (libavformat's PCM packets)
+
+
+def _expand_runs(values: np.ndarray, counts: np.ndarray, n: int) -> np.ndarray:
+    """np.repeat(values, counts) cut off at n elements WITHOUT materialising more: counts come from the file and a
+    corrupt run length (0xCE000000 ...) would otherwise allocate and fill gigabytes before the result is trimmed."""
+    c = np.clip(np.asarray(counts, np.int64), 0, max(n, 0))
+    before = np.cumsum(c) - c
+    c = np.clip(n - before, 0, c)
+    return np.repeat(values, c)
+
+
 def _parse_track(moov: bytes, s: int, e: int) -> Track | None:
     tkhd = find_box(moov, s, e, b"tkhd")
     mdia = find_box(moov, s, e, b"mdia")
@@ -249,14 +265,22 @@ def _parse_track(moov: bytes, s: int, e: int) -> Track | None:
         if handler == b"vide" and sd_s + 8 + 36 <= sd_e:
             width, height = struct.unpack_from(">HH", moov, sd_s + 8 + 8 + 24)
     # sample sizes
+    uniform = None
     if b"stsz" in tabs:
         zs = tabs[b"stsz"][0]
         fixed, n = struct.unpack_from(">II", moov, zs + 4)
-        sizes = np.full(n, fixed, np.uint64) if fixed else _be(moov, ">u4", n, zs + 12).astype(np.uint64)
+        if fixed and n > UNIFORM_MIN_SAMPLES:
+            uniform = _uniform_track(moov, tabs, int(fixed), int(n))
+        if uniform is None:
+            if n > MAX_TRACK_SAMPLES:
+                raise BmffError("track with %d samples (limit %d)" % (n, MAX_TRACK_SAMPLES))
+            sizes = np.full(n, fixed, np.uint64) if fixed else _be(moov, ">u4", n, zs + 12).astype(np.uint64)
     elif b"stz2" in tabs:
         zs = tabs[b"stz2"][0]
         fsize = moov[zs + 7]
         n = struct.unpack_from(">I", moov, zs + 8)[0]
+        if n > MAX_TRACK_SAMPLES:
+            raise BmffError("track with %d samples (limit %d)" % (n, MAX_TRACK_SAMPLES))
         if fsize == 16:
             sizes = _be(moov, ">u2", n, zs + 12).astype(np.uint64)
         elif fsize == 8:
@@ -268,6 +292,13 @@ def _parse_track(moov: bytes, s: int, e: int) -> Track | None:
             raise BmffError("stz2 field size %d" % fsize)
     else:
         sizes = np.zeros(0, np.uint64)
+    if uniform is not None:
+        sizes, offsets, deltas, unit = uniform
+        n = int(sizes.size)
+        dts = np.concatenate(([0], np.cumsum(deltas)[:-1])).astype(np.int64) if n else np.zeros(0, np.int64)
+        return Track(track_id, handler, codec, int(timescale), int(mdur), int(width), int(height), tk, md,
+                     moov[hdlr[0]:hdlr[1]], minf_other, stsd_box, sizes, offsets, dts, deltas, None, np.ones(n, bool),
+                     False, edits, entry_payload, unit)
     n = int(sizes.size)
     # chunk offsets
     if b"co64" in tabs:
@@ -290,12 +321,12 @@ def _parse_track(moov: bytes, s: int, e: int) -> Track | None:
             raise BmffError("empty stsc")
         first = np.clip(sc[:, 0] - 1, 0, n_co)
         nxt = np.append(first[1:], n_co)
-        per_chunk = np.repeat(sc[:, 1], np.maximum(nxt - first, 0))
+        per_chunk = _expand_runs(sc[:, 1], np.maximum(nxt - first, 0), n_co)
         if per_chunk.size < n_co:
             per_chunk = np.append(per_chunk, np.zeros(n_co - per_chunk.size, np.int64))
         per_chunk = per_chunk[:n_co]
         first_sample = np.concatenate(([0], np.cumsum(per_chunk)[:-1]))
-        chunk_of = np.repeat(np.arange(n_co), per_chunk)
+        chunk_of = _expand_runs(np.arange(n_co), per_chunk, n)
         if chunk_of.size < n:
             raise BmffError("stsc/stco describe %d samples, stsz has %d" % (chunk_of.size, n))
         chunk_of = chunk_of[:n]
@@ -309,7 +340,7 @@ def _parse_track(moov: bytes, s: int, e: int) -> Track | None:
         ts_ = tabs[b"stts"][0]
         n_tt = struct.unpack_from(">I", moov, ts_ + 4)[0]
         tt = _be(moov, ">u4", 2 * n_tt, ts_ + 8).reshape(-1, 2).astype(np.int64)
-        d = np.repeat(tt[:, 1], tt[:, 0])
+        d = _expand_runs(tt[:, 1], tt[:, 0], n)
         if d.size < n:
             d = np.append(d, np.full(n - d.size, d[-1] if d.size else 0, np.int64))
         deltas = d[:n].copy()
@@ -325,7 +356,7 @@ def _parse_track(moov: bytes, s: int, e: int) -> Track | None:
         # libavformat reads the field as signed in both cases
         off = raw[:, 1].astype(np.uint32).view(np.int32).astype(np.int64)
         _ = cv
-        c = np.repeat(off, cnt)
+        c = _expand_runs(off, cnt, n)
         if c.size < n:
             c = np.append(c, np.zeros(n - c.size, np.int64))
         cts_off = c[:n].copy()
@@ -340,6 +371,68 @@ def _parse_track(moov: bytes, s: int, e: int) -> Track | None:
     return Track(track_id, handler, codec, int(timescale), int(mdur), int(width), int(height), tk, md,
                  moov[hdlr[0]:hdlr[1]], minf_other, stsd_box, sizes, offsets, dts, deltas, cts_off, sync, has_stss,
                  edits, entry_payload)
+
+
+def _chunk_table(moov: bytes, tabs: dict):
+    """(chunk offsets u64[n_co], samples per chunk i64[n_co]) from stco|co64 + stsc, or None."""
+    if b"co64" in tabs:
+        cs = tabs[b"co64"][0]
+        chunk_off = _be(moov, ">u8", struct.unpack_from(">I", moov, cs + 4)[0], cs + 8).astype(np.uint64)
+    elif b"stco" in tabs:
+        cs = tabs[b"stco"][0]
+        chunk_off = _be(moov, ">u4", struct.unpack_from(">I", moov, cs + 4)[0], cs + 8).astype(np.uint64)
+    else:
+        return None
+    n_co = int(chunk_off.size)
+    if not n_co or b"stsc" not in tabs:
+        return None
+    ss = tabs[b"stsc"][0]
+    n_sc = struct.unpack_from(">I", moov, ss + 4)[0]
+    if n_sc == 0:
+        return None
+    sc = _be(moov, ">u4", 3 * n_sc, ss + 8).reshape(-1, 3).astype(np.int64)
+    first = np.clip(sc[:, 0] - 1, 0, n_co)
+    nxt = np.append(first[1:], n_co)
+    per_chunk = _expand_runs(sc[:, 1], np.maximum(nxt - first, 0), n_co)
+    if per_chunk.size < n_co:
+        per_chunk = np.append(per_chunk, np.zeros(n_co - per_chunk.size, np.int64))
+    return chunk_off, per_chunk[:n_co]
+
+
+def _uniform_track(moov: bytes, tabs: dict, fixed: int, n: int):
+    """Grouped description of a track whose n samples all have `fixed` bytes, one duration, no composition offsets and
+    no sync table -- uncompressed audio, where a sample is ONE audio frame: two hours at 48 kHz are 345 million samples,
+    and per-sample tables of that length cost gigabytes.  Samples are grouped into runs of at most UNIFORM_GROUP inside a
+    chunk (the packets libavformat's demuxer forms for PCM, so a stream copy cuts where ffmpeg's would); the arrays then
+    describe groups, `unit` = (bytes, duration) of one sample lets the writer emit true per-sample tables again
+    (fixed-size stsz, one stts run).  Returns (sizes, offsets, deltas, unit) or None when the track is not uniform."""
+    if b"ctts" in tabs or b"stss" in tabs or b"stts" not in tabs:
+        return None
+    ts_ = tabs[b"stts"][0]
+    n_tt = struct.unpack_from(">I", moov, ts_ + 4)[0]
+    tt = _be(moov, ">u4", 2 * n_tt, ts_ + 8).reshape(-1, 2).astype(np.int64)
+    tt = tt[tt[:, 0] > 0]
+    if tt.shape[0] == 0 or (tt[:, 1] != tt[0, 1]).any():
+        return None
+    delta = int(tt[0, 1])
+    table = _chunk_table(moov, tabs)
+    if table is None:
+        return None
+    chunk_off, per_chunk = table
+    per_chunk = np.clip(per_chunk, 0, n)
+    room = n - (np.cumsum(per_chunk) - per_chunk)
+    per_chunk = np.clip(room, 0, per_chunk)                    # the chunk table may not describe more than n samples
+    if int(per_chunk.sum()) < n:
+        raise BmffError("stsc/stco describe %d samples, stsz has %d" % (int(per_chunk.sum()), n))
+    groups = -(-per_chunk // UNIFORM_GROUP)                     # groups per chunk
+    n_g = int(groups.sum())
+    if n_g > MAX_TRACK_SAMPLES:
+        raise BmffError("track with %d sample groups (limit %d)" % (n_g, MAX_TRACK_SAMPLES))
+    chunk_of = np.repeat(np.arange(per_chunk.size), groups)
+    k_in_chunk = np.arange(n_g) - np.repeat(np.cumsum(groups) - groups, groups)
+    count = np.minimum(UNIFORM_GROUP, per_chunk[chunk_of] - k_in_chunk * UNIFORM_GROUP).astype(np.int64)
+    offsets = chunk_off[chunk_of] + (k_in_chunk * UNIFORM_GROUP * fixed).astype(np.uint64)
+    return (count * fixed).astype(np.uint64), offsets.astype(np.uint64), count * delta, (fixed, delta)
 
 
 def _fragments_duration(path: Path, tops, moov: bytes, movie: Movie) -> float:
@@ -793,7 +886,12 @@ def write_plans(dst: str | Path, plans: list, mts: int, ftyp: bytes = b"", src_p
         for ti, p in enumerate(plans):
             t = p["t"]
             n = p["b"] - p["a"]
-            c, v = _runs(p["deltas"])
+            unit = getattr(t, "unit", None)
+            if unit is not None:                 # groups of equal samples: one stts run over the true sample count
+                n = int(p["sizes"].sum()) // unit[0]
+                c, v = np.asarray([n], np.int64), np.asarray([unit[1]], np.int64)
+            else:
+                c, v = _runs(p["deltas"])
             stts = full_box(b"stts", 0, 0, struct.pack(">I", c.size) +
                             np.stack([c, v], 1).astype(">u4").tobytes())
             ctts = b""
@@ -806,12 +904,14 @@ def write_plans(dst: str | Path, plans: list, mts: int, ftyp: bytes = b"", src_p
             if (t.has_stss and not p.get("all_sync")) or not p["sync"].all():
                 k = np.nonzero(p["sync"])[0] + 1
                 stss = full_box(b"stss", 0, 0, struct.pack(">I", k.size) + k.astype(">u4").tobytes())
-            c, v = _runs(p["chunk_count"])
+            c, v = _runs(p["chunk_count"] if unit is None else p["chunk_bytes"] // unit[0])
             firsts = np.concatenate(([0], np.cumsum(c)[:-1])) + 1
             stsc = full_box(b"stsc", 0, 0, struct.pack(">I", c.size) +
                             np.stack([firsts, v, np.ones_like(v)], 1).astype(">u4").tobytes())
             sz = p["sizes"]
-            if n and (sz == sz[0]).all():
+            if unit is not None:
+                stsz = full_box(b"stsz", 0, 0, struct.pack(">II", unit[0], n))
+            elif n and (sz == sz[0]).all():
                 stsz = full_box(b"stsz", 0, 0, struct.pack(">II", int(sz[0]), n))
             else:
                 stsz = full_box(b"stsz", 0, 0, struct.pack(">II", 0, n) + sz.astype(">u4").tobytes())

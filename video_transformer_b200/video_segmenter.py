@@ -139,6 +139,8 @@ def _picture_times(idx) -> np.ndarray:
     tt = idx.extra.get("times")
     if tt is not None:
         return np.asarray(tt, np.float64)
+    if idx.fps_num <= 0 or idx.fps_den <= 0:          # a corrupt header: no usable time base, nothing gets selected
+        return np.full(idx.n_frames, np.inf)
     return scene.pts(np.arange(idx.n_frames), idx.fps_num, idx.fps_den)
 
 
