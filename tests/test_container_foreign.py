@@ -63,12 +63,25 @@ def _options():
 
 
 @pytest.mark.parametrize("name,fourcc", [("a.mp4", "mp4v"), ("b.mp4", "vp09"), ("c.mkv", "VP90"), ("d.mkv", "mp4v"),
-                                         ("e.avi", "MJPG"), ("f.mov", "mp4v"), ("g.webm", "VP90")])
+                                         ("e.avi", "MJPG"), ("f.mov", "mp4v"), ("g.webm", "VP90"), ("h.flv", "FLV1")])
 def test_probe_duration_matches_libavformat(tmp_path, name, fourcc):
     p = tmp_path / name
     _cv_write(p, fourcc, n=83, fps=25.0)
     assert abs(probe_duration(p) - _cv_duration(p)) < 1e-3
     assert abs(probe_duration(p) - 83 / 25.0) < 1e-3
+
+
+def test_flv_without_metadata_duration_uses_its_last_tag(tmp_path):
+    p = tmp_path / "a.flv"
+    _cv_write(p, "FLV1", n=50, fps=25.0)
+    b = bytearray(p.read_bytes())
+    at = b.find(b"\x00\x08duration\x00")
+    assert at > 0 and abs(probe_duration(p) - 2.0) < 1e-3
+    b[at + 2:at + 10] = b"xuration"
+    p.write_bytes(bytes(b))
+    assert abs(probe_duration(p) - 49 / 25.0) < 1e-3      # timestamp of the last picture
+    p.write_bytes(bytes(b[:len(b) // 2]))                  # truncated: the trailing tag size is garbage
+    assert probe_duration(p) >= 0.0
 
 
 @pytest.mark.parametrize("fourcc", ["mp4v", "vp09"])

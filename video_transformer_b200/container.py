@@ -347,6 +347,8 @@ def container_duration(path: Path) -> float:
         return matroska.duration_seconds(path)
     if head[:4] == b"RIFF" and head[8:12] == b"AVI ":
         return _avi_duration(path)
+    if head[:3] == b"FLV" and head[3] == 1:
+        return _flv_duration(path)
     if head[4:8] in (b"ftyp", b"moov", b"free", b"mdat", b"styp", b"wide", b"skip", b"pnot"):
         try:
             return isobmff.read_movie(path).duration_seconds()
@@ -378,6 +380,34 @@ def _avi_duration(path: Path) -> float:
             best = max(best, length * scale / rate)
         pos += 4
     return best if best > 0 else fallback
+
+
+def _flv_duration(path: Path) -> float:
+    """FLV (the downloader's `best[height<=N]` fallback can deliver it, src/downloader/video_downloader.py:56): the
+    `duration` number of the onMetaData script tag, which is what libavformat's flv demuxer reports; files without it
+    get the timestamp of their last tag (found through the trailing PreviousTagSize), as the demuxer does by seeking."""
+    size = path.stat().st_size
+    with open(path, "rb") as f:
+        buf = f.read(min(size, 1 << 16))
+        at = buf.find(b"onMetaData")
+        if at >= 0:
+            k = buf.find(b"\x00\x08duration\x00", at)           # AMF0: key length, key, type 0 (number), float64
+            if k >= 0 and k + 19 <= len(buf):
+                d, = struct.unpack_from(">d", buf, k + 11)
+                if d == d and 0 < d < 1e9:
+                    return float(d)
+        if size < 13 + 15:
+            return 0.0
+        f.seek(size - 4)
+        prev, = struct.unpack(">I", f.read(4))
+        if prev < 11 or prev + 4 > size - 9:
+            return 0.0
+        f.seek(size - 4 - prev)
+        tag = f.read(11)
+    if len(tag) < 11 or tag[0] & 0x1F not in (8, 9, 18):
+        return 0.0
+    ms = (tag[7] << 24) | (tag[4] << 16) | (tag[5] << 8) | tag[6]
+    return ms / 1000.0
 
 
 def annexb_to_mp4(src_h264: str | Path, dst_mp4: str | Path) -> StreamIndex:
