@@ -33,10 +33,12 @@ def _runs(values):
 def write_av_mp4(path, *, sps, pps, video_samples, keyframes, width, height, timescale=15360, delta=512,
                  ctts=None, video_media_time=0, audio_rate=48000, audio_channels=2, audio_pcm=None,
                  audio_chunk=1024, video_chunk=5, moov_first=False, co64=False, movie_timescale=1000,
-                 audio_empty_edit=0, version1=False, stz2=False, audio_codec=b"sowt"):
+                 audio_empty_edit=0, version1=False, stz2=False, audio_codec=b"sowt", second_entry_chunk=None):
     """video_samples: list of lists of NAL byte strings (no start codes / lengths).  audio_pcm: int16 array
     [n, channels] or None.  version1: 64-bit mvhd / tkhd / mdhd / elst; stz2: the video sizes as a compact (16-bit)
-    `stz2` box.  Returns a dict describing what was written (sample byte strings per track)."""
+    `stz2` box.  second_entry_chunk: video chunks from this index on use a SECOND sample entry in `stsd` (same parameter
+    sets, another compressor name), the way files assembled from several encodes do.  Returns a dict describing what
+    was written (sample byte strings per track)."""
     def hdr_times(ts, dur):            # creation, modification, timescale, duration of mvhd / mdhd
         return struct.pack(">QQIQ", 0, 0, ts, dur) if version1 else struct.pack(">IIII", 0, 0, ts, dur)
 
@@ -83,17 +85,23 @@ def write_av_mp4(path, *, sps, pps, video_samples, keyframes, width, height, tim
         avc1 = struct.pack(">6xH", 1) + bytes(16) + struct.pack(">HH", width, height) + \
             struct.pack(">IIIH", 0x00480000, 0x00480000, 0, 1) + bytes(32) + struct.pack(">Hh", 0x18, -1) + \
             box(b"avcC", avcc) + box(b"pasp", struct.pack(">II", 1, 1))
-        stbl = full(b"stsd", 0, 0, struct.pack(">I", 1) + box(b"avc1", avc1))
+        if second_entry_chunk is None:
+            stbl = full(b"stsd", 0, 0, struct.pack(">I", 1) + box(b"avc1", avc1))
+        else:
+            name = b"\x0csecond entry" + bytes(19)
+            avc1_b = avc1[:42] + name + avc1[74:]
+            stbl = full(b"stsd", 0, 0, struct.pack(">I", 2) + box(b"avc1", avc1) + box(b"avc1", avc1_b))
         stbl += full(b"stts", 0, 0, struct.pack(">III", 1, n_v, delta))
         if ctts is not None:
             r = _runs(list(ctts))
             stbl += full(b"ctts", 0, 0, struct.pack(">I", len(r)) + b"".join(struct.pack(">II", c, v) for c, v in r))
         sync = [i + 1 for i, k in enumerate(keyframes) if k]
         stbl += full(b"stss", 0, 0, struct.pack(">I", len(sync)) + struct.pack(">%dI" % len(sync), *sync))
-        r = _runs([b - a for a, b in v_chunks])
+        r = _runs([(b - a, 1 if second_entry_chunk is None or ci < second_entry_chunk else 2)
+                   for ci, (a, b) in enumerate(v_chunks)])
         ent, first = b"", 1
-        for c, v in r:
-            ent += struct.pack(">III", first, v, 1)
+        for c, (v, d) in r:
+            ent += struct.pack(">III", first, v, d)
             first += c
         stbl += full(b"stsc", 0, 0, struct.pack(">I", len(r)) + ent)
         if stz2 and max(len(s) for s in vs) < 65536:

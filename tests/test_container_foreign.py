@@ -567,3 +567,40 @@ def test_corrupt_run_lengths_do_not_allocate_the_world(tmp_path):
     assert isinstance(probe_duration(f), float)
     assert video_segmenter.extract_segment(f, 0.2, 1.0, tmp_path / "o2.mp4") is False
     assert time.perf_counter() - t0 < 2.0
+
+
+def test_several_sample_entries_keep_their_chunks(tmp_path):
+    """A track may use more than one sample entry (`stsd`), chosen per chunk by stsc's third column (files assembled
+    from several encodes).  The cut copies all entries verbatim and every copied sample keeps its entry."""
+    w, h, n, gop, fps = 96, 80, 90, 10, 30
+    sps, pps, samples, keys, luma = _pcm_samples(w, h, n, gop)
+    src = tmp_path / "src.mp4"
+    meta = write_av_mp4(src, sps=sps, pps=pps, video_samples=samples, keyframes=keys, width=w, height=h,
+                        timescale=fps * 512, delta=512, video_chunk=5, second_entry_chunk=9)   # samples 45.. use entry 2
+    movie = isobmff.read_movie(src)
+    v = movie.video_track()
+    assert v.desc is not None and v.desc[:45].tolist() == [1] * 45 and v.desc[45:].tolist() == [2] * 45
+    assert struct.unpack_from(">I", v.stsd, 12)[0] == 2 and b"second entry" in v.stsd
+    out = tmp_path / "cut.mp4"
+    r = isobmff.cut_movie(movie, 1.0, 2.5, out)                      # pictures 30..75: both entries are in use
+    assert (r.first, r.last) == (30, 75)
+    cut = isobmff.read_movie(out)
+    c = cut.video_track()
+    assert c.stsd == v.stsd
+    assert c.desc is not None and c.desc.tolist() == [1] * 15 + [2] * 30
+    data = out.read_bytes()
+    assert [data[int(o):int(o) + int(z)] for o, z in zip(c.offsets, c.sizes)] == meta["video_samples"][30:75]
+    cap = cv2.VideoCapture(str(out), cv2.CAP_FFMPEG)                 # libavformat follows the entries, too
+    cap.set(cv2.CAP_PROP_CONVERT_RGB, 0)
+    k = 30
+    while True:
+        ok, fr = cap.read()
+        if not ok:
+            break
+        assert np.array_equal(np.asarray(fr).reshape(-1)[: w * h].reshape(h, w), luma[k]), k
+        k += 1
+    assert k == 75
+    # a window inside the second entry's range: only entry 2 is referenced, the table still names it
+    r2 = isobmff.cut_movie(movie, 2.0, 2.9, tmp_path / "late.mp4")
+    late = isobmff.read_movie(tmp_path / "late.mp4").video_track()
+    assert late.desc is not None and set(late.desc.tolist()) == {2} and late.n == r2.last - r2.first

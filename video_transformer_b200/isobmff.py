@@ -123,6 +123,7 @@ class Track:
     has_stss: bool
     edits: list                     # [(segment_duration (movie ts), media_time, rate_16_16)]
     entry_payload: tuple = (0, 0)   # (start, end) of the first sample entry's payload inside `stsd`
+    desc: np.ndarray | None = None  # int64 [n] sample description index (1-based) of every sample; None = all use entry 1
     unit: tuple | None = None       # (bytes, duration) of ONE sample when the arrays above describe GROUPS of equal
                                     # samples (uniform tracks with millions of samples, e.g. PCM audio: see _parse_track)
 
@@ -298,7 +299,7 @@ def _parse_track(moov: bytes, s: int, e: int) -> Track | None:
         dts = np.concatenate(([0], np.cumsum(deltas)[:-1])).astype(np.int64) if n else np.zeros(0, np.int64)
         return Track(track_id, handler, codec, int(timescale), int(mdur), int(width), int(height), tk, md,
                      moov[hdlr[0]:hdlr[1]], minf_other, stsd_box, sizes, offsets, dts, deltas, None, np.ones(n, bool),
-                     False, edits, entry_payload, unit)
+                     False, edits, entry_payload, unit=unit)
     n = int(sizes.size)
     # chunk offsets
     if b"co64" in tabs:
@@ -313,6 +314,7 @@ def _parse_track(moov: bytes, s: int, e: int) -> Track | None:
         chunk_off = np.zeros(0, np.uint64)
     n_co = int(chunk_off.size)
     offsets = np.zeros(n, np.uint64)
+    desc = None
     if n and n_co and b"stsc" in tabs:
         ss = tabs[b"stsc"][0]
         n_sc = struct.unpack_from(">I", moov, ss + 4)[0]
@@ -330,6 +332,11 @@ def _parse_track(moov: bytes, s: int, e: int) -> Track | None:
         if chunk_of.size < n:
             raise BmffError("stsc/stco describe %d samples, stsz has %d" % (chunk_of.size, n))
         chunk_of = chunk_of[:n]
+        if (sc[:, 2] != 1).any():                 # several sample entries (stsd) in use: remember which sample uses which
+            d_chunk = _expand_runs(sc[:, 2], np.maximum(nxt - first, 0), n_co)
+            if d_chunk.size < n_co:
+                d_chunk = np.append(d_chunk, np.ones(n_co - d_chunk.size, np.int64))
+            desc = d_chunk[chunk_of].astype(np.int64)
         excl = np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(np.uint64)
         offsets = chunk_off[chunk_of] + excl - excl[first_sample[chunk_of]]
     elif n:
@@ -370,7 +377,7 @@ def _parse_track(moov: bytes, s: int, e: int) -> Track | None:
         sync[k[(k >= 0) & (k < n)]] = True
     return Track(track_id, handler, codec, int(timescale), int(mdur), int(width), int(height), tk, md,
                  moov[hdlr[0]:hdlr[1]], minf_other, stsd_box, sizes, offsets, dts, deltas, cts_off, sync, has_stss,
-                 edits, entry_payload)
+                 edits, entry_payload, desc=desc)
 
 
 def _chunk_table(moov: bytes, tabs: dict):
@@ -408,6 +415,11 @@ def _uniform_track(moov: bytes, tabs: dict, fixed: int, n: int):
     (fixed-size stsz, one stts run).  Returns (sizes, offsets, deltas, unit) or None when the track is not uniform."""
     if b"ctts" in tabs or b"stss" in tabs or b"stts" not in tabs:
         return None
+    if b"stsc" in tabs:
+        ss = tabs[b"stsc"][0]
+        n_sc = struct.unpack_from(">I", moov, ss + 4)[0]
+        if (_be(moov, ">u4", 3 * n_sc, ss + 8).reshape(-1, 3)[:, 2] != 1).any():
+            return None                           # several sample entries in use: the per-sample path keeps track of them
     ts_ = tabs[b"stts"][0]
     n_tt = struct.unpack_from(">I", moov, ts_ + 4)[0]
     tt = _be(moov, ">u4", 2 * n_tt, ts_ + 8).reshape(-1, 2).astype(np.int64)
@@ -780,9 +792,11 @@ def cut_movie(movie: Movie, start: float, end: float, dst: str | Path, *, stream
         pres_ticks = max(0, (media_dur - (media_time - min_cts)) * mts + t.timescale - 1) // t.timescale
         # chunking: consecutive samples up to chunk_seconds / chunk_bytes
         rel = (t.dts[a:b] - t.dts[a]).astype(np.float64) / t.timescale
-        chunk_first, chunk_count, chunk_bytes_ = _chunk_plan(rel, sizes, chunk_seconds, chunk_bytes)
+        desc = None if t.desc is None else t.desc[a:b]
+        chunk_first, chunk_count, chunk_bytes_ = _chunk_plan(rel, sizes, chunk_seconds, chunk_bytes, desc)
         chunk_time = tp[chunk_first] if cts_off is None else (t.dts[a:b][chunk_first] - mt_src) / t.timescale
         plans.append({"t": t, "a": a, "b": b, "sizes": sizes, "deltas": deltas, "cts_off": cts_off, "sync": sync,
+                      "chunk_desc": None if desc is None else desc[chunk_first],
                       "override": override, "empty_ticks": empty_ticks, "media_time": media_time,
                       "media_dur": media_dur, "pres_ticks": pres_ticks + empty_ticks, "chunk_first": chunk_first,
                       "chunk_count": chunk_count, "chunk_bytes": chunk_bytes_,
@@ -793,14 +807,18 @@ def cut_movie(movie: Movie, start: float, end: float, dst: str | Path, *, stream
     return CutResult(first, last, first_acc, len(plans), total_bytes, t_present)
 
 
-def _chunk_plan(rel_seconds: np.ndarray, sizes: np.ndarray, chunk_seconds: float, chunk_bytes: int):
-    """Group consecutive samples into chunks of at most chunk_seconds / chunk_bytes -> (first, count, bytes) per chunk."""
+def _chunk_plan(rel_seconds: np.ndarray, sizes: np.ndarray, chunk_seconds: float, chunk_bytes: int, desc=None):
+    """Group consecutive samples into chunks of at most chunk_seconds / chunk_bytes -> (first, count, bytes) per chunk.
+    A chunk has ONE sample description (stsc), so a change of `desc` also starts a new chunk."""
     n = sizes.size
     bucket_t = np.floor(rel_seconds / chunk_seconds).astype(np.int64)
     csum = np.concatenate(([0], np.cumsum(sizes)[:-1])).astype(np.int64)
     bucket_b = csum // chunk_bytes
     key = bucket_t * (1 << 20) + (bucket_b - bucket_b[np.searchsorted(bucket_t, bucket_t, side="left")])
-    brk = np.nonzero(np.diff(key))[0] + 1
+    change = np.diff(key) != 0
+    if desc is not None:
+        change |= np.diff(desc) != 0
+    brk = np.nonzero(change)[0] + 1
     chunk_first = np.concatenate(([0], brk)).astype(np.int64)
     chunk_count = np.diff(np.concatenate((chunk_first, [n]))).astype(np.int64)
     chunk_bytes_ = np.add.reduceat(sizes.astype(np.int64), chunk_first)
@@ -812,13 +830,14 @@ def plan_whole_track(t: Track, movie_timescale: int, chunk_seconds: float = 0.5,
     empty_s, mt = t.edit_shift(movie_timescale)
     media_dur = int(t.deltas.sum())
     rel = t.dts.astype(np.float64) / t.timescale
-    cf, cc, cb = _chunk_plan(rel, t.sizes, chunk_seconds, chunk_bytes)
+    cf, cc, cb = _chunk_plan(rel, t.sizes, chunk_seconds, chunk_bytes, t.desc)
     empty_ticks = int(round(empty_s * movie_timescale))
     pres_ticks = max(0, (media_dur - mt) * movie_timescale + t.timescale - 1) // t.timescale
     return {"t": t, "a": 0, "b": t.n, "sizes": t.sizes.copy(), "deltas": t.deltas, "cts_off": t.cts_off,
             "sync": t.sync.copy(), "override": None, "empty_ticks": empty_ticks, "media_time": mt,
             "media_dur": media_dur, "pres_ticks": pres_ticks + empty_ticks, "chunk_first": cf, "chunk_count": cc,
-            "chunk_bytes": cb, "chunk_time": rel[cf] + empty_s}
+            "chunk_bytes": cb, "chunk_time": rel[cf] + empty_s,
+            "chunk_desc": None if t.desc is None else t.desc[cf]}
 
 
 def make_video_track(track_id: int, codec: bytes, width: int, height: int, timescale: int,
@@ -904,10 +923,17 @@ def write_plans(dst: str | Path, plans: list, mts: int, ftyp: bytes = b"", src_p
             if (t.has_stss and not p.get("all_sync")) or not p["sync"].all():
                 k = np.nonzero(p["sync"])[0] + 1
                 stss = full_box(b"stss", 0, 0, struct.pack(">I", k.size) + k.astype(">u4").tobytes())
-            c, v = _runs(p["chunk_count"] if unit is None else p["chunk_bytes"] // unit[0])
+            per = p["chunk_count"] if unit is None else p["chunk_bytes"] // unit[0]
+            cd = p.get("chunk_desc")
+            if cd is None:
+                c, v = _runs(per)
+                dv = np.ones_like(v)
+            else:                                 # runs of (samples per chunk, sample description index)
+                c, pair = _runs(per.astype(np.int64) * (1 << 20) + cd.astype(np.int64))
+                v, dv = pair >> 20, pair & ((1 << 20) - 1)
             firsts = np.concatenate(([0], np.cumsum(c)[:-1])) + 1
             stsc = full_box(b"stsc", 0, 0, struct.pack(">I", c.size) +
-                            np.stack([firsts, v, np.ones_like(v)], 1).astype(">u4").tobytes())
+                            np.stack([firsts, v, dv], 1).astype(">u4").tobytes())
             sz = p["sizes"]
             if unit is not None:
                 stsz = full_box(b"stsz", 0, 0, struct.pack(">II", unit[0], n))
