@@ -101,7 +101,11 @@ def test_scale_plane_generic_bit_exact(cuda, oracle_c, flags, sw, sh, dw, dh):
     (2880, 1620, 3072, 960, 540, ops.SWS_BICUBIC),
     (810, 540, 896, 540, 360, ops.SWS_BICUBIC),         # 3:2 but the width is not a multiple of 8: pair layout
     (960, 540, 1024, 640, 360, ops.SWS_BILINEAR),
-    # planes the pair kernel does not take: narrower than a strip / odd chroma width -> fast two-pass kernels;
+    # odd chroma widths (427, 683, 213): the pair kernel with byte stores, the last strip starting on an odd column
+    (1920, 1080, 1920, 1366, 768, ops.SWS_BICUBIC),
+    (3840, 2160, 3840, 854, 480, ops.SWS_BICUBIC),
+    (1280, 720, 1280, 854, 480, ops.SWS_BILINEAR),
+    # planes the pair kernel does not take: narrower than a strip -> fast two-pass kernels;
     # more than 16 horizontal taps -> general two-pass kernels (both batched over the pictures)
     (322, 182, 336, 160, 90, ops.SWS_BICUBIC),
     (640, 360, 640, 200, 112, ops.SWS_BILINEAR),
@@ -126,7 +130,8 @@ def test_scale_nv12_to_yuv420p_bit_exact(cuda, oracle_c, sw, sh, pitch, dw, dh, 
         assert np.array_equal(gv, ev), ("V", np.abs(gv.astype(int) - ev.astype(int)).max())
 
 
-@pytest.mark.parametrize("sw,sh,dw,dh", [(1920, 1080, 1280, 720), (1280, 720, 640, 360), (3840, 2160, 1280, 720)])
+@pytest.mark.parametrize("sw,sh,dw,dh", [(1920, 1080, 1280, 720), (1280, 720, 640, 360), (3840, 2160, 1280, 720),
+                                         (1920, 1080, 854, 480)])      # the downloader's default height: 427-wide chroma
 def test_headline_shapes_take_the_streaming_kernel(cuda, sw, sh, dw, dh):
     plan = ops.ScalePlan(sw, sh, dw, dh, ops.SWS_BICUBIC)
     for chroma in (False, True):

@@ -146,6 +146,13 @@ __device__ __forceinline__ void st_u32(uint8_t *p, uint32_t v) {
 __device__ __forceinline__ void st_u32x2(uint8_t *p, uint32_t lo, uint32_t hi) {
     asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(lo), "r"(hi) : "memory");
 }
+// A column pair of a plane whose width is odd (427-wide chroma of 854x480): its rows alternate between even and odd byte
+// addresses, so the pair leaves as two byte stores.  The strips still end exactly on the last column (the last strip
+// slides left), so no column of a pair is out of range.
+__device__ __forceinline__ void st_u8x2(uint8_t *p, uint32_t v) {
+    asm volatile("st.global.L1::no_allocate.u8 [%0], %1;" ::"l"(p), "r"(v & 0xFFu) : "memory");
+    asm volatile("st.global.L1::no_allocate.u8 [%0], %1;" ::"l"(p + 1), "r"((v >> 8) & 0xFFu) : "memory");
+}
 __device__ __forceinline__ void st_u16(uint8_t *p, uint32_t v) {
     if (VT_ABLATE & 8) {
         if (v == 0x12345u) asm volatile("st.global.L1::no_allocate.u16 [%0], %1;" ::"l"(p), "h"((unsigned short)v) : "memory");
@@ -539,6 +546,18 @@ scale_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 return;
             }
             // (HS chroma with one column pair per lane stores its two 16-bit halves exactly like the generic layout)
+            if (a.dw & 1) {                                                  // odd plane width (warp-uniform): byte stores
+#pragma unroll
+                for (int g = 0; g < NP; g++) {
+                    if (!UV) {
+                        st_u8x2(dptr + 64 * g, pack_sat_u8x2(acc[2 * g + 1] >> 19, acc[2 * g] >> 19));
+                    } else {
+                        st_u8x2(dptr + 64 * g, pack_sat_u8x2(acc[4 * g + 1] >> 19, acc[4 * g] >> 19));
+                        st_u8x2(dptr + a.dst_plane2 + 64 * g, pack_sat_u8x2(acc[4 * g + 3] >> 19, acc[4 * g + 2] >> 19));
+                    }
+                }
+                return;
+            }
 #pragma unroll
             for (int g = 0; g < NP; g++) {
                 if (!UV) {
@@ -903,11 +922,13 @@ int build_pair(vt_scale_plan *p, int c) {
     const int bn = s.hp + 1;
     s.np = uv ? pair_np(s.hp, s.tv) / 2 : pair_np(s.hp, s.tv);
     s.strip_cols = s.np * 64;
-    if ((dw & 1) || (p->dw & 1) || dw < s.strip_cols) return VT_OK;
+    // an odd CHROMA width is fine (byte stores; the last strip slides left onto the last column, so its pairs start on
+    // odd columns); the luma width is even by construction (`scale=-2:H`)
+    if ((!uv && (dw & 1)) || (p->dw & 1) || dw < s.strip_cols) return VT_OK;
     if ((c ? p->csh : p->sh) > 32767) return VT_OK;              // the vertical table holds source rows as int16
     for (int x = 0; x + 1 < dw; x++)
         if (hpos[x + 1] < hpos[x]) return VT_OK;
-    for (int x = 0; x + 1 < dw; x += 2)
+    for (int x = 0; x + 1 < dw; x += (dw & 1) ? 1 : 2)           // every pair a lane can own
         if (hpos[x + 1] - hpos[x] + ht > 2 * bn) return VT_OK;
     for (int y = 0; y + 1 < dh; y++)
         if (vpos[y + 1] < vpos[y]) return VT_OK;
