@@ -105,8 +105,15 @@ def test_scale_plane_generic_bit_exact(cuda, oracle_c, flags, sw, sh, dw, dh):
     (1920, 1080, 1920, 1366, 768, ops.SWS_BICUBIC),
     (3840, 2160, 3840, 854, 480, ops.SWS_BICUBIC),
     (1280, 720, 1280, 854, 480, ops.SWS_BILINEAR),
-    # planes the pair kernel does not take: narrower than a strip -> fast two-pass kernels;
-    # more than 16 horizontal taps -> general two-pass kernels (both batched over the pictures)
+    # large ratios: 17-32 taps run on the dp2a two-pass kernels (12 / 16 coefficient pairs, 24 / 32 vertical taps) ...
+    (3840, 2160, 3840, 640, 360, ops.SWS_BICUBIC),      # 6:1, the upload reducer's shape for 4K sources
+    (1920, 1080, 2048, 320, 180, ops.SWS_BICUBIC),
+    (1920, 1080, 1920, 284, 160, ops.SWS_AREA),
+    (2560, 1440, 2560, 426, 240, ops.SWS_BILINEAR),
+    # ... and more than 32 taps on the general two-pass kernels
+    (3840, 2160, 3840, 426, 240, ops.SWS_BICUBIC),
+    # planes the pair kernel does not take: narrower than a strip -> fast two-pass kernels
+    # (both batched over the pictures)
     (322, 182, 336, 160, 90, ops.SWS_BICUBIC),
     (640, 360, 640, 200, 112, ops.SWS_BILINEAR),
     (1920, 1080, 1920, 426, 240, ops.SWS_BICUBIC),

@@ -1,4 +1,4 @@
-// vt_hscale_fast.cuh -- horizontal polyphase taps through dp2a for word-aligned NV12 surfaces (taps <= 16), shared by
+// vt_hscale_fast.cuh -- horizontal polyphase taps through dp2a for word-aligned NV12 surfaces (taps <= 32), shared by
 // the RGB path (vt_rgb.cu) and by the batched two-pass scaler (vt_scale.cu) for planes the pair kernel does not take.
 // Results are libswscale's 15-bit intermediates: min((sum pixel * coef14) >> 7, 32767).
 #pragma once
@@ -62,11 +62,23 @@ hscale_luma_fast(const uint8_t *__restrict__ src, int pitch, size_t src_fs, int 
     hs_load_pairs<HP>(coef2 + (size_t)x * HP, c);
     const uint32_t *row = reinterpret_cast<const uint32_t *>(src + (size_t)blockIdx.z * src_fs + (size_t)r0 * pitch);
     int16_t *mo = mid + (size_t)blockIdx.z * mid_fs + (size_t)r0 * dw + x;
+    // Long windows (the 12- and 16-pair banks of the large ratios): all but the row's last few samples lie inside the
+    // row, and their words then sit at constant offsets from ONE pointer (measured 7 % on 3840x2160 -> 640x360; for the
+    // short banks the second code path only costs registers: 122 per thread for the 8-pair chroma kernel).
+    constexpr bool DUAL = HP >= 12;
+    const bool inside = DUAL && w0 + NW - 1 <= wl;
+    const uint32_t *base = row + w0;
 #pragma unroll 4
     for (int r = 0; r < nr; r++) {
         uint32_t w[NW];
+        if (DUAL && inside) {
 #pragma unroll
-        for (int i = 0; i < NW; i++) w[i] = __ldg(row + wi[i]);
+            for (int i = 0; i < NW; i++) w[i] = __ldg(base + i);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NW; i++) w[i] = __ldg(row + wi[i]);
+        }
+        base += pw;
         int v = 0;
 #pragma unroll
         for (int i = 0; i < HP; i++) {
@@ -100,11 +112,20 @@ hscale_chroma_fast(const uint8_t *__restrict__ src, int pitch, size_t src_fs, in
     hs_load_pairs<HP>(coef2 + (size_t)x * HP, c);
     const uint32_t *row = reinterpret_cast<const uint32_t *>(src + (size_t)blockIdx.z * src_fs + (size_t)r0 * pitch);
     size_t o = (size_t)blockIdx.z * mid_fs + (size_t)r0 * cdw + x;
+    constexpr bool DUAL = HP >= 12;                    // see hscale_luma_fast
+    const bool inside = DUAL && w0 + HP <= wl;
+    const uint32_t *base = row + w0;
 #pragma unroll 4
     for (int r = 0; r < nr; r++) {
         uint32_t w[HP + 1];
+        if (DUAL && inside) {
 #pragma unroll
-        for (int i = 0; i < HP + 1; i++) w[i] = __ldg(row + wi[i]);
+            for (int i = 0; i < HP + 1; i++) w[i] = __ldg(base + i);
+        } else {
+#pragma unroll
+            for (int i = 0; i < HP + 1; i++) w[i] = __ldg(row + wi[i]);
+        }
+        base += pw;
         int u = 0, v = 0;
 #pragma unroll
         for (int i = 0; i < HP; i++) {
@@ -120,10 +141,11 @@ hscale_chroma_fast(const uint8_t *__restrict__ src, int pitch, size_t src_fs, in
 }
 
 
-// coefficient pairs per output sample, padded to an instantiated count (0 = more than 16 taps: general kernels)
+// coefficient pairs per output sample, padded to an instantiated count (0 = more than 32 taps: general kernels).
+// 12 and 16 pairs serve the large ratios (3840x2160 -> 640x360 is 6:1: 24 bicubic taps; 1920x1080 -> 426x240 4.5:1).
 inline int hscale_fast_pairs(int taps) {
     const int hp = (taps + 1) / 2;
-    return hp <= 2 ? 2 : hp <= 3 ? 3 : hp <= 4 ? 4 : hp <= 6 ? 6 : hp <= 8 ? 8 : 0;
+    return hp <= 2 ? 2 : hp <= 3 ? 3 : hp <= 4 ? 4 : hp <= 6 ? 6 : hp <= 8 ? 8 : hp <= 12 ? 12 : hp <= 16 ? 16 : 0;
 }
 
 }  // namespace vt

@@ -65,6 +65,36 @@ vscale_generic_kernel(const int16_t *__restrict__ mid, size_t mid_fs, int dw, ui
 }
 
 // Vertical taps, VT unrolled (bank padded with zero coefficients; padded taps read a clamped row), 32-bit indices.
+// One output row per blockIdx.y, so everything that depends on y is block-uniform: the VT coefficients arrive through
+// the widest aligned loads the padded bank allows, and rows whose window lies inside the plane (all but the last few)
+// walk a pointer instead of clamping an index per tap -- 3 instructions per tap instead of ~10, which is what the
+// 24- and 32-tap banks of the large ratios (3840x2160 -> 640x360) are made of.
+template <int VT>
+__device__ __forceinline__ void vs_load_coef(const int16_t *__restrict__ c, int (&k)[VT]) {
+    if constexpr (VT % 8 == 0) {
+#pragma unroll
+        for (int i = 0; i < VT / 8; i++) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(c) + i);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                k[8 * i + 2 * j] = (int)(int16_t)(w[j] & 0xFFFFu);
+                k[8 * i + 2 * j + 1] = (int)(int16_t)(w[j] >> 16);
+            }
+        }
+    } else if constexpr (VT % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < VT / 2; i++) {
+            const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(c) + i);
+            k[2 * i] = (int)(int16_t)(w & 0xFFFFu);
+            k[2 * i + 1] = (int)(int16_t)(w >> 16);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < VT; i++) k[i] = (int)__ldg(c + i);
+    }
+}
+
 template <int VT>
 __global__ void __launch_bounds__(256)
 vscale_fast_kernel(const int16_t *__restrict__ mid, size_t mid_fs, int dw, int sh, uint8_t *__restrict__ dst, int dst_pitch,
@@ -72,18 +102,29 @@ vscale_fast_kernel(const int16_t *__restrict__ mid, size_t mid_fs, int dw, int s
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     if (x >= dw) return;
-    const int16_t *m = mid + (size_t)blockIdx.z * mid_fs + x;
     const int r0 = __ldg(vpos + y);
-    int t[VT];
-#pragma unroll
-    for (int j = 0; j < VT; j++) t[j] = __ldg(m + min(r0 + j, sh - 1) * dw);
+    int k[VT];
+    vs_load_coef<VT>(vc2 + (size_t)y * VT, k);          // rows of the bank are VT * 2 bytes: 16-byte aligned for VT % 8 == 0
     int v = 1 << 18;
+    if (r0 + VT <= sh) {                                 // block-uniform
+        const int16_t *m = mid + (size_t)blockIdx.z * mid_fs + (size_t)r0 * dw + x;
 #pragma unroll
-    for (int j = 0; j < VT; j++) v += t[j] * (int)__ldg(vc2 + y * VT + j);
+        for (int j = 0; j < VT; j++) {
+            v += (int)__ldg(m) * k[j];
+            m += dw;
+        }
+    } else {
+        const int16_t *m = mid + (size_t)blockIdx.z * mid_fs + x;
+#pragma unroll
+        for (int j = 0; j < VT; j++) v += (int)__ldg(m + min(r0 + j, sh - 1) * dw) * k[j];
+    }
     dst[(size_t)blockIdx.z * dst_fs + (size_t)y * dst_pitch + x] = (uint8_t)max(0, min(255, v >> 19));
 }
 
-static int pad_vt2(int taps) { return taps < 2 ? 0 : taps <= 4 ? 4 : taps <= 6 ? 6 : taps <= 8 ? 8 : taps <= 12 ? 12 : taps <= 16 ? 16 : 0; }
+static int pad_vt2(int taps) {
+    return taps < 2 ? 0 : taps <= 4 ? 4 : taps <= 6 ? 6 : taps <= 8 ? 8 : taps <= 12 ? 12 : taps <= 16 ? 16 : taps <= 24 ? 24
+         : taps <= 32 ? 32 : 0;
+}
 
 template <int VT>
 static void launch_vfast(const vt_scale_plan *p, int c, const int16_t *mid, size_t mid_fs, uint8_t *dst, size_t dst_fs, int nf,
@@ -98,7 +139,9 @@ static int vfast(const vt_scale_plan *p, int c, const int16_t *mid, size_t mid_f
         case 6: launch_vfast<6>(p, c, mid, mid_fs, dst, dst_fs, nf, st); break;
         case 8: launch_vfast<8>(p, c, mid, mid_fs, dst, dst_fs, nf, st); break;
         case 12: launch_vfast<12>(p, c, mid, mid_fs, dst, dst_fs, nf, st); break;
-        default: launch_vfast<16>(p, c, mid, mid_fs, dst, dst_fs, nf, st); break;
+        case 16: launch_vfast<16>(p, c, mid, mid_fs, dst, dst_fs, nf, st); break;
+        case 24: launch_vfast<24>(p, c, mid, mid_fs, dst, dst_fs, nf, st); break;
+        default: launch_vfast<32>(p, c, mid, mid_fs, dst, dst_fs, nf, st); break;
     }
     VT_LAUNCHED("vscale_fast_kernel");
     return VT_OK;
@@ -118,13 +161,13 @@ int scale_plane_fast(const vt_scale_plan *p, int c, const uint8_t *src, int pitc
         const dim3 g((dw + 255) / 256, (sh + HS_RPT - 1) / HS_RPT, nf);
         if (!c) {
 #define VT_H(H) case H: hscale_luma_fast<H><<<g, 256, 0, st>>>(s, pitch, src_fs, sh, ma, mid_fs, dw, p->hc2[0], p->hpos[0]); break
-            switch (p->hp2[0]) { VT_H(2); VT_H(3); VT_H(4); VT_H(6); VT_H(8); }
+            switch (p->hp2[0]) { VT_H(2); VT_H(3); VT_H(4); VT_H(6); VT_H(8); VT_H(12); VT_H(16); }
 #undef VT_H
             VT_LAUNCHED("hscale_luma_fast");
             if (int rc = vfast(p, 0, ma, mid_fs, dst_a + (size_t)f0 * dst_fs, dst_fs, nf, st)) return rc;
         } else {
 #define VT_H(H) case H: hscale_chroma_fast<H><<<g, 256, 0, st>>>(s, pitch, src_fs, sh, ma, mb, mid_fs, dw, p->hc2[1], p->hpos[1]); break
-            switch (p->hp2[1]) { VT_H(2); VT_H(3); VT_H(4); VT_H(6); VT_H(8); }
+            switch (p->hp2[1]) { VT_H(2); VT_H(3); VT_H(4); VT_H(6); VT_H(8); VT_H(12); VT_H(16); }
 #undef VT_H
             VT_LAUNCHED("hscale_chroma_fast");
             if (int rc = vfast(p, 1, ma, mid_fs, dst_a + (size_t)f0 * dst_fs, dst_fs, nf, st)) return rc;
