@@ -152,10 +152,11 @@ def _pwrite_all(fd: int, mv: memoryview, offset: int) -> None:
 
 
 def _arena_cap() -> int:
-    """Page-locked landing memory this process keeps (registered files, in use or free).  Beyond it the oldest files are
-    released: unregistered, unmapped, their arena name removed -- the `.frames` hard link stays an ordinary file.  (An
-    unbounded arena made every later page-locking call of the process slower: 64 retained 415 MB files took engine
-    set-up from 30 ms to 530 ms in the configs[3] batch.)"""
+    """Page-locked landing memory this process keeps (registered files, in use or free).  At the cap the oldest FREE
+    files are released (unregistered, unmapped, their arena name removed); files whose `.frames` name still exists are
+    left alone and new outputs take the staged writer instead (_make_room).  (An unbounded arena made every later
+    page-locking call of the process slower: 64 retained 415 MB files took engine set-up from 30 ms to 530 ms in the
+    configs[3] batch.)"""
     return int(float(os.environ.get("VT_LANDING_CAP_GB", "12")) * (1 << 30))
 
 
