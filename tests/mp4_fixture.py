@@ -266,10 +266,11 @@ def _u(eid, value, width=None):
 
 
 def write_mkv(path, *, sps, pps, video_samples, keyframes, width, height, fps=30, opus_packets=None, opus_ms=20,
-              frames_per_cluster=10):
+              frames_per_cluster=10, audio_codec=None):
     """video_samples: lists of NAL byte strings (stored length-prefixed, CodecPrivate = avcC, as V_MPEG4/ISO/AVC);
     opus_packets: list of byte strings, one per opus_ms milliseconds (A_OPUS with an OpusHead CodecPrivate).  SimpleBlocks,
-    1 ms timestamps, Duration filled in.  Returns the sample byte strings per track."""
+    1 ms timestamps, Duration filled in.  audio_codec = (codec id, CodecPrivate, sampling rate, channels) labels the
+    audio packets as another codec (their bytes are opaque to a stream copy).  Returns the sample byte strings per track."""
     vs = [b"".join(struct.pack(">I", len(n)) + n for n in nals) for nals in video_samples]
     avcc = struct.pack(">BBBBBB", 1, sps[1], sps[2], sps[3], 0xFF, 0xE1) + struct.pack(">H", len(sps)) + sps + \
         struct.pack(">BH", 1, len(pps)) + pps
@@ -286,9 +287,10 @@ def write_mkv(path, *, sps, pps, video_samples, keyframes, width, height, fps=30
     opus_head = b""
     if opus_packets:
         opus_head = b"OpusHead" + bytes([1, 2]) + struct.pack("<HIh", 312, 48000, 0) + bytes([0])
-        tracks += _ebml(b"\xae", _u(b"\xd7", 2) + _u(b"\x73\xc5", 2) + _u(b"\x83", 2) + _ebml(b"\x86", b"A_OPUS") +
-                        _ebml(b"\x63\xa2", opus_head) +
-                        _ebml(b"\xe1", _ebml(b"\xb5", struct.pack(">f", 48000.0)) + _u(b"\x9f", 2)))
+        a_id, a_priv, a_rate, a_ch = audio_codec or (b"A_OPUS", opus_head, 48000.0, 2)
+        tracks += _ebml(b"\xae", _u(b"\xd7", 2) + _u(b"\x73\xc5", 2) + _u(b"\x83", 2) + _ebml(b"\x86", a_id) +
+                        (_ebml(b"\x63\xa2", a_priv) if a_priv else b"") +
+                        _ebml(b"\xe1", _ebml(b"\xb5", struct.pack(">f", float(a_rate))) + _u(b"\x9f", a_ch)))
     tracks = _ebml(b"\x16\x54\xae\x6b", tracks)
     events = [(int(round(i * 1000.0 / fps)), 1, i) for i in range(n)]
     events += [(i * opus_ms, 2, i) for i in range(len(opus_packets or []))]

@@ -372,7 +372,7 @@ def test_truncated_and_garbage_inputs_are_refused(tmp_path):
     assert video_segmenter.extract_segment(junk, 0.0, 1.0, tmp_path / "o2.mp4") is False
 
 
-@pytest.mark.parametrize("name,fourcc", [("m.mkv", "VP90"), ("n.mkv", "mp4v"), ("o.webm", "VP90")])
+@pytest.mark.parametrize("name,fourcc", [("m.mkv", "VP90"), ("n.mkv", "mp4v"), ("o.webm", "VP90"), ("p.mkv", "VP80")])
 def test_matroska_source_is_stream_copied_into_mp4(tmp_path, name, fourcc):
     """`ffmpeg -ss S -i IN.webm -t D -c copy OUT.mp4` re-wraps Matroska streams: VP9 and MPEG-4 tracks written by
     libavformat's matroska muxer are indexed, cut at a keyframe and decode to exactly the source's pictures."""
@@ -604,3 +604,37 @@ def test_several_sample_entries_keep_their_chunks(tmp_path):
     r2 = isobmff.cut_movie(movie, 2.0, 2.9, tmp_path / "late.mp4")
     late = isobmff.read_movie(tmp_path / "late.mp4").video_track()
     assert late.desc is not None and set(late.desc.tolist()) == {2} and late.n == r2.last - r2.first
+
+
+@pytest.mark.parametrize("codec_id,private,rate,fourcc", [
+    (b"A_MPEG/L3", b"", 44100.0, b"mp4a"),
+    (b"A_FLAC", b"fLaC" + bytes([0x80, 0, 0, 34]) + bytes(10) + bytes([0x0A, 0xC4, 0x42, 0xF0]) + bytes(20), 44100.0, b"fLaC"),
+    (b"A_VORBIS", b"\x02\x1e\x20" + bytes(60), 44100.0, None),
+])
+def test_matroska_audio_codecs_map_to_mp4_sample_entries(tmp_path, codec_id, private, rate, fourcc):
+    """MP3 -> `mp4a` with object type 0x6B and no decoder-specific info, FLAC -> `fLaC` + dfLa (the CodecPrivate's
+    metadata blocks); a codec without an MP4 mapping (Vorbis: ffmpeg's mov muxer refuses it, too) is left out, the video
+    still arrives.  Packets are opaque to a stream copy, so the fixture's are arbitrary bytes."""
+    w, h, n, gop, fps = 64, 48, 40, 10, 30
+    sps, pps, samples, keys, _ = _pcm_samples(w, h, n, gop)
+    packets = [bytes([0xFF, 0xFB, k & 0xFF]) + bytes((k + j) & 0xFF for j in range(50)) for k in range(50)]
+    src = tmp_path / "a.mkv"
+    write_mkv(src, sps=sps, pps=pps, video_samples=samples, keyframes=keys, width=w, height=h, fps=fps,
+              opus_packets=packets, opus_ms=26, audio_codec=(codec_id, private, rate, 2))
+    video_segmenter.configure(frame_buffers=False)
+    out = tmp_path / "cut.mp4"
+    assert video_segmenter.extract_segment(src, 0.0, 1.0, out) is True
+    cut = isobmff.read_movie(out)
+    if fourcc is None:
+        assert [t.codec for t in cut.tracks] == [b"avc1"]
+        return
+    assert [t.codec for t in cut.tracks] == [b"avc1", fourcc]
+    a = cut.tracks[1]
+    data = out.read_bytes()
+    got = [data[int(o):int(o) + int(z)] for o, z in zip(a.offsets, a.sizes)]
+    assert got == packets[:len(got)] and len(got) >= 38                 # one second of 26 ms packets
+    if fourcc == b"mp4a":
+        assert b"esds" in a.stsd and bytes([0x04]) in a.stsd and b"\x6b\x15" in a.stsd and b"\x05\x80" not in a.stsd
+    else:
+        assert a.stsd.count(b"dfLa") == 1 and private[4:] in a.stsd
+    assert len(_cv_frames(out)) == 30                                   # libavformat opens the file, video intact

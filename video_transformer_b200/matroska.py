@@ -192,7 +192,7 @@ def duration_seconds(path: str | Path) -> float:
 # re-wraps Matroska streams into MP4 without decoding.  read_movie() indexes the blocks of every track (offsets, sizes,
 # timestamps, keyframe flags) and builds the MP4 sample description each codec needs from its CodecPrivate, so that
 # isobmff.cut_movie treats the file like any MP4.  Codecs that have an MP4 mapping here: V_VP9, V_AV1,
-# V_MPEG4/ISO/AVC, V_MPEGH/ISO/HEVC, V_MPEG4/ISO/ASP; A_OPUS, A_AAC.  Tracks with other codecs (VP8, Vorbis ...) have
+# V_MPEG4/ISO/AVC, V_MPEGH/ISO/HEVC, V_MPEG4/ISO/ASP, V_VP8; A_OPUS, A_AAC, A_MPEG/L3, A_FLAC.  Tracks with other codecs (Vorbis ...) have
 # no MP4 sample entry and are left out (ffmpeg refuses them in MP4 as well).
 ID_TRACKS = 0x1654AE6B
 ID_TRACK_ENTRY = 0xAE
@@ -232,7 +232,8 @@ def _descr(tag: int, payload: bytes) -> bytes:
 
 def _esds(object_type: int, stream_type: int, dsi: bytes) -> bytes:
     from .isobmff import full_box
-    dcd = bytes([object_type, (stream_type << 2) | 1]) + bytes(3) + struct.pack(">II", 0, 0) + _descr(5, dsi)
+    dcd = bytes([object_type, (stream_type << 2) | 1]) + bytes(3) + struct.pack(">II", 0, 0) + \
+        (_descr(5, dsi) if dsi else b"")         # MP3 has no decoder-specific info
     es = struct.pack(">HB", 0, 0) + _descr(4, dcd) + _descr(6, b"\x02")
     return full_box(b"esds", 0, 0, _descr(3, es))
 
@@ -256,6 +257,9 @@ def _sample_entry(codec_id: str, private: bytes, width: int, height: int, channe
         # vpcC: profile 0, level unknown (10), 8 bit 4:2:0, limited range, unspecified colour; no init data
         vpcc = full_box(b"vpcC", 1, 0, bytes([0, 10, (8 << 4) | (1 << 1) | 0, 2, 2, 2]) + struct.pack(">H", 0))
         return b"vp09", _video_entry(b"vp09", width, height, vpcc)
+    if codec_id == "V_VP8":
+        vpcc = full_box(b"vpcC", 1, 0, bytes([0, 10, (8 << 4) | (1 << 1) | 0, 2, 2, 2]) + struct.pack(">H", 0))
+        return b"vp08", _video_entry(b"vp08", width, height, vpcc)
     if codec_id == "V_AV1" and private:
         return b"av01", _video_entry(b"av01", width, height, box(b"av1C", private))
     if codec_id == "V_MPEG4/ISO/AVC" and private:
@@ -273,6 +277,11 @@ def _sample_entry(codec_id: str, private: bytes, width: int, height: int, channe
         return b"Opus", _audio_entry(b"Opus", ch, 48000, box(b"dOps", dops))
     if codec_id == "A_AAC" and private:
         return b"mp4a", _audio_entry(b"mp4a", channels or 2, int(rate or 48000), _esds(0x40, 5, private))
+    if codec_id == "A_MPEG/L3":                      # MPEG-1/2 layer III: `mp4a` with object type 0x6B, no decoder config
+        return b"mp4a", _audio_entry(b"mp4a", channels or 2, int(rate or 44100), _esds(0x6B, 5, b""))
+    if codec_id == "A_FLAC" and private[:4] == b"fLaC" and len(private) >= 4 + 4 + 34:
+        # dfLa: the metadata blocks of the CodecPrivate (STREAMINFO first) without the `fLaC` marker
+        return b"fLaC", _audio_entry(b"fLaC", channels or 2, int(rate or 48000), full_box(b"dfLa", 0, 0, private[4:]))
     return None
 
 
