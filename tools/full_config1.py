@@ -7,6 +7,10 @@ The source is the bench clip (3840 pictures, I_PCM IDR / GOP 30 + P_Skip, scene 
 tiled into one 24 GB file by isobmff.write_plans (file -> file ranges, nothing held in memory).
 
     gpurun --timeout 900 -- python tools/full_config1.py            (needs ~60 GB of /dev/shm)
+
+`--config5` runs BASELINE.json configs[4]'s product on the same source instead: one picture per second as 768x768
+RGB24 (`output="rgb24", rgb_size=(768, 768), sample_every=30`), hour-long segments (the budget plan of a 10-hour
+file), every picture still decoded and scored.
 """
 import dataclasses
 import json
@@ -54,12 +58,22 @@ def main():
         out["source_bytes"] = os.path.getsize(big)
         out["source_build_s"] = round(time.perf_counter() - t0, 2)
 
-        video_segmenter.configure(target_height=720, frame_buffers=True)
+        config5 = "--config5" in sys.argv
+        if config5:
+            video_segmenter.configure(target_height=720, frame_buffers=True, output="rgb24", rgb_size=(768, 768),
+                                      sample_every=30)
+            out["workload"] = ("configs[4] product on %.1f h of 1920x1080@30 (%d pictures): every picture decoded and "
+                               "scored, one per second converted to 768x768 RGB24, hour-long segments" % (hours, n_total))
+        else:
+            video_segmenter.configure(target_height=720, frame_buffers=True)
         temp = os.path.join(work, "temp")
         t_job = time.perf_counter()
         duration = probe_duration(big)
         t_probe = time.perf_counter() - t_job
         plan = budget_planner.plan_segments_with_budget(duration, {}, 0)
+        if config5:                                  # a 10-hour file plans (3600, 0): use that segment length here
+            plan = type(plan)(3600, 0, int(-(-duration // 3600)), plan.estimated_calls, plan.available_calls,
+                              plan.hard_max_calls, plan.fits_budget)
         manifest = video_segmenter.load_or_create_manifest(video_id="lecture_2h", duration=duration,
                                                            segment_seconds=plan.segment_duration,
                                                            overlap_seconds=plan.overlap, temp_dir=temp)
@@ -77,9 +91,10 @@ def main():
             side = json.loads(open(seg[:-4] + ".json").read())
             frames_bytes = os.path.getsize(seg[:-4] + ".frames")
             assert frames_bytes == side["frames"] * side["frame_bytes"]
-            pictures += side["frames"]
+            pictures += side["last_picture"] - side["first_picture"]
             cuts += len(side["cuts"])
-            segs.append({"id": entry["id"], "seconds": round(dt, 3), "pictures": side["frames"],
+            segs.append({"id": entry["id"], "seconds": round(dt, 3), "pictures": side["last_picture"] - side["first_picture"],
+                         "frames_out": side["frames"],
                          "landing": side["landing"], "recycled": side["landing_recycled"],
                          "mp4_bytes": os.path.getsize(seg),
                          "ms": {k: round(v * 1e3, 1) for k, v in video_segmenter.LAST_TIMINGS.items()}})
