@@ -190,11 +190,12 @@ class SegmentIngestor:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self._pool = None
-        self._copy_threads = int(os.environ.get("VT_INGEST_COPY_THREADS", "1"))   # > 1: split large staging copies (measured: device-sink path 58 -> 104 k pictures/s at 128-picture batches)
+        # Staging copies (files that are not page-locked: small ones, and those over VT_INGEST_DIRECT_MAX_GB) are split
+        # over a few threads: one thread moves 6-8 GB/s out of the page cache, which bounded every pass that is not
+        # D2H-bound at 54 k pictures/s (configs[4] product on a 25 GB source, tools/full_config1.py --config5).  The pool
+        # is created on first use.
+        self._copy_threads = max(1, int(os.environ.get("VT_INGEST_COPY_THREADS", "4")))
         self._copy_pool = None
-        if self._copy_threads > 1:
-            from concurrent.futures import ThreadPoolExecutor
-            self._copy_pool = ThreadPoolExecutor(max_workers=self._copy_threads)
 
     # ------------------------------------------------------------------------------------------------------
     def _register_source(self) -> None:
@@ -236,6 +237,11 @@ class SegmentIngestor:
         self.close()
 
     def close(self) -> None:
+        for name in ("_pool", "_copy_pool"):
+            pool = getattr(self, name, None)
+            if pool is not None:
+                pool.shutdown(wait=False)
+                setattr(self, name, None)
         if self._src_map is not None:
             mm, arr, base = self._src_map
             self._src_map = None
@@ -272,7 +278,10 @@ class SegmentIngestor:
         if slot["bs_host"] is None:
             slot["bs_host"] = torch.empty(self.bs_cap, dtype=torch.uint8, pin_memory=True)
         dst = slot["bs_host"].numpy()
-        if self._copy_pool is not None and nbytes >= (4 << 20):
+        if self._copy_threads > 1 and nbytes >= (4 << 20):
+            if self._copy_pool is None:
+                from concurrent.futures import ThreadPoolExecutor
+                self._copy_pool = ThreadPoolExecutor(max_workers=self._copy_threads)
             # PCM-intra streams are uncompressed (115 KB per 1080p picture on average): one thread copies ~8 GB/s out of
             # the page cache, which would bound the device-sink path; numpy releases the GIL, so split the copy
             n = self._copy_threads
