@@ -438,12 +438,16 @@ def test_matroska_avc_and_opus_tracks_become_avc1_and_opus(tmp_path):
     assert k == last
 
 
-def test_mapped_and_in_kernel_copies_write_the_same_file(tmp_path):
+@pytest.mark.parametrize("parallel", [False, True])
+def test_mapped_and_in_kernel_copies_write_the_same_file(tmp_path, monkeypatch, parallel):
     """The segment MP4 written through the recycled mapping (RAM-backed output directory) is byte-identical to the one
-    copy_file_range writes, including a re-cut into recycled pages and a first-sample replacement."""
+    copy_file_range writes, including a re-cut into recycled pages and a first-sample replacement; `parallel` lowers
+    the size from which a sample range is copied by several threads (gigabyte ranges in production)."""
     import shutil
     import tempfile
     from video_transformer_b200 import landing
+    if parallel:
+        monkeypatch.setattr(isobmff, "_PARALLEL_COPY_MIN", 4096)
     if not landing.on_memory_fs("/dev/shm"):
         pytest.skip("no RAM-backed file system here")
     w, h, n, gop, fps = 96, 80, 90, 10, 30
