@@ -24,6 +24,7 @@ from __future__ import annotations
 
 import argparse
 import json
+from pathlib import Path
 import os
 import shutil
 import statistics
@@ -901,6 +902,8 @@ def _run_config3(args, rank, world, local, dev, barrier, workdir, torch, dist, v
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         dist.all_gather(per, cnt)
+        torch.cuda.synchronize(dev)          # NCCL calls return once enqueued: wait until every rank has arrived, i.e.
+                                             # has written its progress file, before rank 0 merges them
     else:
         per = [cnt]
     if rank == 0:
@@ -912,7 +915,9 @@ def _run_config3(args, rank, world, local, dev, barrier, workdir, torch, dist, v
             "segments_per_sec": segs / float(dt[0]), "videos_per_sec": n_clips / float(dt[0]), "n_gpus": world,
             "seconds": float(dt[0]), "pictures": int(pictures), "segments": int(segs),
             "videos_per_rank": [int(t[2]) for t in per], "failed": int(sum(float(t[3]) for t in per)),
-            "progress_json_processed": len(merged["processed"]), "last_call_ms": last_call,
+            "progress_json_processed": len(merged["processed"]),
+            "progress_json_missing": sorted(set(Path(v).stem for v in vids) - set(merged["processed"])),
+            "last_call_ms": last_call,
             "config": {"workload": "configs[3]: %d synthetic %dx%d@30 clips of %d pictures (I_PCM IDR / GOP 30 + P_Skip), "
                                    "same-height sources are converted NV12 -> YUV420P (not resized) + SAD/hist, one "
                                    "segment each; probe -> budget plan -> manifest -> extract_segment per clip"
