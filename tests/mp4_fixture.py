@@ -310,3 +310,42 @@ def write_mkv(path, *, sps, pps, video_samples, keyframes, width, height, fps=30
     with open(path, "wb") as f:
         f.write(head + _ebml(b"\x18\x53\x80\x67", info + tracks + clusters))
     return {"video_samples": vs, "opus_packets": list(opus_packets or []), "opus_head": opus_head}
+
+
+def write_flv(path, *, sps, pps, video_samples, keyframes, fps=30, aac_frames=None, aac_rate_index=3, cto_ms=None,
+              with_duration=True):
+    """FLV with AVC video (sequence header + one NALU tag per sample, composition offsets cto_ms) and AAC audio
+    (AudioSpecificConfig tag + raw frames of 1024 samples at the rate of aac_rate_index, 3 = 48 kHz), tags interleaved by
+    time, onMetaData first.  Returns the sample byte strings per stream and the AudioSpecificConfig."""
+    vs = [b"".join(struct.pack(">I", len(n)) + n for n in nals) for nals in video_samples]
+    avcc = struct.pack(">BBBBBB", 1, sps[1], sps[2], sps[3], 0xFF, 0xE1) + struct.pack(">H", len(sps)) + sps + \
+        struct.pack(">BH", 1, len(pps)) + pps
+    asc = struct.pack(">H", (2 << 11) | (aac_rate_index << 7) | (2 << 3))        # AAC-LC, rate index, stereo
+    rate = (96000, 88200, 64000, 48000, 44100, 32000, 24000, 22050)[aac_rate_index]
+
+    def tag(kind, ts, data):
+        body = bytes([kind]) + len(data).to_bytes(3, "big") + (ts & 0xFFFFFF).to_bytes(3, "big") + \
+            bytes([(ts >> 24) & 0xFF]) + bytes(3) + data
+        return body + struct.pack(">I", len(body))
+
+    n = len(vs)
+    dur = n / fps
+    meta = b"\x02" + struct.pack(">H", 10) + b"onMetaData" + b"\x08" + struct.pack(">I", 1) + \
+        (struct.pack(">H", 8) + b"duration" + b"\x00" + struct.pack(">d", dur) if with_duration
+         else struct.pack(">H", 5) + b"width" + b"\x00" + struct.pack(">d", 64.0)) + b"\x00\x00\x09"
+    out = b"FLV\x01\x05" + struct.pack(">I", 9) + struct.pack(">I", 0) + tag(18, 0, meta)
+    out += tag(9, 0, bytes([0x17, 0]) + bytes(3) + avcc)
+    events = [(int(round(i * 1000.0 / fps)), 0, i) for i in range(n)]
+    if aac_frames:
+        out += tag(8, 0, bytes([0xAF, 0]) + asc)
+        events += [(int(round(i * 1024 * 1000.0 / rate)), 1, i) for i in range(len(aac_frames))]
+    events.sort()
+    for ts, kind, i in events:
+        if kind == 0:
+            cto = (cto_ms[i] if cto_ms else 0)
+            out += tag(9, ts, bytes([0x17 if keyframes[i] else 0x27, 1]) + cto.to_bytes(3, "big", signed=True) + vs[i])
+        else:
+            out += tag(8, ts, bytes([0xAF, 1]) + aac_frames[i])
+    with open(path, "wb") as f:
+        f.write(out)
+    return {"video_samples": vs, "aac_frames": list(aac_frames or []), "asc": asc, "avcc": avcc}

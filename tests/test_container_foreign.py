@@ -642,3 +642,51 @@ def test_matroska_audio_codecs_map_to_mp4_sample_entries(tmp_path, codec_id, pri
     else:
         assert a.stsd.count(b"dfLa") == 1 and private[4:] in a.stsd
     assert len(_cv_frames(out)) == 30                                   # libavformat opens the file, video intact
+
+
+def test_flv_source_is_stream_copied_into_mp4(tmp_path):
+    """FLV (AVC + AAC): the cut is an MP4 whose `avc1` entry carries the file's AVCDecoderConfigurationRecord verbatim,
+    whose `mp4a` entry carries the AudioSpecificConfig, with sample bytes unchanged, audio pre-roll behind the edit
+    list, and pictures libavcodec decodes to the generator's."""
+    from mp4_fixture import write_flv
+    from oracle import scene_oracle
+    w, h, n, gop, fps = 128, 96, 60, 10, 30
+    sps, pps, samples, keys, luma = _pcm_samples(w, h, n, gop)
+    frames = [bytes([0x21, k & 0xFF]) + bytes((k * 5 + j) & 0xFF for j in range(60 + k % 7)) for k in range(95)]   # ~2 s
+    src = tmp_path / "a.flv"
+    meta = write_flv(src, sps=sps, pps=pps, video_samples=samples, keyframes=keys, fps=fps, aac_frames=frames)
+    assert abs(probe_duration(src) - 2.0) < 1e-3
+    idx = container.probe(src)
+    assert idx is not None and idx.extra["container"] == "flv" and idx.n_frames == n and (idx.width, idx.height) == (w, h)
+    assert len(_cv_frames(src)) == n                          # libavformat reads the fixture as 60 pictures
+    video_segmenter.configure(frame_buffers=False)
+    out = tmp_path / "cut.mp4"
+    assert video_segmenter.extract_segment(src, 0.7, 1.6, out) is True
+    first, last = scene_oracle.frames_for_window(0.7, 1.6, n, fps, 1, np.nonzero(keys)[0], True)
+    cut = isobmff.read_movie(out)
+    assert [t.codec for t in cut.tracks] == [b"avc1", b"mp4a"]
+    v, a = cut.tracks
+    assert meta["avcc"] in v.stsd and meta["asc"] in a.stsd and b"esds" in a.stsd
+    data = out.read_bytes()
+    assert [data[int(o):int(o) + int(z)] for o, z in zip(v.offsets, v.sizes)] == meta["video_samples"][first:last]
+    got = [data[int(o):int(o) + int(z)] for o, z in zip(a.offsets, a.sizes)]
+    k0 = frames.index(got[0])
+    assert got == frames[k0:k0 + len(got)]
+    t_lo = first / fps
+    assert k0 * 1024 / 48000.0 <= t_lo and (k0 + 3) * 1024 / 48000.0 > t_lo - 1e-9      # one frame of AAC pre-roll kept
+    cap = cv2.VideoCapture(str(out), cv2.CAP_FFMPEG)
+    cap.set(cv2.CAP_PROP_CONVERT_RGB, 0)
+    k = first
+    while True:
+        ok, fr = cap.read()
+        if not ok:
+            break
+        assert np.array_equal(np.asarray(fr).reshape(-1)[: w * h].reshape(h, w), luma[k]), k
+        k += 1
+    assert k == last
+    assert abs(probe_duration(out) - (last - first) / fps) < 0.03
+    # truncated download: whatever tags are complete still index; garbage does not raise
+    (tmp_path / "t.flv").write_bytes(src.read_bytes()[: src.stat().st_size * 2 // 3])
+    assert container.probe(tmp_path / "t.flv").n_frames < n
+    (tmp_path / "g.flv").write_bytes(b"FLV\x01\x05\x00\x00\x00\x09" + bytes(range(200)))
+    assert video_segmenter.extract_segment(tmp_path / "g.flv", 0.0, 1.0, tmp_path / "g.mp4") is False

@@ -9,7 +9,7 @@ import time
 import numpy as np
 import pytest
 
-from mp4_fixture import write_av_mp4, write_fragmented_av, write_mkv
+from mp4_fixture import write_av_mp4, write_flv, write_fragmented_av, write_mkv
 from test_container_foreign import _pcm_samples
 from video_transformer_b200 import video_segmenter
 from video_transformer_b200.video_utils import probe_duration
@@ -28,10 +28,13 @@ def _sources(tmp_path):
     mkv = tmp_path / "src.mkv"
     write_mkv(mkv, sps=sps, pps=pps, video_samples=samples, keyframes=keys, width=w, height=h, fps=fps,
               opus_packets=[bytes([i % 251]) * 40 for i in range(70)])
-    return plain, frag, mkv
+    flv = tmp_path / "src.flv"
+    write_flv(flv, sps=sps, pps=pps, video_samples=samples, keyframes=keys, fps=fps,
+              aac_frames=[bytes([0x21, i & 0xFF]) * 30 for i in range(60)])
+    return plain, frag, mkv, flv
 
 
-@pytest.mark.parametrize("which", [0, 1, 2])
+@pytest.mark.parametrize("which", [0, 1, 2, 3])
 def test_mutated_files_never_raise_and_never_stall(tmp_path, which):
     import torch  # noqa: F401  (lazily imported by the cut path; keep it out of the per-call timings)
     src = _sources(tmp_path)[which]

@@ -253,13 +253,13 @@ def test_frames_land_directly_in_the_file_and_landing_files_are_recycled(cuda, t
         shutil.rmtree(out_dir, ignore_errors=True)
 
 
-def test_pixel_pass_reads_a_matroska_source(cuda, oracle_c, tmp_path):
-    """The decode front end indexes slice NALs by file offset, so a PCM-intra AVC track inside Matroska goes through the
-    same GPU pass as one inside MP4: same frame buffers, same SADs."""
+def test_pixel_pass_reads_matroska_and_flv_sources(cuda, oracle_c, tmp_path):
+    """The decode front end indexes slice NALs by file offset, so a PCM-intra AVC track inside Matroska or FLV goes
+    through the same GPU pass as one inside MP4: same frame buffers, same SADs."""
     import struct
     import sys
     sys.path.insert(0, str(__import__("pathlib").Path(__file__).parent))
-    from mp4_fixture import write_mkv
+    from mp4_fixture import write_flv, write_mkv
     w, h, n, gop = 320, 240, 40, 8
     wr = synth.H264PcmWriter(w, h, 30, 1)
     samples, keys = [], []
@@ -272,6 +272,8 @@ def test_pixel_pass_reads_a_matroska_source(cuda, oracle_c, tmp_path):
             keys.append(False)
     mkv = tmp_path / "clip.mkv"
     write_mkv(mkv, sps=wr._sps[4:], pps=wr._pps[4:], video_samples=samples, keyframes=keys, width=w, height=h, fps=30)
+    flv = tmp_path / "clip.flv"
+    write_flv(flv, sps=wr._sps[4:], pps=wr._pps[4:], video_samples=samples, keyframes=keys, fps=30)
     mp4 = tmp_path / "clip.mp4"
     sys.path.insert(0, str(tmp_path))
     from mp4_fixture import write_av_mp4
@@ -281,14 +283,15 @@ def test_pixel_pass_reads_a_matroska_source(cuda, oracle_c, tmp_path):
     try:
         video_segmenter.configure(target_height=120, batch_frames=8, scene_threshold=0.05)
         outs = []
-        for src in (mkv, mp4):
+        for src in (mkv, flv, mp4):
             out = tmp_path / (src.suffix[1:]) / "segment_0000.mp4"
             assert video_segmenter.extract_segment(src, 0.3, 1.2, out) is True
             side = json.loads(out.with_suffix(".json").read_text())
             outs.append((side, np.fromfile(out.with_suffix(".frames"), np.uint8)))
-        assert outs[0][0]["frames"] == outs[1][0]["frames"] > 0
-        assert outs[0][0]["sad"] == outs[1][0]["sad"] and outs[0][0]["cuts"] == outs[1][0]["cuts"]
-        assert np.array_equal(outs[0][1], outs[1][1])
+        for other in outs[1:]:
+            assert outs[0][0]["frames"] == other[0]["frames"] > 0
+            assert outs[0][0]["sad"] == other[0]["sad"] and outs[0][0]["cuts"] == other[0]["cuts"]
+            assert np.array_equal(outs[0][1], other[1])
     finally:
         video_segmenter.configure(**saved)
 

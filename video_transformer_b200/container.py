@@ -307,8 +307,8 @@ def probe_h264(path: Path) -> StreamIndex | None:
 
 def probe(path: Path) -> StreamIndex | None:
     """Index a media file.  Returns None when the file is not a container this layer can cut (ISO-BMFF or
-    Matroska/WebM with a video track that has an MP4 mapping, or a raw Annex-B H.264 stream); `container_duration`
-    still knows AVI."""
+    Matroska/WebM or FLV with a video track that has an MP4 mapping, or a raw Annex-B H.264 stream);
+    `container_duration` still knows AVI."""
     path = Path(path)
     if not path.is_file() or path.stat().st_size < 16:
         return None
@@ -328,6 +328,17 @@ def probe(path: Path) -> StreamIndex | None:
         if idx is not None:
             idx.duration = matroska.duration_seconds(path) or idx.duration
             idx.extra["container"] = "matroska"
+        return idx
+    if head[:3] == b"FLV" and head[3] == 1:
+        from . import flv
+        try:
+            movie = flv.read_movie(path)
+        except (isobmff.BmffError, struct.error, OSError, IndexError, ValueError):
+            return None
+        idx = index_from_movie(movie)
+        if idx is not None:
+            idx.duration = _flv_duration(path) or idx.duration
+            idx.extra["container"] = "flv"
         return idx
     return None
 

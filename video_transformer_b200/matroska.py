@@ -285,6 +285,50 @@ def _sample_entry(codec_id: str, private: bytes, width: int, height: int, channe
     return None
 
 
+def build_track(track_id: int, video: bool, codec: bytes, entry_box: bytes, timescale: int, width: int, height: int,
+                samples: list, default_delta: int = 0):
+    """isobmff.Track from a demuxed sample list [(file offset, size, presentation time, keyframe)] in decode order
+    (shared by the Matroska and FLV readers): decode times are the sorted presentation times, the difference becomes
+    `ctts`, the first decode time an empty edit."""
+    import numpy as np
+    from . import isobmff
+    matrix = struct.pack(">9I", 0x10000, 0, 0, 0, 0x10000, 0, 0, 0, 0x40000000)
+    arr = np.asarray([(o, s, ts) for o, s, ts, _k in samples], np.int64)
+    pts = arr[:, 2]
+    dts = np.sort(pts)                                  # samples are in decode order; sorted pts are valid decode times
+    cts_off = pts - dts
+    if cts_off.min() < 0:                               # keep offsets non-negative (the edit list removes the shift)
+        shift = int(-cts_off.min())
+        cts_off = cts_off + shift
+    else:
+        shift = 0
+    deltas = np.diff(dts)
+    last = default_delta if default_delta else (int(deltas[-1]) if deltas.size else 1)
+    deltas = np.append(deltas, max(last, 1)).astype(np.int64)
+    dts0 = int(dts[0])
+    tkhd = struct.pack(">I", 3) + struct.pack(">IIIII", 0, 0, track_id, 0, 0) + bytes(8) + \
+        struct.pack(">hhhH", 0, 0, 0x0100 if not video else 0, 0) + matrix + \
+        struct.pack(">II", (width << 16) if video else 0, (height << 16) if video else 0)
+    mdhd = struct.pack(">I", 0) + struct.pack(">IIIIHH", 0, 0, timescale, 0, 0x55C4, 0)
+    hdlr = struct.pack(">I", 0) + struct.pack(">I4s12x", 0, b"vide" if video else b"soun") + \
+        (b"VideoHandler\x00" if video else b"SoundHandler\x00")
+    dinf = isobmff.box(b"dinf", isobmff.full_box(b"dref", 0, 0, struct.pack(">I", 1) + isobmff.full_box(b"url ", 0, 1, b"")))
+    mh = isobmff.full_box(b"vmhd", 0, 1, bytes(8)) if video else isobmff.full_box(b"smhd", 0, 0, bytes(4))
+    stsd = isobmff.full_box(b"stsd", 0, 0, struct.pack(">I", 1) + entry_box)
+    key = np.asarray([k for _o, _s, _t, k in samples], bool)
+    reorder = bool((cts_off != cts_off[0]).any())
+    # media time 0 = the first sample's decode time; presentation = (cts - shift) + dts0 on the file's timeline
+    edits = []
+    if dts0 > 0:
+        edits.append((dts0, -1, 0x10000))
+    edits.append((0, shift, 0x10000))
+    return isobmff.Track(track_id, b"vide" if video else b"soun", codec, timescale, int(deltas.sum()),
+                         width if video else 0, height if video else 0, tkhd, mdhd, hdlr, mh + dinf, stsd,
+                         arr[:, 1].astype(np.uint64), arr[:, 0].astype(np.uint64), (dts - dts0).astype(np.int64), deltas,
+                         cts_off.astype(np.int64) if (reorder or shift) else None, key, not bool(key.all()), edits,
+                         (24, len(stsd)))
+
+
 def read_movie(path: str | Path):
     """Index a Matroska/WebM file into an isobmff.Movie (tracks with sample tables and MP4 sample descriptions).
     Raises isobmff.BmffError when the file cannot be read as Matroska or holds no track with an MP4 mapping."""
@@ -400,7 +444,6 @@ def read_movie(path: str | Path):
         rd.close()
     timescale = max(1, int(round(1e9 / scale_ns)))          # ticks per second of the block timestamps (usually 1000)
     movie = isobmff.Movie(path, timescale, int(round(duration)) if duration > 0 else 0)
-    matrix = struct.pack(">9I", 0x10000, 0, 0, 0, 0x10000, 0, 0, 0, 0x40000000)
     next_id = 1
     for num in sorted(tracks):
         t, bl = tracks[num], blocks[num]
@@ -410,41 +453,8 @@ def read_movie(path: str | Path):
         if entry is None:
             continue
         codec, entry_box = entry
-        arr = np.asarray([(o, s, ts) for o, s, ts, _k in bl], np.int64)
-        pts = arr[:, 2]
-        dts = np.sort(pts)                                  # blocks are in decode order; sorted pts are valid decode times
-        cts_off = pts - dts
-        if cts_off.min() < 0:                               # keep offsets non-negative (the edit list removes the shift)
-            shift = int(-cts_off.min())
-            cts_off = cts_off + shift
-        else:
-            shift = 0
-        deltas = np.diff(dts)
-        last = int(round(t["default_ns"] / scale_ns)) if t["default_ns"] else (int(deltas[-1]) if deltas.size else 1)
-        deltas = np.append(deltas, max(last, 1)).astype(np.int64)
-        dts0 = int(dts[0])
-        video = t["type"] == 1
-        tkhd = struct.pack(">I", 3) + struct.pack(">IIIII", 0, 0, next_id, 0, 0) + bytes(8) + \
-            struct.pack(">hhhH", 0, 0, 0x0100 if not video else 0, 0) + matrix + \
-            struct.pack(">II", (t["w"] << 16) if video else 0, (t["h"] << 16) if video else 0)
-        mdhd = struct.pack(">I", 0) + struct.pack(">IIIIHH", 0, 0, timescale, 0, 0x55C4, 0)
-        hdlr = struct.pack(">I", 0) + struct.pack(">I4s12x", 0, b"vide" if video else b"soun") + \
-            (b"VideoHandler\x00" if video else b"SoundHandler\x00")
-        dinf = isobmff.box(b"dinf", isobmff.full_box(b"dref", 0, 0, struct.pack(">I", 1) + isobmff.full_box(b"url ", 0, 1, b"")))
-        mh = isobmff.full_box(b"vmhd", 0, 1, bytes(8)) if video else isobmff.full_box(b"smhd", 0, 0, bytes(4))
-        stsd = isobmff.full_box(b"stsd", 0, 0, struct.pack(">I", 1) + entry_box)
-        key = np.asarray([k for _o, _s, _t, k in bl], bool)
-        reorder = bool((cts_off != cts_off[0]).any())
-        # media time 0 = the first block's decode time; presentation = (cts - shift) + dts0 on the file's timeline
-        edits = []
-        if dts0 > 0:
-            edits.append((dts0, -1, 0x10000))
-        edits.append((0, shift, 0x10000))
-        tr = isobmff.Track(next_id, b"vide" if video else b"soun", codec, timescale, int(deltas.sum()),
-                           t["w"] if video else 0, t["h"] if video else 0, tkhd, mdhd, hdlr, mh + dinf, stsd,
-                           arr[:, 1].astype(np.uint64), arr[:, 0].astype(np.uint64), (dts - dts0).astype(np.int64), deltas,
-                           cts_off.astype(np.int64) if (reorder or shift) else None, key, not bool(key.all()), edits,
-                           (24, len(stsd)))
+        default = int(round(t["default_ns"] / scale_ns)) if t["default_ns"] else 0
+        tr = build_track(next_id, t["type"] == 1, codec, entry_box, timescale, t["w"], t["h"], bl, default)
         movie.tracks.append(tr)
         next_id += 1
     if not movie.tracks:
