@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_int, c_int32, c_size_t, c_uint32, c_uint64, c_void_p
+from ctypes import POINTER, c_char_p, c_int, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VT_LIB") or os.path.join(_HERE, "libvtseg.so")   # VT_LIB: measurement builds only

@@ -17,7 +17,6 @@ PyTorch only owns memory, streams and events here.
 """
 from __future__ import annotations
 
-import ctypes
 import os
 from ctypes import c_void_p
 from dataclasses import dataclass, field

@@ -15,7 +15,6 @@ Samples are clipped to [1, 255] so that no emulation-prevention byte is ever nee
 """
 from __future__ import annotations
 
-import struct
 
 import numpy as np
 
