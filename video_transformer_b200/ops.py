@@ -1,7 +1,6 @@
 """Tensor-level wrappers over the C ABI.  torch is only the owner of device memory and streams here."""
 from __future__ import annotations
 
-import ctypes
 from ctypes import byref, c_int, c_void_p
 
 import numpy as np
