@@ -42,6 +42,7 @@ class _Slot:
 
     def __init__(self, path: Path, nbytes: int, register: bool = True):
         self.path, self.nbytes = path, nbytes
+        self.pid = os.getpid()           # a forked child inherits this object but does not own the file or the pinning
         self.fd = os.open(path, os.O_RDWR | os.O_CREAT | os.O_EXCL, 0o644)
         try:
             if register:
@@ -73,6 +74,10 @@ class _Slot:
             return False
 
     def destroy(self) -> None:
+        if self.pid != os.getpid():      # inherited through fork(): the parent unregisters and unlinks
+            self.registered = False
+            self.tensor = self.array = None
+            return
         if self.registered:
             try:
                 lib().vt_host_unregister(ctypes.c_void_p(self.base))
