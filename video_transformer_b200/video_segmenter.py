@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import json
 import logging
+import threading
 from dataclasses import dataclass
 from datetime import datetime, timezone
 from pathlib import Path
@@ -157,11 +158,15 @@ def extract_segment(input_path: str | Path, start: float, end: float, output_pat
         return False
     src, dst = Path(input_path), Path(output_path)
     dst.parent.mkdir(parents=True, exist_ok=True)
-    try:
-        ok = _cut(src, start, end, dst, stream_copy)
-    except Exception as exc:  # noqa: BLE001 - same contract as the reference: failures become False
-        log.warning("event=segment_cut_failed input=%s start=%.3f end=%.3f error=%s", src, start, end, exc)
-        ok = False
+    # The reference is single-threaded (content_analyzer.py:870, pipeline.py:376); the batch scheduler here ingests
+    # video i+1 on a worker thread while the caller works on video i and may cut segments itself.  The engine, index
+    # cache and timing record are per process, so calls take turns.
+    with _CALL_LOCK:
+        try:
+            ok = _cut(src, start, end, dst, stream_copy)
+        except Exception as exc:  # noqa: BLE001 - same contract as the reference: failures become False
+            log.warning("event=segment_cut_failed input=%s start=%.3f end=%.3f error=%s", src, start, end, exc)
+            ok = False
     if not ok:
         for p in (dst, _frames_path(dst), _sidecar_path(dst)):
             if p.exists():
@@ -178,6 +183,7 @@ def _sidecar_path(mp4: Path) -> Path:
     return mp4.with_suffix(".json")
 
 
+_CALL_LOCK = threading.RLock()
 _INDEX_CACHE: dict = {}
 _ENGINE_CACHE: dict = {}
 LAST_TIMINGS: dict = {}          # seconds spent in the stages of the most recent extract_segment call (diagnostics)
