@@ -45,6 +45,7 @@ struct vt_rgb_plan {
     uint32_t *lhcf, *chcf;                    // dw x fhp, cdw x fhp
     int nrl_max, nrc_max;
     size_t fused_smem;
+    int32_t *ttab;                            // fused kernel: per tile row, [RGB_TH][VTP] coefficients then [RGB_TH][VTP] offsets
 };
 
 namespace vt {
@@ -274,6 +275,7 @@ struct RgbTileArgs {
     const int32_t *lhp, *chp, *lvp, *cvp;
     const int16_t *lvc, *cvc;                 // vertical banks padded to LVT / CVT
     int nrl_max, nrc_max;
+    const int32_t *ttab;                      // per tile row: [RGB_TH][VTP] vertical coefficients, then [RGB_TH][VTP] offsets
     uint8_t *dst;
     unsigned long long dst_fs;
     RgbConst k;
@@ -305,16 +307,16 @@ rgb_tile_kernel(const __grid_constant__ RgbTileArgs a) {
     const int nrl = lrow1 - lrow0 + 1, nrc = crow1 - crow0 + 1;
     const uint8_t *frame = a.src + (size_t)blockIdx.z * a.src_fs;
     const int pw = a.pitch >> 2, wl = pw - 1;
-    // ---- per-tile tables: coefficient and shared-memory offset of every (output row, tap)
-    for (int i = threadIdx.x; i < (y1 - y0) * VT; i += RGB_THREADS) {
-        const int yr = i / VT, j = i - yr * VT, y = y0 + yr, t = yr * VTP + j;
-        if (j < LVT) {
-            tcoef[t] = __ldg(a.lvc + y * LVT + j);
-            toff[t] = (min(__ldg(a.lvp + y) + j, a.sh - 1) - lrow0) * (RGB_TW * 4);
-        } else {
-            tcoef[t] = __ldg(a.cvc + y * CVT + (j - LVT));
-            toff[t] = (min(__ldg(a.cvp + y) + (j - LVT), a.csh - 1) - crow0) * (RGB_TW * 4);
-        }
+    // ---- per-tile tables: coefficient and shared-memory offset of every (output row, tap).  They depend on the tile ROW
+    // only, so the host tabulated them once per plan (vt_rgb_plan_create); a block copies its 2 x RGB_TH x VTP words
+    // with 128-bit loads (the in-kernel build -- an integer division and two dependent loads per entry -- was a sixth
+    // of the kernel's time)
+    {
+        constexpr int N4 = 2 * RGB_TH * VTP / 4;
+        const int4 *tsrc = reinterpret_cast<const int4 *>(a.ttab) + (size_t)blockIdx.y * N4;
+        int4 *tdst = reinterpret_cast<int4 *>(tcoef);
+#pragma unroll
+        for (int i = threadIdx.x; i < N4; i += RGB_THREADS) tdst[i] = __ldg(tsrc + i);
     }
     // ---- phase 1, luma: thread = (column, row group); the common case addresses its words with immediates
     {
@@ -578,6 +580,27 @@ extern "C" int vt_rgb_plan_create(int sw, int sh, int dw, int dh, int flags, vt_
                 p->nrl_max = std::max(p->nrl_max, std::min(lvp[y1 - 1] + p->vtl - 1, sh - 1) - lvp[y0] + 1);
                 p->nrc_max = std::max(p->nrc_max, std::min(cvp[y1 - 1] + p->vtc - 1, p->csh - 1) - cvp[y0] + 1);
             }
+            if (rc == VT_OK) {                       // the tile rows' tables (same values the kernel used to compute)
+                const int vt_ = p->vtl + p->vtc, vtp = (vt_ + 3) & ~3, n_rows = (dh + vt::RGB_TH - 1) / vt::RGB_TH;
+                const auto lc = padded(vl, dh, p->lvt, p->vtl), cc = padded(vc, dh, p->cvt, p->vtc);
+                std::vector<int32_t> tab((size_t)n_rows * 2 * vt::RGB_TH * vtp, 0);
+                for (int ty = 0; ty < n_rows; ty++) {
+                    const int y0 = ty * vt::RGB_TH, y1 = std::min(dh, y0 + vt::RGB_TH);
+                    int32_t *tc = &tab[(size_t)ty * 2 * vt::RGB_TH * vtp], *to = tc + vt::RGB_TH * vtp;
+                    for (int y = y0; y < y1; y++)
+                        for (int j = 0; j < vt_; j++) {
+                            const int t = (y - y0) * vtp + j;
+                            if (j < p->vtl) {
+                                tc[t] = lc[(size_t)y * p->vtl + j];
+                                to[t] = (std::min(lvp[y] + j, sh - 1) - lvp[y0]) * (vt::RGB_TW * 4);
+                            } else {
+                                tc[t] = cc[(size_t)y * p->vtc + (j - p->vtl)];
+                                to[t] = (std::min(cvp[y] + (j - p->vtl), p->csh - 1) - cvp[y0]) * (vt::RGB_TW * 4);
+                            }
+                        }
+                }
+                rc = upload(tab.data(), tab.size() * 4, (void **)&p->ttab);
+            }
             p->fused_smem = ((size_t)p->nrl_max * vt::RGB_TW + (size_t)p->nrc_max * vt::RGB_TW +
                              2 * (size_t)vt::RGB_TH * ((p->vtl + p->vtc + 3) & ~3)) * sizeof(int);
             if (p->fused_smem > 96 * 1024 || p->nrl_max <= 0 || p->nrc_max <= 0) p->fhp = 0;   // very steep ratios: three-launch path
@@ -604,7 +627,7 @@ extern "C" void vt_rgb_plan_destroy(vt_rgb_plan *p) {
     cudaFree(p->lhp); cudaFree(p->lvp); cudaFree(p->chp); cudaFree(p->cvp);
     cudaFree(p->my); cudaFree(p->mu); cudaFree(p->mv);
     cudaFree(p->lhc2); cudaFree(p->chc2); cudaFree(p->lvc2); cudaFree(p->cvc2);
-    cudaFree(p->lhcf); cudaFree(p->chcf);
+    cudaFree(p->lhcf); cudaFree(p->chcf); cudaFree(p->ttab);
     delete p;
 }
 
@@ -633,7 +656,7 @@ extern "C" int vt_scale_nv12_to_rgb24(const vt_rgb_plan *p, const uint8_t *src, 
         a.src = src; a.pitch = pitch; a.src_fs = src_fs;
         a.sw = p->sw; a.sh = p->sh; a.csh = p->csh; a.dw = p->dw; a.dh = p->dh; a.cdw = p->cdw;
         a.lhc = p->lhcf; a.chc = p->chcf; a.lhp = p->lhp; a.chp = p->chp; a.lvp = p->lvp; a.cvp = p->cvp;
-        a.lvc = p->lvc2; a.cvc = p->cvc2; a.nrl_max = p->nrl_max; a.nrc_max = p->nrc_max;
+        a.lvc = p->lvc2; a.cvc = p->cvc2; a.nrl_max = p->nrl_max; a.nrc_max = p->nrc_max; a.ttab = p->ttab;
         a.dst = dst; a.dst_fs = dst_fs; a.k = k;
         const dim3 grid((p->dw + vt::RGB_TW - 1) / vt::RGB_TW, (p->dh + vt::RGB_TH - 1) / vt::RGB_TH, 1);
         for (int f0 = 0; f0 < n_frames; f0 += 65535) {
